@@ -1,0 +1,93 @@
+"""The oracle against the golden vectors produced by the UNMODIFIED reference
+(tools/make_golden.py).  uint8 outputs must be bit-exact; this is what pins the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import frames
+from oracle import colorimetry as C
+from oracle import mammals as M
+from oracle import mstpp, uv
+
+
+def _frames(meta):
+    h, w = meta["small_hw"]
+    return dict(frames.parity_set(h, w))
+
+
+def test_versions_match_fixture(golden_meta):
+    import cv2
+    v = golden_meta["versions"]
+    assert (np.__version__, cv2.__version__) == (v["numpy"], v["cv2"]), \
+        "fixtures were generated with other library versions: regenerate with tools/make_golden.py"
+
+
+def test_mammals_bit_exact(golden, golden_meta):
+    fr = _frames(golden_meta)
+    g = golden("mammals")
+    assert len(g) >= 19 * 3
+    for key, ref in g.items():
+        sp, name = key.split("/")
+        base, out = M.mammal_visualize(fr[name], sp)
+        assert base is fr[name]
+        assert out.dtype == np.uint8 and np.array_equal(out, ref), key
+
+
+def test_cat_bit_exact(golden, golden_meta):
+    fr = _frames(golden_meta)
+    g = golden("cat")
+    for name, f in fr.items():
+        human, cat = M.cat_visualize(f)
+        assert np.array_equal(human, g[f"human/{name}"]), name
+        assert np.array_equal(cat, g[f"cat/{name}"]), name
+
+
+def test_honeybee_bit_exact(golden, golden_meta):
+    fr = _frames(golden_meta)
+    Mx = np.array([[0.9, 0.1, 0.0], [0.0, 0.3, 0.8], [0.5, 0.5, 0.1]], np.float32)
+    for key, ref in golden("honeybee").items():
+        mode, adapt, name = key.split("/")
+        base, out = uv.honeybee_visualize(fr[name], mapping_mode=mode, adaptation=adapt, custom_matrix=Mx)
+        assert base is fr[name]
+        assert np.array_equal(out, ref), key
+
+
+def test_intermediates(golden, golden_meta):
+    h, w = golden_meta["small_hw"]
+    f = frames.natural(h, w)
+    g = golden("intermediates")
+    lin = C.decode_srgb(C.normalize_frame(f))
+    lms = (lin.reshape(-1, 3) @ C.RGB_TO_LMS.T).reshape(lin.shape)
+    np.testing.assert_array_equal(lms, g["lms"])
+    dog = M.dichromat_linear(f, M.RECIPES["dog"])
+    np.testing.assert_array_equal(dog, g["dog_blur"])
+    U, B, G = uv.honeybee_receptors(f)
+    np.testing.assert_array_equal(np.stack([U, B, G], 2).astype(np.float32), g["bee_ubg"])
+    np.testing.assert_array_equal(uv.analytic_hsi(uv.to_float01(f))[::9, ::16], g["hsi_px"])
+
+
+@pytest.mark.parametrize("hw", [(270, 480), (1080, 1920)])
+def test_large_frame_hashes(golden_meta, hw):
+    H, W = hw
+    ref = golden_meta["hashes"][f"{H}x{W}"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+    f = frames.noise(H, W, 0)
+    assert sha(f) == ref["input"]
+    assert sha(M.mammal_visualize(f, "dog")[1]) == ref["dog"]
+    human, cat = M.cat_visualize(f)
+    assert sha(human) == ref["cat_human"] and sha(cat) == ref["cat"]
+    if H <= 270:   # the 1080p honeybee oracle needs ~1 GB and several seconds; hash pinned at 270p
+        assert sha(uv.honeybee_visualize(f)[1]) == ref["honeybee"]
+
+
+def test_mstpp_matches_reference_module(golden, golden_meta):
+    sd = mstpp.make_weights(0)
+    assert len(sd) == 227 and sum(v.numel() for v in sd.values()) == 1619625
+    x = torch.rand(1, 3, 42, 52, generator=torch.Generator().manual_seed(1))
+    y = mstpp.forward(x, sd).numpy()
+    ref = golden("mstpp")["y"]
+    assert y.shape == ref.shape == (1, 31, 42, 52)
+    assert np.abs(y - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert abs(float(y.std()) - golden_meta["mstpp"]["std"]) < 1e-5
