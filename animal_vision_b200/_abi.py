@@ -1,0 +1,73 @@
+"""ctypes binding of libavb200.so (include/avb200.h).
+
+The library is built in-tree by `animal_vision_b200._build` (nvcc, sm_100a).  There is NO CPU
+fallback: if the library cannot be built / loaded, or no CUDA device is present, every compute
+entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+
+AVB_NORM_DIV255 = 0
+AVB_NORM_AUTO = 1
+AVB_ENC_TABLE_MAX = 2048
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/avb200.h declares
+SIGNATURES = {
+    "avb_version": (_i, []),
+    "avb_last_error": (C.c_char_p, []),
+    "avb_build_encode_table": (_i, [_p, _p, _i]),
+    "avb_colorimetric_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "avb_dichromat_blur_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _i, _p, _p]),
+    "avb_cat_u8": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
+}
+
+
+class AvbError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if the sources changed) and type every exported symbol."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if build_if_missing and not _build.is_current():
+            try:
+                _build.build()
+            except Exception as e:  # a prebuilt .so that travelled with the snapshot is still usable
+                if not os.path.exists(path):
+                    raise AvbError(f"libavb200.so is missing and could not be built: {e}") from e
+        if not os.path.exists(path):
+            raise AvbError(f"{path} not found: run `python -m animal_vision_b200._build` (no CPU fallback exists)")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().avb_last_error().decode(errors="replace")
+        raise AvbError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,91 @@
+// Shared host/device helpers for libavb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/avb200.h"
+
+namespace avb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define AVB_CUDA_OK(expr)                                     \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return avb::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define AVB_REQUIRE(cond, msg)                  \
+    do {                                        \
+        if (!(cond)) {                          \
+            avb::set_error("%s: %s", __func__, msg); \
+            return AVB_E_ARG;                   \
+        }                                       \
+    } while (0)
+
+int sm_count();  // multiprocessors of the current device (cached)
+
+// ---------------------------------------------------------------- frame addressing
+struct FrameIO {
+    const uint8_t *in;
+    uint8_t *out;
+    int64_t in_fs, in_rs, out_fs, out_rs;  // byte strides
+    int n, H, W;
+};
+
+struct Mat3 {
+    float m[9];
+};
+
+// ---------------------------------------------------------------- encode table
+// Layout of the table built by avb_build_encode_table:
+//   [0] key_min   (float bits >> shift of the first bucket)
+//   [1] shift     (23 - mantissa bits kept)
+//   [2] n_buckets
+//   [3] reserved
+//   [4 .. 4+n_buckets) entries: (threshold_low_bits << 8) | byte_at_bucket_start
+// A bucket is the set of floats sharing (bits >> shift); it contains at most one quantisation
+// threshold, stored as its low `shift` bits (or 1<<shift when the bucket has none).
+constexpr int ENC_HEADER = 4;
+
+struct EncTable {            // view over shared memory
+    const uint32_t *e;       // entries
+    uint32_t lo_bits;        // key_min << shift : everything below encodes to byte 0
+    uint32_t shift;
+    uint32_t mask;
+};
+
+__device__ __forceinline__ EncTable enc_view(const uint32_t *smem_table) {
+    EncTable t;
+    t.shift = smem_table[1];
+    t.lo_bits = smem_table[0] << t.shift;
+    t.mask = (1u << t.shift) - 1u;
+    t.e = smem_table + ENC_HEADER;
+    return t;
+}
+
+// clip(x,0,1) -> OETF -> *255+0.5 -> truncate, as one table lookup.  NaN encodes to 0.
+__device__ __forceinline__ uint32_t encode_u8(const EncTable &t, float x) {
+    uint32_t b = __float_as_uint(__saturatef(x));
+    b = max(b, t.lo_bits);
+    uint32_t ent = t.e[(b - t.lo_bits) >> t.shift];
+    return (ent & 0xffu) + (((b & t.mask) >= (ent >> 8)) ? 1u : 0u);
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // cv::borderInterpolate(BORDER_REFLECT_101); loops only for overshoots beyond one period
+    if (n == 1) return 0;
+    while ((unsigned)i >= (unsigned)n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// cooperative copy of a small global table into shared memory
+__device__ __forceinline__ void copy_to_smem(uint32_t *dst, const uint32_t *src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+}  // namespace avb

@@ -1,0 +1,225 @@
+// K1: fused per-pixel colorimetric kernel -- uint8 sRGB -> LUT decode -> 3x3 -> [row gain on
+// channel 2] -> clip -> sRGB encode -> uint8.  HBM bound: 3 B/px in, 3 B/px out, nothing else.
+//
+// Packed RGB does not divide into 16-byte vectors (16 B = 5 1/3 px), so a warp moves 1536 B =
+// 512 px at a time: three fully coalesced 128-bit loads per lane into a per-warp shared-memory
+// slab, then each lane owns 48 contiguous bytes (16 whole pixels) of the slab, transforms them in
+// registers and the slab goes back out with three coalesced 128-bit stores.
+#include "avb_common.cuh"
+
+namespace avb {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_UNIT = 1536;          // bytes per warp iteration
+constexpr int K1_ENC_SMEM = AVB_ENC_TABLE_MAX;
+
+struct K1Params {
+    FrameIO io;
+    Mat3 M;
+    const float *lut;
+    const uint32_t *enc;
+    const float *row_gain;   // nullptr or [H]
+    uint32_t *flags;
+    int fixup;
+    int units_per_frame;     // ceil(3*W*H / 1536)
+};
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[12], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 0xffu; }
+
+template <bool GAIN>
+__device__ __forceinline__ void transform16(uint32_t (&w)[12], const float *lut, const EncTable &enc, const float (&m)[9],
+                                            const float *row_gain, int64_t first_px, int W) {
+    uint32_t o[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = 0;
+    int y = 0, xr = 0;
+    if (GAIN) {
+        y = (int)(first_px / W);
+        xr = (int)(first_px - (int64_t)y * W);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float l0 = lut[byte_of(w, 3 * j)], l1 = lut[byte_of(w, 3 * j + 1)], l2 = lut[byte_of(w, 3 * j + 2)];
+        const float r0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
+        const float r1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
+        float r2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+        if (GAIN) {
+            // animal_utils.py:254: out[...,2] = clip(out[...,2] * w, 0, 1)
+            const int yy = y + ((xr + j >= W) ? 1 : 0);   // contiguous path requires W >= 16: one wrap at most
+            r2 = __fmul_rn(r2, __ldg(row_gain + yy));
+        }
+        const uint32_t e0 = encode_u8(enc, r0), e1 = encode_u8(enc, r1), e2 = encode_u8(enc, r2);
+        o[(3 * j) >> 2] |= e0 << (8 * ((3 * j) & 3));
+        o[(3 * j + 1) >> 2] |= e1 << (8 * ((3 * j + 1) & 3));
+        o[(3 * j + 2) >> 2] |= e2 << (8 * ((3 * j + 2) & 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = o[i];
+}
+
+// Fast path: frames are contiguous (row stride == 3*W) and 16-byte aligned.
+template <bool GAIN>
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_contig_kernel(const __grid_constant__ K1Params p) {
+    __shared__ __align__(16) uint4 slab[K1_WARPS][96];
+    __shared__ float lut_s[256];
+    __shared__ uint32_t enc_s[K1_ENC_SMEM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256; i += K1_THREADS) lut_s[i] = __ldg(p.lut + i);
+    copy_to_smem(enc_s, p.enc, min(K1_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+    float m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = p.M.m[i];
+
+    const int64_t frame_bytes = 3LL * p.io.W * p.io.H;
+    const int64_t total_units = (int64_t)p.units_per_frame * p.io.n;
+    uint32_t seen = 0;
+    int flagged_frame = -1;
+    for (int64_t u = (int64_t)blockIdx.x * K1_WARPS + warp; u < total_units; u += (int64_t)gridDim.x * K1_WARPS) {
+        const int frame = (int)(u / p.units_per_frame);
+        if (p.fixup && p.flags[frame] != 0) continue;
+        if (frame != flagged_frame) {   // flush the per-frame "byte >= 2" accumulator
+            if (p.flags && !p.fixup && flagged_frame >= 0 && __any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0)
+                p.flags[flagged_frame] = 1u;
+            seen = 0;
+            flagged_frame = frame;
+        }
+        const int64_t off = (u - (int64_t)frame * p.units_per_frame) * K1_UNIT;
+        const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs + off;
+        uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs + off;
+        const int64_t remain = frame_bytes - off;              // > 0
+        if (remain >= K1_UNIT) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) slab[warp][k * 32 + lane] = __ldcs(reinterpret_cast<const uint4 *>(src) + k * 32 + lane);
+            __syncwarp();
+            uint32_t w[12];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 t = slab[warp][lane * 3 + k];
+                w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) seen |= w[i];
+            transform16<GAIN>(w, lut_s, enc, m, p.row_gain, (off + lane * 48) / 3, p.io.W);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) slab[warp][lane * 3 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) __stcs(reinterpret_cast<uint4 *>(dst) + k * 32 + lane, slab[warp][k * 32 + lane]);
+            __syncwarp();
+        } else {
+            // frame tail (< 1536 B): whole pixels, one per lane-iteration
+            const int npx = (int)(remain / 3);
+            const int64_t px0 = off / 3;
+            for (int j = lane; j < npx; j += 32) {
+                const uint32_t b0 = src[3 * j], b1 = src[3 * j + 1], b2 = src[3 * j + 2];
+                seen |= b0 | b1 | b2;
+                const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
+                const float r0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
+                const float r1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
+                float r2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+                if (GAIN) r2 = __fmul_rn(r2, __ldg(p.row_gain + (int)((px0 + j) / p.io.W)));
+                dst[3 * j] = (uint8_t)encode_u8(enc, r0);
+                dst[3 * j + 1] = (uint8_t)encode_u8(enc, r1);
+                dst[3 * j + 2] = (uint8_t)encode_u8(enc, r2);
+            }
+        }
+    }
+    if (p.flags && !p.fixup && flagged_frame >= 0 && __any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0)
+        p.flags[flagged_frame] = 1u;
+}
+
+// Generic path: arbitrary strides / alignment, one pixel per thread-iteration.
+template <bool GAIN>
+__global__ void __launch_bounds__(K1_THREADS) k1_strided_kernel(const __grid_constant__ K1Params p) {
+    __shared__ float lut_s[256];
+    __shared__ uint32_t enc_s[K1_ENC_SMEM];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += K1_THREADS) lut_s[i] = __ldg(p.lut + i);
+    copy_to_smem(enc_s, p.enc, min(K1_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+    const int frame = blockIdx.z;
+    if (p.fixup && p.flags[frame] != 0) return;
+    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
+    uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs;
+    uint32_t seen = 0;
+    for (int y = blockIdx.y; y < p.io.H; y += gridDim.y) {
+        const float g = GAIN ? __ldg(p.row_gain + y) : 1.f;
+        for (int x = blockIdx.x * K1_THREADS + tid; x < p.io.W; x += gridDim.x * K1_THREADS) {
+            const uint8_t *q = src + (int64_t)y * p.io.in_rs + 3 * x;
+            const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
+            seen |= b0 | b1 | b2;
+            const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
+            const float r0 = p.M.m[0] * l0 + p.M.m[1] * l1 + p.M.m[2] * l2;
+            const float r1 = p.M.m[3] * l0 + p.M.m[4] * l1 + p.M.m[5] * l2;
+            float r2 = p.M.m[6] * l0 + p.M.m[7] * l1 + p.M.m[8] * l2;
+            if (GAIN) r2 = __fmul_rn(r2, g);
+            uint8_t *o = dst + (int64_t)y * p.io.out_rs + 3 * x;
+            o[0] = (uint8_t)encode_u8(enc, r0);
+            o[1] = (uint8_t)encode_u8(enc, r1);
+            o[2] = (uint8_t)encode_u8(enc, r2);
+        }
+    }
+    if (p.flags && !p.fixup && __any_sync(0xffffffffu, (seen & 0xfeu) != 0) && (tid & 31) == 0) p.flags[frame] = 1u;
+}
+
+static int launch_k1(const K1Params &p, cudaStream_t st) {
+    const FrameIO &io = p.io;
+    const bool contig = io.W >= 16 && io.in_rs == 3LL * io.W && io.out_rs == 3LL * io.W && (io.in_fs & 15) == 0 && (io.out_fs & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(io.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(io.out) & 15) == 0;
+    if (contig) {
+        const int64_t total_units = (int64_t)p.units_per_frame * io.n;
+        int64_t blocks = (total_units + K1_WARPS - 1) / K1_WARPS;
+        const int64_t cap = (int64_t)sm_count() * 4 * 4;   // 4 resident CTAs per SM, a few waves each
+        if (blocks > cap) blocks = cap;
+        if (p.row_gain) k1_contig_kernel<true><<<(unsigned)blocks, K1_THREADS, 0, st>>>(p);
+        else k1_contig_kernel<false><<<(unsigned)blocks, K1_THREADS, 0, st>>>(p);
+    } else {
+        dim3 grid((io.W + K1_THREADS - 1) / K1_THREADS, io.H < 1024 ? io.H : 1024, io.n);
+        if (p.row_gain) k1_strided_kernel<true><<<grid, K1_THREADS, 0, st>>>(p);
+        else k1_strided_kernel<false><<<grid, K1_THREADS, 0, st>>>(p);
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+}  // namespace avb
+
+using namespace avb;
+
+extern "C" int avb_colorimetric_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                                   int64_t in_frame_stride, int64_t in_row_stride,
+                                   int64_t out_frame_stride, int64_t out_row_stride,
+                                   const float *dec_dev, const float *dec_raw_dev, const uint32_t *enc_dev,
+                                   const float *m_host, const float *row_gain_dev,
+                                   int norm_mode, uint32_t *flags_dev, avb_stream_t stream) {
+    K1Params p{};
+    p.io = FrameIO{in, out, in_frame_stride, in_row_stride, out_frame_stride, out_row_stride, n, H, W};
+    AVB_REQUIRE(in && out, "null frame pointer");
+    AVB_REQUIRE(n > 0 && H > 0 && W > 0, "bad frame geometry");
+    AVB_REQUIRE(in_row_stride >= 3LL * W && out_row_stride >= 3LL * W, "row stride smaller than 3*W");
+    AVB_REQUIRE(dec_dev && enc_dev && m_host, "null table pointer");
+    AVB_REQUIRE(norm_mode == AVB_NORM_DIV255 || (norm_mode == AVB_NORM_AUTO && dec_raw_dev && flags_dev),
+                "AVB_NORM_AUTO needs dec_raw_dev and flags_dev");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < 9; ++i) p.M.m[i] = m_host[i];
+    p.lut = dec_dev;
+    p.enc = enc_dev;
+    p.row_gain = row_gain_dev;
+    p.units_per_frame = (int)((3LL * W * H + K1_UNIT - 1) / K1_UNIT);
+    if (norm_mode == AVB_NORM_AUTO) {
+        AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
+        p.flags = flags_dev;
+    }
+    p.fixup = 0;
+    if (int e = launch_k1(p, st)) return e;
+    if (norm_mode == AVB_NORM_AUTO) {
+        p.fixup = 1;
+        p.lut = dec_raw_dev;
+        if (int e = launch_k1(p, st)) return e;
+    }
+    return AVB_OK;
+}

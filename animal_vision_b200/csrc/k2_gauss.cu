@@ -1,0 +1,473 @@
+// K2: fused  producer -> separable Gaussian (REFLECT_101) -> clip -> sRGB encode -> uint8.
+//
+// One CTA owns a vertical strip of TW pixels and streams down a segment of rows in blocks of RB=8
+// rows.  Per block:  produce (decode + 3x3 into a planar fp32 staging tile with an R-pixel x halo)
+// -> horizontal pass -> vertical pass over a window of horizontally-blurred rows that each thread
+// keeps in REGISTERS for the whole segment (no ring buffer, 8 new values per block) -> encode -> packed uint8 staging -> 128-bit stores.  The fp32 intermediate never leaves
+// shared memory: HBM sees the uint8 frame once in and once out (6 B/px).
+//
+// Both passes are register blocked: a thread produces 8 consecutive outputs from an (8+2R)-wide
+// window held in registers, so shared-memory traffic is (8+2R)/8 loads per 2R+1 FMAs and the
+// kernel is bound by the FP32 FMA pipe, not by LDS.  Taps live in the kernel-parameter constant
+// bank and feed FFMA directly.
+//
+// The producer is a policy: DogProducer (LUT decode + 3x3; animals/dog.py:35-48) or CatProducer
+// (binocular wide-FOV gather + blend + pow decode + 3x3; animals/cat_widevision_utils.py:46-99,
+// animals/cat.py:95-101).
+#include "avb_common.cuh"
+
+namespace avb {
+
+constexpr int G_TW = 64;        // strip width in pixels
+constexpr int G_RB = 8;         // rows per block
+constexpr int G_THREADS = 192;  // 6 warps: (channel, half-strip)
+constexpr int G_MAX_TAPS = 33;
+constexpr int G_ENC_SMEM = AVB_ENC_TABLE_MAX;  // uint32 words reserved for the encode table
+
+template <int R>
+struct GaussCfg {
+    static constexpr int LAG = (2 * R + G_RB - 1) / G_RB;             // input blocks an output block waits for
+    static constexpr int VW = (LAG + 1) * G_RB;                       // vertical register window (rows)
+    static constexpr int WIN = G_RB + 2 * R;                          // rows/cols actually used by 8 outputs
+    static constexpr int NW4 = (WIN + 3) / 4;                         // float4 loads per horizontal window
+    static constexpr int SP0 = (G_TW - 8) + 4 * NW4;
+    static constexpr int S_PITCH = (SP0 % 8 == 4) ? SP0 : SP0 + 4;    // odd multiple of 16 B: conflict-free LDS.128
+    static constexpr int IN_W = G_TW + 2 * R;                         // produced columns per row
+    static constexpr int X_PITCH = G_TW + 4;                          // same trick for the STS.128 of the H pass
+    static constexpr int S_FLOATS = 3 * G_RB * S_PITCH;
+    static constexpr int X_FLOATS = 3 * G_RB * X_PITCH;
+    static constexpr int STAGE_BYTES = G_RB * G_TW * 3;
+};
+
+struct GaussCommon {
+    FrameIO io;
+    float taps[G_MAX_TAPS];
+    const uint32_t *enc;   // encode table (device)
+    uint32_t *flags;       // per-frame "some byte >= 2" (AVB_NORM_AUTO) or nullptr
+    int seg_h;             // rows per segment (multiple of G_RB)
+    int fixup;             // 1: second launch, only frames whose flag stayed 0 are (re)processed
+};
+
+// ------------------------------------------------------------------------------------ producers
+struct DogProducer {
+    struct Params {
+        Mat3 M;
+        const float *lut;  // 256-entry decode LUT (device)
+    };
+    static constexpr int SMEM_FLOATS = 256;
+    const float *lut_s;
+    const uint8_t *src;
+    int64_t rs;
+    float m[9];
+    uint32_t seen;
+
+    __device__ __forceinline__ void init(const Params &pp, float *smem, const uint8_t *frame, int64_t row_stride,
+                                         int /*H*/, int /*W*/, int /*frame_idx*/) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = __ldg(pp.lut + i);
+        lut_s = smem;
+        src = frame;
+        rs = row_stride;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = pp.M.m[i];
+        seen = 0;
+    }
+    __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
+        const uint8_t *q = src + (int64_t)y * rs + 3 * x;
+        const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
+        seen |= b0 | b1 | b2;
+        const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
+        o0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
+        o1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
+        o2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+    }
+};
+
+struct CatProducer {
+    struct Params {
+        Mat3 M;             // RGB->LMS, L/M merge, LMS->RGB collapsed into one 3x3 (host, float64 -> f32)
+        const float *xl, *xr, *wl, *wr;  // per-column tables, length W (device)
+        const uint32_t *frame_flags;     // per frame: != 0 when some byte >= 2 (written by frame_flags_kernel)
+        int norm_mode;                   // AVB_NORM_DIV255: always /255; AVB_NORM_AUTO: /255 iff flag set
+    };
+    static constexpr int SMEM_FLOATS = 256;
+    const float *norm_s;
+    const uint8_t *src;
+    int64_t rs;
+    int W;
+    float m[9];
+    const float *xl, *xr, *wl, *wr;
+    uint32_t seen;
+
+    __device__ __forceinline__ void init(const Params &pp, float *smem, const uint8_t *frame, int64_t row_stride,
+                                         int /*H*/, int W_, int frame_idx) {
+        // normalised byte values exactly as NumPy makes them: float32(v) / float32(255), or, when the
+        // frame max is <= 1 (get_normalized_image's other branch), the byte itself clipped to [0,1]
+        const bool div255 = pp.norm_mode == AVB_NORM_DIV255 || __ldg(pp.frame_flags + frame_idx) != 0;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            smem[i] = div255 ? __fdiv_rn((float)i, 255.0f) : fminf((float)i, 1.0f);
+        norm_s = smem;
+        src = frame;
+        rs = row_stride;
+        W = W_;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = pp.M.m[i];
+        xl = pp.xl; xr = pp.xr; wl = pp.wl; wr = pp.wr;
+        seen = 0;
+    }
+    // cv::remap INTER_LINEAR on a row: map coordinate quantised to 1/32 px, two taps, border 0
+    __device__ __forceinline__ void gather(const uint8_t *row, float xs, float &c0, float &c1, float &c2) {
+        const int sx = __float2int_rn(xs * 32.0f);
+        const int ix = sx >> 5;
+        const float f = (float)(sx & 31) * (1.0f / 32.0f);
+        const float w0 = 1.0f - f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if ((unsigned)ix < (unsigned)W) {
+            const uint8_t *q = row + 3 * ix;
+            const uint32_t u0 = q[0], u1 = q[1], u2 = q[2];
+            seen |= u0 | u1 | u2;
+            a0 = norm_s[u0]; a1 = norm_s[u1]; a2 = norm_s[u2];
+        }
+        if ((unsigned)(ix + 1) < (unsigned)W) {
+            const uint8_t *q = row + 3 * (ix + 1);
+            const uint32_t u0 = q[0], u1 = q[1], u2 = q[2];
+            seen |= u0 | u1 | u2;
+            b0 = norm_s[u0]; b1 = norm_s[u1]; b2 = norm_s[u2];
+        }
+        c0 = __fadd_rn(__fmul_rn(a0, w0), __fmul_rn(b0, f));
+        c1 = __fadd_rn(__fmul_rn(a1, w0), __fmul_rn(b1, f));
+        c2 = __fadd_rn(__fmul_rn(a2, w0), __fmul_rn(b2, f));
+    }
+    static __device__ __forceinline__ float decode(float v) {
+        // animals/animal_utils.py:5-11 on float32
+        return v <= 0.04045f ? __fdiv_rn(v, 12.92f) : powf(__fdiv_rn(v + 0.055f, 1.055f), 2.4f);
+    }
+    __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
+        const uint8_t *row = src + (int64_t)y * rs;
+        const float wL = __ldg(wl + x), wR = __ldg(wr + x);
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        // a zero weight multiplies a finite sample: skipping the gather leaves the sum unchanged
+        if (wL != 0.0f) gather(row, __ldg(xl + x), l0, l1, l2);
+        if (wR != 0.0f) gather(row, __ldg(xr + x), r0, r1, r2);
+        const float ws = __fadd_rn(__fadd_rn(wL, wR), 1e-8f);
+        float s0 = __fdiv_rn(__fadd_rn(__fmul_rn(l0, wL), __fmul_rn(r0, wR)), ws);
+        float s1 = __fdiv_rn(__fadd_rn(__fmul_rn(l1, wL), __fmul_rn(r1, wR)), ws);
+        float s2 = __fdiv_rn(__fadd_rn(__fmul_rn(l2, wL), __fmul_rn(r2, wR)), ws);
+        s0 = decode(__saturatef(s0)); s1 = decode(__saturatef(s1)); s2 = decode(__saturatef(s2));
+        o0 = m[0] * s0 + m[1] * s1 + m[2] * s2;
+        o1 = m[3] * s0 + m[4] * s1 + m[5] * s2;
+        o2 = m[6] * s0 + m[7] * s1 + m[8] * s2;
+    }
+};
+
+// ------------------------------------------------------------------------------------ kernel
+template <int R, class Prod>
+__global__ void __launch_bounds__(G_THREADS, 3)
+gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant__ typename Prod::Params pp) {
+    using C = GaussCfg<R>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float *S = reinterpret_cast<float *>(smem_raw);            // [3][RB][S_PITCH] produced rows (+x halo)
+    float *X = S + C::S_FLOATS;                                // [3][RB][X_PITCH] horizontally blurred rows
+    float *prod_smem = X + C::X_FLOATS;
+    uint8_t *stage = reinterpret_cast<uint8_t *>(prod_smem + Prod::SMEM_FLOATS);   // [RB][TW*3] encoded bytes
+    uint32_t *enc_s = reinterpret_cast<uint32_t *>(stage + C::STAGE_BYTES);
+
+    const int frame = blockIdx.z;
+    if (p.fixup && p.flags[frame] != 0) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.io.H, W = p.io.W;
+    const int x0 = blockIdx.x * G_TW;
+    const int y_start = blockIdx.y * p.seg_h;
+    const int y_end = min(H, y_start + p.seg_h);
+
+    Prod prod;
+    prod.init(pp, prod_smem, p.io.in + (int64_t)frame * p.io.in_fs, p.io.in_rs, H, W, frame);
+    copy_to_smem(enc_s, p.enc, min(G_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+
+    uint8_t *dst_frame = p.io.out + (int64_t)frame * p.io.out_fs;
+    const bool vec_ok = (x0 + G_TW <= W) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
+
+    const int n_out_blocks = (y_end - y_start + G_RB - 1) / G_RB;
+    const int n_in_blocks = n_out_blocks + C::LAG;
+
+    // task coordinates: warp -> (channel, half strip); H pass: lane -> (row, 8-px group);
+    // V pass: lane -> column.  The V window lives in registers for the whole segment.
+    const int ch = warp >> 1;
+    const int h_r = lane & 7, h_xg = ((warp & 1) << 2) + (lane >> 3);
+    const int v_x = ((warp & 1) << 5) + lane;
+    float vw[C::VW];
+#pragma unroll
+    for (int i = 0; i < C::VW; ++i) vw[i] = 0.f;
+
+    for (int ib = 0; ib < n_in_blocks; ++ib) {
+        // ---- produce RB rows x IN_W columns of linear-light values (input rows y_start-R+8*ib ..)
+        const int yb = y_start - R + ib * G_RB;
+        for (int idx = tid; idx < G_RB * C::IN_W; idx += G_THREADS) {
+            const int r = idx / C::IN_W, i = idx - r * C::IN_W;
+            const int y = reflect101(yb + r, H), x = reflect101(x0 - R + i, W);
+            float o0, o1, o2;
+            prod(y, x, o0, o1, o2);
+            S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
+            S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
+            S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+        }
+        __syncthreads();
+
+        // ---- horizontal pass: 8 outputs per thread from a WIN-wide register window
+        {
+            const float4 *w4 = reinterpret_cast<const float4 *>(&S[(ch * G_RB + h_r) * C::S_PITCH + h_xg * 8]);
+            float v[4 * C::NW4];
+#pragma unroll
+            for (int q = 0; q < C::NW4; ++q) {
+                const float4 t = w4[q];
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                const float tk = p.taps[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(tk, v[j + k], acc[j]);
+            }
+            float4 *d4 = reinterpret_cast<float4 *>(&X[(ch * G_RB + h_r) * C::X_PITCH + h_xg * 8]);
+            d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        __syncthreads();
+
+        // ---- vertical pass: slide the register window down by 8 rows, emit 8 outputs once it is full
+        {
+            const float *col = X + ch * G_RB * C::X_PITCH + v_x;
+#pragma unroll
+            for (int j = 0; j < G_RB; ++j) vw[C::VW - G_RB + j] = col[j * C::X_PITCH];
+        }
+        const int ob = ib - C::LAG;
+        if (ob >= 0) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                const float tk = p.taps[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(tk, vw[j + k], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) stage[j * (G_TW * 3) + v_x * 3 + ch] = (uint8_t)encode_u8(enc, acc[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < C::VW - G_RB; ++i) vw[i] = vw[i + G_RB];
+        __syncthreads();
+
+        // ---- store the 8 x (TW*3)-byte block
+        if (ob >= 0) {
+            const int oy = y_start + ob * G_RB;
+            if (vec_ok) {
+                constexpr int V_PER_ROW = G_TW * 3 / 16;       // 12 x 16 B per row
+                for (int idx = tid; idx < G_RB * V_PER_ROW; idx += G_THREADS) {
+                    const int r = idx / V_PER_ROW, q = idx - r * V_PER_ROW;
+                    if (oy + r < y_end) {
+                        const uint4 val = reinterpret_cast<const uint4 *>(stage + r * (G_TW * 3))[q];
+                        *reinterpret_cast<uint4 *>(dst_frame + (int64_t)(oy + r) * p.io.out_rs + (int64_t)x0 * 3 + q * 16) = val;
+                    }
+                }
+            } else {
+                const int nbytes = min(G_TW, W - x0) * 3;
+                for (int idx = tid; idx < G_RB * G_TW * 3; idx += G_THREADS) {
+                    const int r = idx / (G_TW * 3), b = idx - r * (G_TW * 3);
+                    if (oy + r < y_end && b < nbytes)
+                        dst_frame[(int64_t)(oy + r) * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[idx];
+                }
+            }
+        }
+        // hazards: the next produce only writes S (H pass done); X is rewritten after the next
+        // produce barrier (V pass done); stage is rewritten two barriers from here.
+    }
+
+    if (p.flags != nullptr && !p.fixup) {
+        if (__any_sync(0xffffffffu, (prod.seen & 0xfeu) != 0) && lane == 0) p.flags[frame] = 1u;
+    }
+}
+
+template <int R, class Prod>
+static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
+    using C = GaussCfg<R>;
+    const size_t smem = (size_t)(C::S_FLOATS + C::X_FLOATS + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::STAGE_BYTES;
+    auto kern = gauss_stream_kernel<R, Prod>;
+    AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
+    kern<<<grid, G_THREADS, smem, st>>>(gc, pp);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+// rows per segment: enough CTAs to fill the machine a few times over, but tall enough that the
+// 2*RP halo rows re-produced per segment stay a small fraction
+static int pick_seg_h(int n, int H, int W, int radius) {
+    const int strips = (W + G_TW - 1) / G_TW;
+    const long target = 4L * 3 * sm_count();                 // ~4 waves at 3 CTAs/SM
+    long segs = (target + (long)strips * n - 1) / ((long)strips * n);
+    const int min_h = 16 * radius;                             // halo rows re-produced per segment <= 12.5 %
+    long max_segs = (H + min_h - 1) / min_h;
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    int seg_h = (int)((H + segs - 1) / segs);
+    seg_h = (seg_h + G_RB - 1) / G_RB * G_RB;
+    return seg_h;
+}
+
+template <class Prod>
+static int dispatch_gauss(int radius, GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
+    gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius);
+    switch (radius) {
+#define AVB_CASE(RR) case RR: return launch_gauss<RR, Prod>(gc, pp, st);
+        AVB_CASE(1) AVB_CASE(2) AVB_CASE(3) AVB_CASE(4) AVB_CASE(5) AVB_CASE(6) AVB_CASE(7) AVB_CASE(8)
+        AVB_CASE(9) AVB_CASE(10) AVB_CASE(11) AVB_CASE(12) AVB_CASE(13) AVB_CASE(14) AVB_CASE(15) AVB_CASE(16)
+#undef AVB_CASE
+        default:
+            set_error("gaussian radius %d unsupported (ksize must be odd, 3..33)", radius);
+            return AVB_E_UNSUPPORTED;
+    }
+}
+
+static int check_io(const FrameIO &io) {
+    if (!io.in || !io.out) { set_error("null frame pointer"); return AVB_E_ARG; }
+    if (io.n <= 0 || io.H <= 0 || io.W <= 0) { set_error("bad frame geometry n=%d H=%d W=%d", io.n, io.H, io.W); return AVB_E_ARG; }
+    if (io.in_rs < 3LL * io.W || io.out_rs < 3LL * io.W) { set_error("row stride smaller than 3*W"); return AVB_E_ARG; }
+    return AVB_OK;
+}
+
+}  // namespace avb
+
+using namespace avb;
+
+extern "C" int avb_dichromat_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                                     int64_t in_frame_stride, int64_t in_row_stride,
+                                     int64_t out_frame_stride, int64_t out_row_stride,
+                                     const float *dec_dev, const float *dec_raw_dev, const uint32_t *enc_dev,
+                                     const float *m_host, const float *taps_host, int ksize,
+                                     int norm_mode, uint32_t *flags_dev, avb_stream_t stream) {
+    GaussCommon gc{};
+    gc.io = FrameIO{in, out, in_frame_stride, in_row_stride, out_frame_stride, out_row_stride, n, H, W};
+    if (int e = check_io(gc.io)) return e;
+    AVB_REQUIRE(dec_dev && enc_dev && m_host && taps_host, "null table pointer");
+    AVB_REQUIRE(ksize >= 3 && ksize <= G_MAX_TAPS && (ksize & 1), "ksize must be odd, 3..33");
+    AVB_REQUIRE(norm_mode == AVB_NORM_DIV255 || (norm_mode == AVB_NORM_AUTO && dec_raw_dev && flags_dev),
+                "AVB_NORM_AUTO needs dec_raw_dev and flags_dev");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];
+    gc.enc = enc_dev;
+    DogProducer::Params pp{};
+    for (int i = 0; i < 9; ++i) pp.M.m[i] = m_host[i];
+    pp.lut = dec_dev;
+    if (norm_mode == AVB_NORM_AUTO) {
+        AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
+        gc.flags = flags_dev;
+    }
+    gc.fixup = 0;
+    if (int e = dispatch_gauss<DogProducer>(ksize / 2, gc, pp, st)) return e;
+    if (norm_mode == AVB_NORM_AUTO) {
+        gc.fixup = 1;
+        pp.lut = dec_raw_dev;
+        if (int e = dispatch_gauss<DogProducer>(ksize / 2, gc, pp, st)) return e;
+    }
+    return AVB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ Cat
+namespace avb {
+
+// per-frame "some byte >= 2" (the data-dependent branch of get_normalized_image) for kernels that
+// do not visit every input pixel themselves
+__global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *flags) {
+    const int frame = blockIdx.y;
+    const uint8_t *src = io.in + (int64_t)frame * io.in_fs;
+    const int row_bytes = 3 * io.W;
+    uint32_t seen = 0;
+    const bool vec = ((io.in_rs & 15) == 0) && ((io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(io.in) & 15) == 0);
+    for (int y = blockIdx.x; y < io.H; y += gridDim.x) {
+        const uint8_t *row = src + (int64_t)y * io.in_rs;
+        int b = 0;
+        if (vec) {
+            const int nv = row_bytes >> 4;
+            for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row) + i);
+                seen |= v.x | v.y | v.z | v.w;
+            }
+            b = nv << 4;
+        }
+        for (int i = b + threadIdx.x; i < row_bytes; i += blockDim.x) seen |= row[i];
+    }
+    if (__any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && (threadIdx.x & 31) == 0) flags[frame] = 1u;
+}
+
+// Centre zoom (cat_widevision_utils.py:11-29): crop + cv2.resize(INTER_LINEAR) on uint8, restated
+// in OpenCV's 11-bit fixed point so the result is bit-exact.  tab = xi0,xi1,xw0,xw1 [W] then
+// yi0,yi1,yw0,yw1 [H] (source indices already include the crop origin).
+__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab) {
+    const int W = io.W, H = io.H;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const int32_t *tx = tab, *ty = tab + 4 * W;
+    const int xi0 = __ldg(tx + x), xi1 = __ldg(tx + W + x), xw0 = __ldg(tx + 2 * W + x), xw1 = __ldg(tx + 3 * W + x);
+    const int yi0 = __ldg(ty + y), yi1 = __ldg(ty + H + y), yw0 = __ldg(ty + 2 * H + y), yw1 = __ldg(ty + 3 * H + y);
+    const uint8_t *src = io.in + (int64_t)blockIdx.z * io.in_fs;
+    const uint8_t *r0 = src + (int64_t)yi0 * io.in_rs, *r1 = src + (int64_t)yi1 * io.in_rs;
+    uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y * io.out_rs + 3 * x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int s0 = r0[3 * xi0 + c] * xw0 + r0[3 * xi1 + c] * xw1;
+        const int s1 = r1[3 * xi0 + c] * xw0 + r1[3 * xi1 + c] * xw1;
+        const int v = ((((yw0 * (s0 >> 4)) >> 16) + ((yw1 * (s1 >> 4)) >> 16) + 2) >> 2);
+        o[c] = (uint8_t)min(255, max(0, v));
+    }
+}
+
+}  // namespace avb
+
+extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_cat, int n, int H, int W,
+                          int64_t in_frame_stride, int64_t in_row_stride,
+                          int64_t human_frame_stride, int64_t human_row_stride,
+                          int64_t cat_frame_stride, int64_t cat_row_stride,
+                          const uint32_t *enc_dev, const float *m_host, const float *taps_host, int ksize,
+                          const float *warp_dev, const int32_t *zoom_dev,
+                          int norm_mode, uint32_t *flags_dev, avb_stream_t stream) {
+    GaussCommon gc{};
+    gc.io = FrameIO{in, out_cat, in_frame_stride, in_row_stride, cat_frame_stride, cat_row_stride, n, H, W};
+    if (int e = check_io(gc.io)) return e;
+    AVB_REQUIRE(enc_dev && m_host && taps_host && warp_dev, "null table pointer");
+    AVB_REQUIRE(ksize >= 3 && ksize <= G_MAX_TAPS && (ksize & 1), "ksize must be odd, 3..33");
+    AVB_REQUIRE(norm_mode == AVB_NORM_DIV255 || (norm_mode == AVB_NORM_AUTO && flags_dev), "AVB_NORM_AUTO needs flags_dev");
+    AVB_REQUIRE((out_human == nullptr) == (zoom_dev == nullptr), "out_human and zoom_dev go together");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (norm_mode == AVB_NORM_AUTO) {
+        AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
+        dim3 grid(H < 256 ? H : 256, n);
+        frame_flags_kernel<<<grid, 256, 0, st>>>(gc.io, flags_dev);
+        AVB_CUDA_OK(cudaGetLastError());
+    }
+    if (out_human) {
+        AVB_REQUIRE(human_row_stride >= 3LL * W, "row stride smaller than 3*W");
+        FrameIO zio{in, out_human, in_frame_stride, in_row_stride, human_frame_stride, human_row_stride, n, H, W};
+        dim3 grid((W + 255) / 256, H, n);
+        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev);
+        AVB_CUDA_OK(cudaGetLastError());
+    }
+    for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];
+    gc.enc = enc_dev;
+    gc.flags = nullptr;   // the producer does not see every pixel: normalisation comes from frame_flags_kernel
+    gc.fixup = 0;
+    CatProducer::Params pp{};
+    for (int i = 0; i < 9; ++i) pp.M.m[i] = m_host[i];
+    pp.xl = warp_dev; pp.xr = warp_dev + W; pp.wl = warp_dev + 2 * W; pp.wr = warp_dev + 3 * W;
+    pp.frame_flags = flags_dev;
+    pp.norm_mode = norm_mode;
+    return dispatch_gauss<CatProducer>(ksize / 2, gc, pp, st);
+}

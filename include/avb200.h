@@ -1,0 +1,115 @@
+/* avb200.h -- C ABI of libavb200.so: the B200 (sm_100a) pixel pipeline behind animal-vision's
+ * `Animal.visualize()`.
+ *
+ * Every entry point replaces a piece of the reference's per-frame NumPy/OpenCV/torch code path
+ * (cited per function as file:line under the reference tree).  Conventions:
+ *   - frames are packed 8-bit, 3 interleaved channels, addressed with explicit BYTE strides
+ *     (frame stride, row stride); channel order is never interpreted (the reference is fed RGB by
+ *     its renderers and BGR by its server and indexes channels 0/1/2 either way);
+ *   - `in`, `out`, `*_dev` pointers are DEVICE pointers owned by the caller (torch); `*_host`
+ *     pointers are small host arrays read during the call; nothing is retained after return;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises the device;
+ *   - return value 0 = ok, negative = AVB_E_*; avb_last_error() gives the message of the last
+ *     failure on the calling thread.
+ * There is no CPU fallback: with no CUDA device every compute entry point returns AVB_E_CUDA.
+ */
+#ifndef AVB200_H
+#define AVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVB_VERSION 100            /* 0.1.0 */
+
+#define AVB_OK 0
+#define AVB_E_ARG (-1)             /* bad argument (null pointer, non-positive size, unsupported radius ...) */
+#define AVB_E_CUDA (-2)            /* CUDA runtime error (message in avb_last_error) */
+#define AVB_E_UNSUPPORTED (-3)
+
+/* How the 8-bit input is normalised before the sRGB decode. */
+#define AVB_NORM_DIV255 0          /* uv_helpers.py:15-19 to_float01: uint8 is always divided by 255 */
+#define AVB_NORM_AUTO 1            /* animals/animal_utils.py:41-50 get_normalized_image: divide by 255
+                                      only if the frame maximum exceeds 1 (decided per frame, on device) */
+
+typedef void *avb_stream_t;        /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define AVB_API __attribute__((visibility("default")))
+#else
+#define AVB_API
+#endif
+
+AVB_API int avb_version(void);
+AVB_API const char *avb_last_error(void);
+
+/* Number of uint32 entries avb_build_encode_table writes at most. */
+#define AVB_ENC_TABLE_MAX 2048
+
+/* Host helper.  Turns the 255 quantisation thresholds of the reference's encode tail
+ * (clip -> linear_to_srgb -> clip -> x*255+0.5 -> astype(uint8); animals/dog.py:54-59 with
+ * animals/animal_utils.py:13-19) into the bucketed lookup table the kernels use.
+ *   thr_host[i-1] = smallest float32 x in [0,1] whose encoded byte is >= i, i = 1..255
+ * (built by the host with the reference's own NumPy expression, so the device quantiser IS the
+ * reference's step function).  Writes table_host[0..n) (n <= AVB_ENC_TABLE_MAX) and returns n, or
+ * a negative error.  The caller uploads the table and passes the device pointer as `enc_dev`. */
+AVB_API int avb_build_encode_table(const float *thr_host, uint32_t *table_host, int capacity);
+
+/* K1 -- fused per-pixel colorimetric kernel (HBM bound, 6 B/px).
+ * Replaces animals/animal_utils.py:41-50 (normalise), :5-11 (sRGB decode), the `pixels @ T.T`
+ * 3x3 of animals/dog.py:44-48 with T from animal_utils.py:88-119, the optional per-row S-cone gain
+ * of animal_utils.py:206-259 (rat.py:34), and the encode tail dog.py:54-59.
+ *   dec_dev      256 float32 decode LUT for frames that are divided by 255
+ *   dec_raw_dev  256 float32 decode LUT for frames whose max is <= 1 (AVB_NORM_AUTO only; may be NULL
+ *                with AVB_NORM_DIV255)
+ *   enc_dev      table from avb_build_encode_table
+ *   m_host       9 floats, row-major T; out[c] = sum_k T[c][k] * lin[k]
+ *   row_gain_dev NULL, or H floats: channel 2 is multiplied by row_gain[y] and clipped to [0,1]
+ *   flags_dev    n uint32 scratch words (AVB_NORM_AUTO only) */
+AVB_API int avb_colorimetric_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                        int64_t in_frame_stride, int64_t in_row_stride,
+                        int64_t out_frame_stride, int64_t out_row_stride,
+                        const float *dec_dev, const float *dec_raw_dev, const uint32_t *enc_dev,
+                        const float *m_host, const float *row_gain_dev,
+                        int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
+
+/* K2 -- dichromat recipe with an isotropic acuity blur, one fused kernel:
+ * decode -> 3x3 -> separable Gaussian (BORDER_REFLECT_101) -> clip -> encode.
+ * Replaces animals/dog.py:35-59 (and the 8 sibling species that call apply_acuity_blur,
+ * animals/animal_utils.py:121-145 = cv2.GaussianBlur(img,(0,0),sigma)).
+ *   taps_host    ksize float32 taps (cv2.getGaussianKernel(ksize, sigma, CV_32F)), ksize odd, <= 33 */
+AVB_API int avb_dichromat_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                          int64_t in_frame_stride, int64_t in_row_stride,
+                          int64_t out_frame_stride, int64_t out_row_stride,
+                          const float *dec_dev, const float *dec_raw_dev, const uint32_t *enc_dev,
+                          const float *m_host, const float *taps_host, int ksize,
+                          int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
+
+/* Cat -- both outputs of Cat.visualize (animals/cat.py:73-114, the runnable side of the merge
+ * conflict) for a batch of frames:
+ *   out_human  centre zoom (animals/cat_widevision_utils.py:11-29: crop + cv2.resize INTER_LINEAR on
+ *              uint8, restated in OpenCV's 11-bit fixed point, bit-exact); may be NULL with zoom_dev NULL
+ *   out_cat    binocular wide-FOV warp (cat_widevision_utils.py:46-99; cv2.remap INTER_LINEAR with its
+ *              1/32-px coordinate quantisation, BORDER_CONSTANT 0, cos^2 blend) fused, as the producer
+ *              stage, into the K2 blur kernel: decode (pow) -> collapsed 3x3 (cat.py:95-101) ->
+ *              Gaussian sigma=1.0 (9 taps) -> encode.
+ *   warp_dev   4*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights)
+ *   zoom_dev   4*W + 4*H int32: xi0, xi1, xw0, xw1, yi0, yi1, yw0, yw1 (source indices incl. crop
+ *              origin, 11-bit weights)
+ *   enc_dev    encode table built from the float64 tail's thresholds (cat.py runs float64 from
+ *              LMS_to_RGB on; the device tail is float32)
+ *   flags_dev  n uint32 scratch (AVB_NORM_AUTO): filled by a pre-pass over each frame */
+AVB_API int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_cat, int n, int H, int W,
+                       int64_t in_frame_stride, int64_t in_row_stride,
+                       int64_t human_frame_stride, int64_t human_row_stride,
+                       int64_t cat_frame_stride, int64_t cat_row_stride,
+                       const uint32_t *enc_dev, const float *m_host, const float *taps_host, int ksize,
+                       const float *warp_dev, const int32_t *zoom_dev,
+                       int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVB200_H */

@@ -38,7 +38,7 @@ def impulses(h: int, w: int) -> np.ndarray:
     f = np.zeros((h, w, 3), np.uint8)
     for (y, x, c) in [(0, 0, 0), (h - 1, w - 1, 1), (h // 2, w // 2, 2), (1, w - 2, 0), (h - 2, 1, 2),
                       (h // 3, 2 * w // 3, 1)]:
-        f[y, x, c] = 255
+        f[min(max(y, 0), h - 1), min(max(x, 0), w - 1), c] = 255
     f[h // 4, w // 4] = 255
     return f
 

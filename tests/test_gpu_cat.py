@@ -1,0 +1,49 @@
+"""GPU parity for Cat: centre zoom must be bit-exact (integer arithmetic), the wide-FOV view
+<= 1 LSB (float32 tail instead of the reference's float64 tail)."""
+import numpy as np
+import pytest
+
+import frames
+from oracle import mammals as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(human, cat, ref_h, ref_c, what):
+    assert human.dtype == cat.dtype == np.uint8 and human.shape == ref_h.shape and cat.shape == ref_c.shape
+    assert np.array_equal(human, ref_h), f"{what}: centre zoom differs ({(human != ref_h).mean():.5f} of bytes)"
+    d = np.abs(cat.astype(np.int16) - ref_c.astype(np.int16))
+    assert d.max() <= 1, f"{what}: cat view max diff {d.max()} LSB"
+    assert (d > 0).mean() <= 0.02, f"{what}: {(d > 0).mean():.4f} of bytes differ"
+
+
+def test_cat_against_golden(golden, golden_meta):
+    from animal_vision_b200.animals import Cat
+    h, w = golden_meta["small_hw"]
+    g = golden("cat")
+    for name, f in frames.parity_set(h, w):
+        human, cat = Cat().visualize(f)
+        assert human is not f and cat is not f
+        _check(human, cat, g[f"human/{name}"], g[f"cat/{name}"], name)
+
+
+@pytest.mark.parametrize("hw", [(61, 67), (270, 480), (33, 300), (1080, 1920)])
+def test_cat_against_oracle(hw):
+    from animal_vision_b200.animals import Cat
+    h, w = hw
+    cases = list(frames.parity_set(h, w)) if h < 1000 else [("noise0", frames.noise(h, w, 0)), ("natural", frames.natural(h, w))]
+    for name, f in cases:
+        ref_h, ref_c = M.cat_visualize(f)
+        human, cat = Cat().visualize(f)
+        _check(human, cat, ref_h, ref_c, f"{name}/{h}x{w}")
+
+
+def test_cat_batch():
+    import torch
+    from animal_vision_b200.animals import Cat
+    fs = [frames.noise(120, 200, s) for s in range(3)] + [frames.le1(120, 200)]
+    batch = torch.from_numpy(np.stack(fs)).cuda()
+    human, cat = Cat().visualize_batch(batch)
+    for i, f in enumerate(fs):
+        ref_h, ref_c = M.cat_visualize(f)
+        _check(human[i].cpu().numpy(), cat[i].cpu().numpy(), ref_h, ref_c, f"batch[{i}]")

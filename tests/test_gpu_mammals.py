@@ -1,0 +1,67 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle and the reference's golden
+vectors.  Tolerance from BASELINE.json north_star: <= 1 LSB on uint8 output."""
+import numpy as np
+import pytest
+
+import frames
+from oracle import mammals as M
+
+pytestmark = pytest.mark.gpu
+
+GAUSS = ["dog", "bear", "lion", "tiger", "elephant", "fox", "wolf", "raccoon", "squirrel"]
+
+
+def _species(name):
+    import animal_vision_b200.animals as A
+    return A.MAMMALS[name]()
+
+
+def _cmp(got, ref, what, max_frac=0.02):
+    assert got.shape == ref.shape and got.dtype == ref.dtype == np.uint8, what
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert d.max() <= 1, f"{what}: max diff {d.max()} LSB"
+    assert (d > 0).mean() <= max_frac, f"{what}: {(d > 0).mean():.4f} of bytes differ by 1 LSB"
+
+
+@pytest.mark.parametrize("name", GAUSS + ["rat"])
+def test_against_golden(name, golden, golden_meta):
+    h, w = golden_meta["small_hw"]
+    fr = dict(frames.parity_set(h, w))
+    g = golden("mammals")
+    sp = _species(name)
+    for key, ref in g.items():
+        s, case = key.split("/")
+        if s != name:
+            continue
+        base, out = sp.visualize(fr[case])
+        assert base is fr[case]
+        _cmp(out, ref, key)
+
+
+@pytest.mark.parametrize("name", ["dog", "squirrel", "raccoon", "rat"])
+@pytest.mark.parametrize("hw", [(61, 67), (8, 200), (270, 480), (1, 5), (37, 1)])
+def test_against_oracle_odd_shapes(name, hw):
+    h, w = hw
+    sp = _species(name)
+    for case, f in frames.parity_set(h, w):
+        _, ref = M.mammal_visualize(f, name)
+        _, out = sp.visualize(f)
+        _cmp(out, ref, f"{name}/{case}/{h}x{w}", max_frac=0.05)
+
+
+def test_dog_1080p_batch_and_strides():
+    import torch
+    from animal_vision_b200.animals import Dog
+    f0, f1 = frames.noise(1080, 1920, 0), frames.natural(1080, 1920)
+    refs = [M.mammal_visualize(f, "dog")[1] for f in (f0, f1)]
+    batch = torch.from_numpy(np.stack([f0, f1])).cuda()
+    base, out = Dog().visualize_batch(batch)
+    assert base is batch
+    for i in range(2):
+        _cmp(out[i].cpu().numpy(), refs[i], f"dog 1080p frame {i}")
+    # non-contiguous rows: a view into a wider buffer
+    wide = torch.zeros((2, 1080, 2000, 3), dtype=torch.uint8, device="cuda")
+    wide[:, :, 40:1960] = batch
+    view = wide[:, :, 40:1960]
+    _, out2 = Dog().visualize_batch(view)
+    assert torch.equal(out2, out)
