@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <vector>
 
 #include "avb_common.cuh"
 
@@ -35,9 +36,58 @@ int sm_count() {
     return v;
 }
 
+// ---- per-kernel timing recorder (thread local; bench.py's roofline leg)
+struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> *g_prof = nullptr;
+
+bool profiling_on() { return g_prof_on; }
+
+void profile_mark(const char *name, cudaStream_t st, bool begin) {
+    if (!g_prof) g_prof = new std::vector<ProfRec>();
+    if (begin) {
+        ProfRec r{name, nullptr, nullptr};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        g_prof->push_back(r);
+    } else if (!g_prof->empty()) {
+        cudaEventRecord(g_prof->back().e1, st);
+    }
+}
+
 }  // namespace avb
 
 extern "C" {
+
+int avb_profile_begin(void) {
+    avb::g_prof_on = true;
+    if (avb::g_prof) avb::g_prof->clear();
+    return AVB_OK;
+}
+
+int avb_profile_end(char *names, int name_stride, float *ms, int capacity) {
+    avb::g_prof_on = false;
+    if (!avb::g_prof) return 0;
+    int n = 0;
+    for (auto &r : *avb::g_prof) {
+        cudaEventSynchronize(r.e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        if (n < capacity && names && ms) {
+            snprintf(names + (size_t)n * name_stride, name_stride, "%s", r.name);
+            ms[n] = t;
+            ++n;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    avb::g_prof->clear();
+    return n;
+}
 
 int avb_version(void) { return AVB_VERSION; }
 

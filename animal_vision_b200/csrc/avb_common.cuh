@@ -29,6 +29,25 @@ int cuda_fail(cudaError_t e, const char *what);
 
 int sm_count();  // multiprocessors of the current device (cached)
 
+// ---------------------------------------------------------------- per-kernel timing (bench only)
+// Between avb_profile_begin() and avb_profile_end() every kernel launched by the library on the
+// calling thread is bracketed by a pair of CUDA events on its own stream.  Off by default.
+bool profiling_on();
+void profile_mark(const char *name, cudaStream_t st, bool begin);
+
+struct LaunchScope {
+    const char *name;
+    cudaStream_t st;
+    bool on;
+    LaunchScope(const char *n, cudaStream_t s) : name(n), st(s), on(profiling_on()) {
+        if (on) profile_mark(name, st, true);
+    }
+    ~LaunchScope() {
+        if (on) profile_mark(name, st, false);
+    }
+};
+#define AVB_TIMED(name, st) avb::LaunchScope _avb_scope_##__LINE__(name, st)
+
 // ---------------------------------------------------------------- frame addressing
 struct FrameIO {
     const uint8_t *in;

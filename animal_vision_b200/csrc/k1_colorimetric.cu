@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_strided_kernel(const __grid_con
 
 static int launch_k1(const K1Params &p, cudaStream_t st) {
     const FrameIO &io = p.io;
+    AVB_TIMED(p.fixup ? "k1_colorimetric_fixup" : "k1_colorimetric", st);
     const bool contig = io.W >= 16 && io.in_rs == 3LL * io.W && io.out_rs == 3LL * io.W && (io.in_fs & 15) == 0 && (io.out_fs & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(io.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(io.out) & 15) == 0;
     if (contig) {

@@ -50,6 +50,8 @@ struct GaussCommon {
 
 // ------------------------------------------------------------------------------------ producers
 struct DogProducer {
+    static const char *name() { return "k2_gauss_dichromat"; }
+    static const char *fixup_name() { return "k2_gauss_dichromat_fixup"; }
     struct Params {
         Mat3 M;
         const float *lut;  // 256-entry decode LUT (device)
@@ -83,6 +85,8 @@ struct DogProducer {
 };
 
 struct CatProducer {
+    static const char *name() { return "k2_gauss_cat_warp"; }
+    static const char *fixup_name() { return "k2_gauss_cat_warp_fixup"; }
     struct Params {
         Mat3 M;             // RGB->LMS, L/M merge, LMS->RGB collapsed into one 3x3 (host, float64 -> f32)
         const float *xl, *xr, *wl, *wr;  // per-column tables, length W (device)
@@ -301,6 +305,7 @@ static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, 
     auto kern = gauss_stream_kernel<R, Prod>;
     AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
+    AVB_TIMED(gc.fixup ? Prod::fixup_name() : Prod::name(), st);
     kern<<<grid, G_THREADS, smem, st>>>(gc, pp);
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
@@ -450,6 +455,7 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
     if (norm_mode == AVB_NORM_AUTO) {
         AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
         dim3 grid(H < 256 ? H : 256, n);
+        AVB_TIMED("frame_flags", st);
         frame_flags_kernel<<<grid, 256, 0, st>>>(gc.io, flags_dev);
         AVB_CUDA_OK(cudaGetLastError());
     }
@@ -457,6 +463,7 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
         AVB_REQUIRE(human_row_stride >= 3LL * W, "row stride smaller than 3*W");
         FrameIO zio{in, out_human, in_frame_stride, in_row_stride, human_frame_stride, human_row_stride, n, H, W};
         dim3 grid((W + 255) / 256, H, n);
+        AVB_TIMED("cat_center_zoom", st);
         center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev);
         AVB_CUDA_OK(cudaGetLastError());
     }

@@ -279,6 +279,35 @@ def honeybee_curves(lam: np.ndarray) -> np.ndarray:
     return np.stack(rows)
 
 
+def uv_band_table(lam: np.ndarray, sens: np.ndarray, illuminant: np.ndarray | None):
+    """Device table for the per-pixel band loop: [B, 8] rows {g0,g1,g2, E, s0,s1,s2, 0} and the
+    float32 normaliser denom + 1e-8 (torch adds the Python float to a float32 tensor)."""
+    G, denom = analytic_lobes(lam)
+    B = len(lam)
+    E = np.ones(B, np.float32) if illuminant is None else np.asarray(illuminant, np.float32)
+    tab = np.zeros((B, 8), np.float32)
+    tab[:, 0:3] = G
+    tab[:, 3] = E
+    tab[:, 4:4 + sens.shape[0]] = sens.T
+    return tab, np.float32(np.float32(denom) + np.float32(1e-8))
+
+
+def uv_collapsed_matrix(lam: np.ndarray, sens: np.ndarray, illuminant: np.ndarray | None) -> np.ndarray:
+    """[R,3] float32: catches = M @ lin.  M[k,c] = sum_l sens[k,l] E[l] G[l,c] / (denom + 1e-8),
+    composed in float64 from the float32 tables (the chain is linear)."""
+    tab, denom_eps = uv_band_table(lam, sens, illuminant)
+    G, E = tab[:, 0:3].astype(np.float64), tab[:, 3].astype(np.float64)
+    M = (sens.astype(np.float64) * E[None, :]) @ G / np.float64(denom_eps)
+    return M.astype(np.float32)
+
+
+def uv_blur_taps(sigma: float) -> np.ndarray:
+    """uv_helpers.py:67-73: ksize = 2*ceil(3 sigma)+1 (empty array: no blur)."""
+    if sigma <= 0:
+        return np.zeros(0, np.float32)
+    return gaussian_taps(int(2 * np.ceil(3 * sigma) + 1), sigma)
+
+
 def bandpass_weights(lam: np.ndarray, lo: float, hi: float) -> np.ndarray:
     """uv_helpers.py:125-139 (uniform 1/B fallback when the band holds no sample / no mass)."""
     wl = lam.astype(np.float32)

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the animal-vision per-frame pixel pipeline on B200 (BASELINE.json metric:
+Mpix/s and 4K frames/s at 1/2/4/8 GPUs, % of HBM roofline).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): a synthetic 4K (3840x2160)
+60-frame uint8 video batch PER GPU (weak scaling: frames are independent, no collective), species
+round-robin Dog -> Cat -> HoneyBee, frame s filled by numpy default_rng(seed s).  One step = one
+pass of the hot path over that batch: 20 Dog + 20 Cat + 20 HoneyBee frames.
+
+  value     whole-job Mpix/s with the frames already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public host API: pinned host frames in, pinned host frames out,
+            H2D + kernels + D2H all inside the timed region (HostBatchPipeline)
+  roofline  dominant kernel: algorithmic bytes per launch / its mean launch time, measured live
+            with CUDA events on the launching stream (avb_profile_begin/end)
+  cpu_baseline  oracle (CPU restatement of the reference; tests pin it bit-exact to the reference)
+            timed on this host's cores on a bounded sample of the same workload
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+H4K, W4K = 2160, 3840
+FRAMES_PER_GPU = 60
+SPECIES = ("Dog", "Cat", "HoneyBee")
+# algorithmic bytes per pixel (uint8 in + uint8 out(s)); SURVEY.md 8(d)
+ALGO_BYTES_PER_PX = {"Dog": 6, "Cat": 9, "HoneyBee": 6}
+KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
+                  "k3_uv_stats": "HoneyBee", "k3_uv_hist1": "HoneyBee", "k3_uv_hist2": "HoneyBee",
+                  "k3_uv_hist3": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_collect": "HoneyBee"}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, cmax = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.25:
+                sm.append(clk)
+                mx.append(cmax)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: use whatever we saw
+            for ts, line in self.lines:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def make_host_frames(rank: int, n_frames: int, H: int, W: int, pinned: bool):
+    """Per species: a uint8 [n_frames/3, H, W, 3] host tensor; frame s = default_rng(rank*n+s)."""
+    import torch
+    per = n_frames // len(SPECIES)
+    out = {}
+    for k, sp in enumerate(SPECIES):
+        t = torch.empty((per, H, W, 3), dtype=torch.uint8)
+        if pinned:
+            t = t.pin_memory()
+        view = t.numpy()
+        for j in range(per):
+            s = rank * n_frames + j * len(SPECIES) + k          # round-robin position in the video
+            view[j] = np.random.default_rng(s).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        out[sp] = t
+    return out
+
+
+def peak_numbers():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def oracle_step_time(frames_by_species, reps: int = 1):
+    """Seconds for one pass of the oracle (reference restatement) over the given frames."""
+    from oracle import mammals as M
+    from oracle import uv
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for sp, frames in frames_by_species.items():
+            for f in frames:
+                if sp == "Dog":
+                    M.mammal_visualize(f, "dog")
+                elif sp == "Cat":
+                    M.cat_visualize(f)
+                else:
+                    uv.honeybee_visualize(f)
+    return (time.perf_counter() - t0) / reps
+
+
+def host_threads():
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["sched_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    try:
+        import cv2
+        info["cv2_threads"] = cv2.getNumThreads()
+    except Exception:
+        pass
+    try:
+        import torch
+        info["torch_threads"] = torch.get_num_threads()
+    except Exception:
+        pass
+    return info
+
+
+def cpu_sample(rows: int):
+    """One frame per species, `rows` x 3840 (a full-width band of a 4K frame)."""
+    return {sp: [np.random.default_rng(1000 + k).integers(0, 256, (rows, W4K, 3), dtype=np.uint8)]
+            for k, sp in enumerate(SPECIES)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
+    is Python and cannot travel to the GPU box, tests pin the port bit-exact to it) on the host."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    cores = threads.get("sched_affinity") or threads.get("os_cpu_count") or 1
+    # size the per-step sample so that (warmup + steps) steps finish in ~150 s
+    probe = cpu_sample(270)
+    t_probe = oracle_step_time(probe)                         # 3 x 270x3840 frames
+    px_probe = 3 * 270 * W4K
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rows = int(min(H4K, max(64, 270 * budget / max(t_probe, 1e-6) * 0.8)))
+    sample = cpu_sample(rows)
+    px = 3 * rows * W4K
+    for _ in range(args.warmup):
+        oracle_step_time(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step_time(sample)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    mpix = px / dt / 1e6
+    desc = f"per step: 1 Dog + 1 Cat + 1 HoneyBee frame of {rows}x{W4K} (full-width band of a 4K frame), oracle port, all host threads"
+    line = {
+        "impl": "reference", "metric": "Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
+                   "resolution": f"{W4K}x{H4K}", "frames_per_gpu": FRAMES_PER_GPU, "species": list(SPECIES)},
+        "fps_4k": mpix * 1e6 / (H4K * W4K),
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc, "threads": threads},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "probe": {"px": px_probe, "seconds": t_probe},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    from animal_vision_b200 import _abi
+    import animal_vision_b200.animals as A
+    from animal_vision_b200.engine import get_engine
+    from animal_vision_b200.pipeline import HostBatchPipeline
+
+    lib = _abi.load()
+    eng = get_engine(dev)
+    H, W, nf = args.height, args.width, args.frames
+    species = {sp: getattr(A, sp)() for sp in SPECIES}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_gen = time.time()
+    host = make_host_frames(rank, nf, H, W, pinned=True)
+    log(f"[rank {rank}] generated {nf} host frames {W}x{H} in {time.time() - t_gen:.1f}s")
+    dev_in = {sp: host[sp].to(dev, non_blocking=True) for sp in SPECIES}
+    dev_out = {sp: ((torch.empty_like(dev_in[sp]), torch.empty_like(dev_in[sp])) if sp == "Cat" else torch.empty_like(dev_in[sp]))
+               for sp in SPECIES}
+    torch.cuda.synchronize()
+    px_step = nf * H * W                                   # per GPU
+
+    def step():
+        for sp in SPECIES:
+            species[sp].visualize_batch(dev_in[sp], out=dev_out[sp])
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = eng.launches - launches0
+
+    # ---- per-kernel timing over the same steps (roofline leg): CUDA events around every launch
+    prof_steps = max(1, min(args.steps, 3))
+    lib.avb_profile_begin()
+    for _ in range(prof_steps):
+        step()
+    cap = 4096
+    names = C.create_string_buffer(cap * 48)
+    msbuf = (C.c_float * cap)()
+    nrec = lib.avb_profile_end(names, 48, msbuf, cap)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    kern = {}
+    for i in range(nrec):
+        nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
+        k = kern.setdefault(nm, [0.0, 0])
+        k[0] += float(msbuf[i])
+        k[1] += 1
+    total_ms = sum(v[0] for v in kern.values()) or 1.0
+    shares = {nm: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / prof_steps, "share": v[0] / total_ms}
+              for nm, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    dom = next(iter(shares))
+    dom_sp = KERNEL_SPECIES.get(dom, "Dog")
+    frames_per_launch = dev_in[dom_sp].shape[0]
+    algo_bytes = ALGO_BYTES_PER_PX[dom_sp] * frames_per_launch * H * W
+    peak, peak_src = peak_numbers()
+    achieved = algo_bytes / (shares[dom]["ms_per_launch"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": f"{ALGO_BYTES_PER_PX[dom_sp]} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
+                "kernel_shares": shares}
+
+    # ---- end to end through the host API: pinned host in -> pinned host out
+    pipe = HostBatchPipeline(dev, chunk_frames=args.chunk)
+    host_out = {sp: pipe.pinned_like(host[sp], pipe.n_outputs(species[sp])) for sp in SPECIES}
+    jobs = [(species[sp], host[sp], host_out[sp]) for sp in SPECIES]
+    for _ in range(max(1, min(args.warmup, 2))):
+        pipe.run(jobs)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h2d, d2h = pipe.run(jobs)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    barrier()
+
+    # sanity: the e2e outputs equal the device-resident outputs (same kernels, same inputs)
+    ok = bool(torch.equal(host_out["Dog"][0][:2], dev_out["Dog"][:2].cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+    e2e_val = world * px_step / (e2e_ms * 1e-3) / 1e6
+    line = {
+        "metric": "Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
+                   "resolution": f"{W}x{H}", "frames_per_gpu": nf, "species": list(SPECIES), "parallelism": f"frame-sharded x{world}, no collective",
+                   "l2": f"inputs {nf * H * W * 3 / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
+                   "normalisation": "AVB_NORM_AUTO (reference semantics, decided per frame on device)"},
+        "fps_4k": value * 1e6 / (H4K * W4K),
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "fps_4k": e2e_val * 1e6 / (H4K * W4K),
+                "api": "HostBatchPipeline.run: pinned host frames -> H2D -> Animal.visualize_batch -> D2H -> pinned host frames",
+                "outputs_match_device_path": ok},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        threads = host_threads()
+        rows = args.cpu_rows
+        sample = cpu_sample(rows)
+        oracle_step_time(cpu_sample(64))                                  # warm up imports / thread pools
+        dt = oracle_step_time(sample)
+        line["cpu_baseline"] = {
+            "value": 3 * rows * W4K / dt / 1e6, "unit": "Mpix/s",
+            "cores": threads.get("sched_affinity") or threads.get("os_cpu_count") or 1, "kind": "port",
+            "sample": f"1 Dog + 1 Cat + 1 HoneyBee frame of {rows}x{W4K} (full-width band of a 4K frame), {dt:.1f} s of CPU work, oracle port with OpenCV/BLAS threads = all cores",
+            "threads": threads}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step (multiple of 3)")
+    ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline chunk in the e2e leg")
+    ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the 3840-wide CPU-baseline sample frames")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,6 @@ if __name__ == "__main__":
     for name in names:
         sp = getattr(A, name)()
         out = [torch.empty_like(frames)]
-        ms = timeit(lambda: sp.visualize_batch(frames, *out) if name != "Cat" else sp.visualize_batch(frames))
+        ms = timeit(lambda: sp.visualize_batch(frames))
         px = N * H * W
         print(f"{name}: {ms:.3f} ms / {N} frames {W}x{H}  -> {px/ms/1e6:.1f} Gpx/s, {6*px/ms/1e6:.0f} GB/s algorithmic, {N/ms*1e3:.0f} fps")
