@@ -111,6 +111,19 @@ class Engine:
         check(rc, "avb_dichromat_blur_u8")
         self.launches += 2 if norm == AVB_NORM_AUTO else 1
 
+    def streak_blur(self, frames, out, M: np.ndarray, streak, chroma: float = 0.0, norm=AVB_NORM_AUTO):
+        n, h, w, fs, rs = self.check_frames(frames)
+        _, _, _, ofs, ors = self.check_frames(out, "out")
+        M = np.ascontiguousarray(M, np.float32)
+        key = ("streak", h, M.tobytes(), tuple(float(v) for v in streak))
+        tab = self.cached(key, lambda: self._dev(tables.streak_row_table(h, M, *streak)))
+        rc = self.lib.avb_streak_blur_u8(
+            frames.data_ptr(), out.data_ptr(), n, h, w, fs, rs, ofs, ors,
+            self.dec.data_ptr(), self.dec_raw.data_ptr(), self.enc.data_ptr(), tab.data_ptr(), float(chroma),
+            norm, self.flags(n).data_ptr() if norm == AVB_NORM_AUTO else None, self.stream_ptr())
+        check(rc, "avb_streak_blur_u8")
+        self.launches += 2 if norm == AVB_NORM_AUTO else 1
+
     def cat(self, frames, out_human, out_cat, M: np.ndarray, taps: np.ndarray, warp_dev, zoom_dev, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, hfs, hrs = self.check_frames(out_human, "out_human")

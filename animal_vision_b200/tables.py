@@ -9,7 +9,7 @@ promotions and roundings) the reference evaluates per frame, then uploaded once 
   * Gaussian taps                         (cv2.getGaussianKernel as called by cv2.GaussianBlur)
   * cat wide-FOV per-column maps/weights  (animals/cat_widevision_utils.py:61-96)
   * centre-zoom fixed-point resize tables (cat_widevision_utils.py:11-29 -> cv2.resize INTER_LINEAR)
-  * streak-blur per-row taps              (animal_utils.py:147-172)
+  * streak-blur per-row taps + 3x3         (animal_utils.py:147-172)
   * S-cone row gain                       (animal_utils.py:236-247)
   * honeybee spectral tables              (classic_rgb_to_hsi.py:55-78, uv_helpers.py:187-192, honeybee.py:81-93,179-192)
 This is the safe route to <=1 LSB: the device only does per-pixel arithmetic.
@@ -194,42 +194,43 @@ def _reflect101(i: int, n: int) -> int:
     return p - m if m >= n else m
 
 
-STREAK_K1_MAX = 17    # taps of the sigmaX pass kept per row (sigmaX <= 2.0)
-STREAK_K2_MAX = 33    # taps of the sigmaY pass kept per row (sigmaY <= 4.0)
+STREAK_RMAX = 16      # combined radius limit of the device kernel (k2_streak.cu ST_RMAX)
+STREAK_TAB = 48       # floats per row: 33 taps (centred at index 16), 9 matrix entries, radius, pad
 
 
-def streak_tables(H: int, y_center: float, s_streak: float, s_far: float, falloff: float):
-    """Per-row tables for the streak blur as it actually behaves:
-      taps1 [H, K1_MAX] centred, zero padded (x blur with sigmaX(y)),
-      mix   [H, 9]      3x3 colour-channel mixing matrix of the same taps (REFLECT_101 over width 3),
-      taps2 [H, K2_MAX] centred, zero padded (x blur with sigmaY(y)),
-      radii [H, 2] int32."""
+def streak_row_table(H: int, M: np.ndarray, y_center: float, s_streak: float, s_far: float, falloff: float) -> np.ndarray:
+    """Per-row table [H, 48] float32 for the streak blur as it actually behaves:
+      [0:33]  the two x passes (taps of sigmaX(y), then taps of sigmaY(y)) composed into one
+              symmetric tap vector, centred at index 16, zero padded;
+      [33:42] row-major 3x3 = (REFLECT_101 channel mix of the sigmaX taps over a width of 3) @ M,
+              M being the species' dichromat matrix (applied as out = A @ lin);
+      [42]    combined radius r1 + r2.
+    Composed in float64 from the float32 taps OpenCV would use, rounded once."""
     sx, sy = streak_sigmas(H, y_center, s_streak, s_far, falloff)
-    taps1 = np.zeros((H, STREAK_K1_MAX), np.float32)
-    taps2 = np.zeros((H, STREAK_K2_MAX), np.float32)
-    mix = np.zeros((H, 9), np.float32)
-    radii = np.zeros((H, 2), np.int32)
+    tab = np.zeros((H, STREAK_TAB), np.float32)
+    M64 = np.asarray(M, np.float64)
     cache = {}
     for y in range(H):
         key = (sx[y], sy[y])
         if key not in cache:
             k1, k2 = gaussian_ksize(sx[y]), gaussian_ksize(sy[y])
-            if k1 > STREAK_K1_MAX or k2 > STREAK_K2_MAX:
-                raise ValueError(f"streak blur sigma too large for the kernel tables (ksize {k1}, {k2})")
-            g1, g2 = gaussian_taps(k1, sx[y]), gaussian_taps(k2, sy[y])
-            r1 = k1 // 2
-            m = np.zeros((3, 3), np.float64)
+            g1, g2 = gaussian_taps(k1, sx[y]).astype(np.float64), gaussian_taps(k2, sy[y]).astype(np.float64)
+            r1, r2 = k1 // 2, k2 // 2
+            if r1 + r2 > STREAK_RMAX:
+                raise ValueError(f"streak blur sigma too large for the device kernel (radius {r1}+{r2} > {STREAK_RMAX})")
+            mix = np.zeros((3, 3), np.float64)
             for c in range(3):
                 for t in range(k1):
-                    m[c, _reflect101(c + t - r1, 3)] += float(g1[t])
-            cache[key] = (g1, g2, m.astype(np.float32).ravel(), r1, k2 // 2)
-        g1, g2, m, r1, r2 = cache[key]
-        c1, c2 = STREAK_K1_MAX // 2, STREAK_K2_MAX // 2
-        taps1[y, c1 - r1:c1 + r1 + 1] = g1
-        taps2[y, c2 - r2:c2 + r2 + 1] = g2
-        mix[y] = m
-        radii[y] = (r1, r2)
-    return taps1, mix, taps2, radii
+                    mix[c, _reflect101(c + t - r1, 3)] += g1[t]
+            row = np.zeros(STREAK_TAB, np.float32)
+            comb = np.convolve(g1, g2)
+            r = r1 + r2
+            row[STREAK_RMAX - r:STREAK_RMAX + r + 1] = comb.astype(np.float32)
+            row[33:42] = (mix @ M64).astype(np.float32).ravel()
+            row[42] = float(r)
+            cache[key] = row
+        tab[y] = cache[key]
+    return tab
 
 
 def scone_row_gain(H: int, s_top=1.0, s_bottom=0.6, power=1.0, extra_boost=0.0) -> np.ndarray:

@@ -94,6 +94,23 @@ AVB_API int avb_dichromat_blur_u8(const uint8_t *in, uint8_t *out, int n, int H,
                           const float *m_host, const float *taps_host, int ksize,
                           int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
 
+/* K2s -- dichromat recipe with the per-row "streak" blur of the grazing mammals, one fused kernel:
+ * decode -> per-row 3x3 -> per-row horizontal correlation -> [chroma compression] -> clip -> encode.
+ * Replaces animals/cow.py:25-45 (and deer, goat, horse, kangaroo, sheep, panda, rabbit, pig), i.e.
+ * apply_anisotropic_acuity_blur_with_streak (animals/animal_utils.py:147-172) as it actually behaves
+ * (x blur + 3-wide colour-channel leak with sigmaX(y), x blur with sigmaY(y), never any vertical
+ * blur) and apply_chroma_compression (animal_utils.py:174-181).
+ *   row_tab_dev     H x 48 float32 (host-built: animal_vision_b200/tables.py streak_row_table):
+ *                   [0:33] combined x taps centred at 16, [33:42] row-major 3x3 (channel mix @ species
+ *                   matrix), [42] combined radius (<= 16)
+ *   chroma_strength 0 = no chroma compression (panda/rabbit: 0.06) */
+AVB_API int avb_streak_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                               int64_t in_frame_stride, int64_t in_row_stride,
+                               int64_t out_frame_stride, int64_t out_row_stride,
+                               const float *dec_dev, const float *dec_raw_dev, const uint32_t *enc_dev,
+                               const float *row_tab_dev, float chroma_strength,
+                               int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
+
 /* Cat -- both outputs of Cat.visualize (animals/cat.py:73-114, the runnable side of the merge
  * conflict) for a batch of frames:
  *   out_human  centre zoom (animals/cat_widevision_utils.py:11-29: crop + cv2.resize INTER_LINEAR on

@@ -9,6 +9,7 @@ from oracle import mammals as M
 pytestmark = pytest.mark.gpu
 
 GAUSS = ["dog", "bear", "lion", "tiger", "elephant", "fox", "wolf", "raccoon", "squirrel"]
+STREAK = ["cow", "deer", "goat", "horse", "kangaroo", "sheep", "panda", "rabbit", "pig"]
 
 
 def _species(name):
@@ -23,7 +24,7 @@ def _cmp(got, ref, what, max_frac=0.02):
     assert (d > 0).mean() <= max_frac, f"{what}: {(d > 0).mean():.4f} of bytes differ by 1 LSB"
 
 
-@pytest.mark.parametrize("name", GAUSS + ["rat"])
+@pytest.mark.parametrize("name", GAUSS + ["rat"] + STREAK)
 def test_against_golden(name, golden, golden_meta):
     h, w = golden_meta["small_hw"]
     fr = dict(frames.parity_set(h, w))
@@ -38,8 +39,8 @@ def test_against_golden(name, golden, golden_meta):
         _cmp(out, ref, key)
 
 
-@pytest.mark.parametrize("name", ["dog", "squirrel", "raccoon", "rat"])
-@pytest.mark.parametrize("hw", [(61, 67), (8, 200), (270, 480), (1, 5), (37, 1)])
+@pytest.mark.parametrize("name", ["dog", "squirrel", "raccoon", "rat", "cow", "panda", "pig"])
+@pytest.mark.parametrize("hw", [(61, 67), (8, 200), (270, 480), (1, 5), (37, 1), (40, 1100)])
 def test_against_oracle_odd_shapes(name, hw):
     h, w = hw
     sp = _species(name)
@@ -65,3 +66,19 @@ def test_dog_1080p_batch_and_strides():
     view = wide[:, :, 40:1960]
     _, out2 = Dog().visualize_batch(view)
     assert torch.equal(out2, out)
+
+
+def test_streak_1080p_batch_and_strides():
+    import torch
+    from animal_vision_b200.animals import Panda, Sheep
+    f0, f1 = frames.noise(1080, 1920, 1), frames.natural(1080, 1920)
+    batch = torch.from_numpy(np.stack([f0, f1])).cuda()
+    for cls, name in ((Sheep, "sheep"), (Panda, "panda")):
+        refs = [M.mammal_visualize(f, name)[1] for f in (f0, f1)]
+        _, out = cls().visualize_batch(batch)
+        for i in range(2):
+            _cmp(out[i].cpu().numpy(), refs[i], f"{name} 1080p frame {i}")
+        wide = torch.zeros((2, 1080, 2000, 3), dtype=torch.uint8, device="cuda")
+        wide[:, :, 39:1959] = batch                      # unaligned rows: scalar store path
+        _, out2 = cls().visualize_batch(wide[:, :, 39:1959])
+        assert torch.equal(out2, out)
