@@ -12,6 +12,7 @@ from ..engine import get_engine
 from .animal import Animal, run_single
 
 _ADAPT = {None: 0, "white_patch": 1, "gray_world": 2}
+_MAP = {"opponent": 0, "falsecolor": 1, "custom_matrix": 2, "uv_purple_yellow": 3, "falsecolor_uv_mixed": 4}   # AVB_MAP_*
 
 
 class HoneyBee(Animal):
@@ -45,8 +46,11 @@ class HoneyBee(Animal):
         self.UV_curve, self.Blue_curve, self.Green_curve = tables.honeybee_curves(self.lambdas)
         if adaptation not in _ADAPT:
             raise ValueError(f"Unknown adaptation: {adaptation}")
-        if mapping_mode != "opponent":
-            raise NotImplementedError(f"mapping_mode={mapping_mode!r}: only the default 'opponent' mapper runs on the GPU path so far")
+        if mapping_mode not in _MAP:
+            raise ValueError(f"Unknown mapping_mode: {mapping_mode}")                      # honeybee.py:163-164
+        if mapping_mode == "custom_matrix":
+            assert custom_matrix is not None and np.shape(custom_matrix) == (3, 3), \
+                "Provide custom_matrix as 3\u00d73 for 'custom_matrix' mode."                    # honeybee.py:153-156
         if self.hsi_downsample:
             raise NotImplementedError("hsi_downsample=True is not implemented on the GPU path (the default is False)")
         # pixel-independent spectral tables, built once with the reference's own expressions
@@ -55,6 +59,7 @@ class HoneyBee(Animal):
         self._band_tab, self._denom_eps = tables.uv_band_table(self.lambdas, sens, E)
         self._M3 = tables.uv_collapsed_matrix(self.lambdas, sens, E)
         self._taps = tables.uv_blur_taps(self.blur_sigma_px)
+        self._map_params = tables.uv_map_params(custom_matrix)
         if self._taps.size > 5:
             raise NotImplementedError("blur_sigma_px > 2/3 (ksize > 5) is not implemented on the GPU path")
 
@@ -62,7 +67,8 @@ class HoneyBee(Animal):
         bands = None
         if self.spectral_mode == "bands":
             bands = eng.cached(("bee_bands", id(self)), lambda: eng._dev(self._band_tab))
-        eng.uv_opponent(frames, out, self._M3, bands, self._denom_eps, _ADAPT[self.adaptation], self._taps, 95.0, dbg)
+        eng.uv_map(frames, out, self._M3, bands, self._denom_eps, _ADAPT[self.adaptation], self._taps,
+                   _MAP[self.mapping_mode], self._map_params, 0.45, dbg)       # honeybee.py:161: alpha=0.45
 
     def visualize_batch(self, frames, out=None):
         eng = get_engine(frames.device)

@@ -1,121 +1,339 @@
 // K3: the UV path -- RGB -> analytic 31-band spectrum -> photoreceptor catches -> von Kries
-// adaptation -> small acuity blur -> opponent (HSV-like) mapping with two GLOBAL 95th percentiles
-// -> sRGB encode, without ever materialising the H x W x 31 hyperspectral cube
-// (257 MB per 1080p frame in the reference: classic_rgb_to_hsi.py:47-82, honeybee.py:126-135).
+// adaptation -> small acuity blur -> (U,B,G) visualisation map with GLOBAL percentiles -> sRGB
+// encode, without ever materialising the H x W x 31 hyperspectral cube (257 MB per 1080p frame in
+// the reference: classic_rgb_to_hsi.py:47-82, honeybee.py:126-135).
 //
 // The global statistics force several passes over the frame; every pass RE-COMPUTES the receptor
-// catches from the uint8 input (3 B/px, L2-resident after the first pass) instead of round-tripping
-// fp32 planes through HBM:
-//   A  catches -> per-frame max (white patch) / sum (gray world)
-//   B1 adapted + blurred catches -> (radius, L) -> histogram of float bits [30:20]
-//   B2 ... bits [19:9] of the values sharing the rank's 11-bit prefix
-//   B3 ... bits [8:0]  -> the two order statistics around rank 0.95 (N-1), exact -> np.percentile
-//   C  catches -> hue/sat/val -> HSV->RGB -> clip -> OETF -> uint8
-// (a one-CTA "scan" kernel between the histogram passes turns counts into the next prefix).
+// catches from the uint8 input (3 B/px, L2-resident between passes for a frame group) instead of
+// round-tripping fp32 planes through HBM:
+//   stats    raw catches -> per-frame max and sum of each receptor          (white patch / gray world)
+//   prep     (1 thread per frame) fold the adaptation into the receptor matrix, size the bins
+//   hist     adapted + blurred catches -> mapper quantities -> 2048 linear bins per quantity
+//   scan     locate the bin(s) that hold the two order statistics of every percentile request
+//   collect  recompute, append the values that fall into those bins to a candidate list
+//   select   exact radix select among the candidates -> numpy.percentile(method="linear")
+//   map      recompute, apply the mapper, clip -> OETF -> uint8
+// The percentile is EXACT (same order statistics numpy picks), whatever the value distribution:
+// binning only decides how many candidates the select step sees.
 //
-// Receptor catches come either from the per-pixel 31-band sum in registers ("bands" mode, the
+// Pixel walk: one warp owns a strip of 120 output columns (lane l holds pixels 4l-4 .. 4l-1 of the
+// strip, three aligned 32-bit loads per row) and streams down 64 rows; horizontal blur neighbours
+// come from the adjacent lanes by shuffle, the vertical window lives in registers, so there is no
+// shared-memory tile, no __syncthreads and no per-pixel index arithmetic.
+//
+// Receptor catches come either from the per-pixel band sum in registers ("bands" mode, the
 // reference's own order of operations) or from the algebraically identical 3x3 (the whole chain
 // lobes -> illuminant -> sensitivities is linear; SURVEY.md 8a-11: 1.9e-7 relative difference).
 #include "avb_common.cuh"
 
 namespace avb {
 
-constexpr int UV_TW = 64, UV_TH = 16, UV_THREADS = 256;
-constexpr int UV_MAX_BANDS = 160;
 constexpr int UV_BINS = 2048;
-constexpr int UV_MAX_BLUR_R = 2;
+constexpr int UV_NH = 3;                 // histograms (mapper quantities) per frame
+constexpr int UV_NR = 4;                 // percentile requests per frame
+constexpr int UV_MAX_BANDS = 160;
+constexpr int UV_THREADS = 256, UV_WARPS = UV_THREADS / 32;
+constexpr int UV_RH = 64;                // output rows per strip
+constexpr unsigned FULL = 0xffffffffu;
 
-// per-frame statistics block in the caller's workspace
+enum { MAP_OPPONENT = 0, MAP_FALSECOLOR = 1, MAP_MATRIX = 2, MAP_PURPLE = 3, MAP_MIXED = 4 };
+enum { QS_OPP = 0, QS_UBG = 1, QS_U = 2 };   // which quantities feed the histograms
+
 struct UvFrameStats {
-    uint32_t max_bits[3];        // white patch: max of each raw catch (non-negative floats as bits)
+    uint32_t max_bits[3];
     uint32_t pad0;
-    double sum[3];               // gray world
-    uint32_t prefix[2][2];       // [quantity][lo/hi rank]: bits fixed so far
-    uint32_t remaining[2][2];    // rank within the current prefix
-    float pct[2];                // the two percentiles (radius, L)
-    uint32_t pad1[2];
-    uint32_t hist1[2][UV_BINS];          // level 1: [quantity]
-    uint32_t hist23[2][2][2][UV_BINS];   // levels 2,3: [level-2][quantity][lo/hi]
+    double sum[3];
+    float rcp[3];                // correctly rounded reciprocals of the adaptation divisors
+    float pad2[6];
+    float scale[3];              // adaptation divisors
+    float inv_w[UV_NH];          // bins per unit value
+    uint32_t bin_lo[UV_NR], bin_hi[UV_NR], rank_lo[UV_NR], rank_hi[UV_NR], cand_count[UV_NR];
+    float pct[UV_NR];
+    uint32_t pad1;
 };
+static_assert(sizeof(UvFrameStats) % 8 == 0, "stats block must stay 8-byte aligned");
 
 struct UvParams {
     FrameIO io;
     const float *lut;            // decode LUT (device, 256)
     float M3[9];                 // collapsed receptor matrix: catch k = sum_c M3[3k+c] * lin[c]
-    const float *bands;          // bands mode: [B][8] = g0,g1,g2 (lobe of input channel c), E, s0,s1,s2 (sensitivities), 0
+    const float *bands;          // bands mode: [B][8] = g0,g1,g2 (lobe of input channel c), E, s0,s1,s2, 0
     int n_bands;                 // 0 -> collapsed mode
     float denom_eps;             // lobe normaliser + 1e-8 (float32, as torch computes it)
     int adapt;                   // 0 none, 1 white patch (max), 2 gray world (mean)
     float eps;                   // 1e-8
-    int blur_r;                  // 0..2
-    float blur_taps[2 * UV_MAX_BLUR_R + 1];
+    float t0, t1, t2;            // blur taps: centre, +-1, +-2
     UvFrameStats *stats;         // [n]
+    uint32_t *hist;              // [n][UV_NH][UV_BINS]
+    float *cand;                 // [n][n_req][cap]
+    long long cap;
     const uint32_t *enc;
-    long long k_lo, k_hi;        // order-statistic ranks of the percentile
-    double gamma;                // interpolation weight
+    int n_req;
+    int req_hist[UV_NR];
+    long long k_lo[UV_NR], k_hi[UV_NR];
+    double gamma[UV_NR];
+    int mapper;
+    float map_m[9];              // MAP_MATRIX
+    float anchors[6];            // MAP_PURPLE / MAP_MIXED: linear-light purple and warm anchors
+    float mix_alpha;             // MAP_MIXED
     float *dbg_catches;          // optional [n][H][W][3] raw catches (test hook), else nullptr
+    int aligned_in, aligned_out; // rows / frames 4-byte aligned -> 32-bit pixel-group accesses
+    int strips_x, strips_y;
 };
+
+// x / s with r = RN(1/s): one Newton correction on the quotient (Markstein) gives the correctly
+// rounded IEEE quotient for the value ranges here (no overflow / underflow), in 3 instructions.
+// Exactness matters: a flat frame must adapt to exactly 1.0 in every receptor, as it does in the
+// reference, or the opponent radius stops being exactly 0.
+__device__ __forceinline__ float div_by(float x, float s, float r) {
+    const float q = __fmul_rn(x, r);
+    return fmaf(fmaf(-q, s, x), r, q);
+}
 
 // ------------------------------------------------------------------ per-pixel receptor catches
 struct Catcher {
     const float *lut_s;
-    const UvParams *p;
-    __device__ __forceinline__ void raw(const uint8_t *q, float &u, float &b, float &g) const {
-        const float c0 = lut_s[q[0]], c1 = lut_s[q[1]], c2 = lut_s[q[2]];
-        if (p->n_bands == 0) {
-            u = p->M3[0] * c0 + p->M3[1] * c1 + p->M3[2] * c2;
-            b = p->M3[3] * c0 + p->M3[4] * c1 + p->M3[5] * c2;
-            g = p->M3[6] * c0 + p->M3[7] * c1 + p->M3[8] * c2;
+    float m[9];
+    const float4 *bands;
+    int n_bands;
+    float denom_eps;
+    float sc[3], rc[3];
+    bool divide;
+
+    __device__ __forceinline__ void init_raw(const UvParams &p, const float *lut) {
+        lut_s = lut;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = p.M3[i];
+        bands = reinterpret_cast<const float4 *>(p.bands);
+        n_bands = p.n_bands;
+        denom_eps = p.denom_eps;
+        sc[0] = sc[1] = sc[2] = 1.f;
+        rc[0] = rc[1] = rc[2] = 1.f;
+        divide = false;
+    }
+    __device__ __forceinline__ void init_adapted(const UvParams &p, const UvFrameStats &st, const float *lut) {
+        init_raw(p, lut);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sc[k] = st.scale[k]; rc[k] = st.rcp[k]; }
+        divide = p.adapt != 0;
+    }
+    __device__ __forceinline__ void operator()(uint32_t b0, uint32_t b1, uint32_t b2, float &u, float &b, float &g) const {
+        const float c0 = lut_s[b0], c1 = lut_s[b1], c2 = lut_s[b2];
+        if (n_bands == 0) {
+            u = m[0] * c0 + m[1] * c1 + m[2] * c2;
+            b = m[3] * c0 + m[4] * c1 + m[5] * c2;
+            g = m[6] * c0 + m[7] * c1 + m[8] * c2;
+            if (divide) {      // uv_helpers.py:195-206: x / scale, correctly rounded (see div_by)
+                u = div_by(u, sc[0], rc[0]);
+                b = div_by(b, sc[1], rc[1]);
+                g = div_by(g, sc[2], rc[2]);
+            }
         } else {
             // classic_rgb_to_hsi.py:70-78, honeybee.py:126-135 in the reference's own order:
             // spec = (g2*c2 + g1*c1 + g0*c0) / (denom+1e-8);  rad = spec * E;  catch += rad * s
             float au = 0.f, ab = 0.f, ag = 0.f;
-            const float4 *t = reinterpret_cast<const float4 *>(p->bands);
-            for (int l = 0; l < p->n_bands; ++l) {
-                const float4 lo = __ldg(t + 2 * l), hi = __ldg(t + 2 * l + 1);
+            for (int l = 0; l < n_bands; ++l) {
+                const float4 lo = __ldg(bands + 2 * l), hi = __ldg(bands + 2 * l + 1);
                 float spec = __fadd_rn(__fadd_rn(__fmul_rn(lo.z, c2), __fmul_rn(lo.y, c1)), __fmul_rn(lo.x, c0));
-                spec = fmaxf(__fdiv_rn(spec, p->denom_eps), 0.f);
+                spec = fmaxf(__fdiv_rn(spec, denom_eps), 0.f);
                 const float rad = __fmul_rn(spec, lo.w);
                 au = fmaf(rad, hi.x, au);
                 ab = fmaf(rad, hi.y, ab);
                 ag = fmaf(rad, hi.z, ag);
+            }
+            if (divide) {      // uv_helpers.py:195-206: divide by the global max / mean
+                au = __fdiv_rn(au, sc[0]);
+                ab = __fdiv_rn(ab, sc[1]);
+                ag = __fdiv_rn(ag, sc[2]);
             }
             u = au; b = ab; g = ag;
         }
     }
 };
 
-__device__ __forceinline__ void adapt_scales(const UvParams &p, const UvFrameStats &st, long long npx, float (&w)[3]) {
+__device__ __forceinline__ uint32_t byte_k(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 + k); }
+
+// 4 packed pixels (three 32-bit words) -> catches
+__device__ __forceinline__ void catches4(const Catcher &cat, const uint32_t (&w)[3], float (&c)[4][3]) {
+    cat(byte_k(w[0], 0), byte_k(w[0], 1), byte_k(w[0], 2), c[0][0], c[0][1], c[0][2]);
+    cat(byte_k(w[0], 3), byte_k(w[1], 0), byte_k(w[1], 1), c[1][0], c[1][1], c[1][2]);
+    cat(byte_k(w[1], 2), byte_k(w[1], 3), byte_k(w[2], 0), c[2][0], c[2][1], c[2][2]);
+    cat(byte_k(w[2], 1), byte_k(w[2], 2), byte_k(w[2], 3), c[3][0], c[3][1], c[3][2]);
+}
+
+// ------------------------------------------------------------------ the strip walk
+// Calls op(y, gx, v, ok) once per output row for every lane: v[j][k] = adapted + blurred catch k of
+// pixel (y, gx + j); ok is false for the two halo lanes.  All 32 lanes call op together.
+template <int R, class Op>
+__device__ __forceinline__ void uv_walk(const UvParams &p, const Catcher &cat, const uint8_t *src, int xs, int ys, int rows, Op &op) {
+    constexpr int OFF = R ? 4 : 0;
+    constexpr int NWIN = 2 * R + 1;
+    const int lane = threadIdx.x & 31;
+    const int H = p.io.H, W = p.io.W;
+    const int gx = xs - OFF + 4 * lane;
+    const bool fast = p.aligned_in && gx >= 0 && gx + 3 < W;
+    int xi[4];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (p.adapt == 1) w[k] = fmaxf(__uint_as_float(st.max_bits[k]), p.eps);          // uv_helpers.py:195-199
-        else if (p.adapt == 2) w[k] = fmaxf((float)(st.sum[k] / (double)npx), p.eps);    // uv_helpers.py:202-206
-        else w[k] = 1.0f;
+    for (int j = 0; j < 4; ++j) xi[j] = 3 * reflect101(gx + j, W);
+    const bool lane_ok = (R == 0) || (lane >= 1 && lane <= 30);
+
+    auto load = [&](int i, uint32_t(&w)[3]) {
+        const uint8_t *row = src + (int64_t)reflect101(ys + i, H) * p.io.in_rs;
+        if (fast) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 3 * gx);
+            w[0] = __ldg(q); w[1] = __ldg(q + 1); w[2] = __ldg(q + 2);
+        } else {
+            uint32_t b[12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t *q = row + xi[j];
+                b[3 * j] = q[0]; b[3 * j + 1] = q[1]; b[3 * j + 2] = q[2];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
+        }
+    };
+
+    float win[NWIN][4][3];
+    uint32_t w[3], wn[3] = {0u, 0u, 0u};
+    const int n_iter = rows + 2 * R;
+    const float t0 = p.t0, t1 = p.t1, t2 = p.t2;
+    load(-R, w);
+    for (int i0 = 0; i0 < n_iter; i0 += NWIN) {
+#pragma unroll
+        for (int ph = 0; ph < NWIN; ++ph) {
+            const int i = i0 + ph;                 // iteration i reads input row ys + i - R
+            if (i < n_iter) {
+                if (i + 1 < n_iter) load(i + 1 - R, wn);
+                float c[4][3];
+                catches4(cat, w, c);
+                if (R == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) win[0][j][k] = c[j][k];
+                } else {
+                    // horizontal pass (rows first, as cv2.GaussianBlur): neighbours from adjacent lanes
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float e[8];
+                        e[1] = __shfl_up_sync(FULL, c[3][k], 1);
+                        e[6] = __shfl_down_sync(FULL, c[0][k], 1);
+                        if (R == 2) {
+                            e[0] = __shfl_up_sync(FULL, c[2][k], 1);
+                            e[7] = __shfl_down_sync(FULL, c[1][k], 1);
+                        } else {
+                            e[0] = e[7] = 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) e[2 + j] = c[j][k];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float a = fmaf(t1, e[1 + j] + e[3 + j], t0 * e[2 + j]);
+                            if (R == 2) a = fmaf(t2, e[j] + e[4 + j], a);
+                            win[ph][j][k] = a;
+                        }
+                    }
+                }
+                if (i >= 2 * R) {
+                    float v[4][3];
+                    if (R == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) v[j][k] = win[0][j][k];
+                    } else {
+                        constexpr int C = NWIN;   // slot of iteration i - d is (ph - d) mod NWIN
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                float a = fmaf(t1, win[(ph - R + 1 + C) % C][j][k] + win[(ph - R - 1 + 2 * C) % C][j][k],
+                                               t0 * win[(ph - R + C) % C][j][k]);
+                                if (R == 2) a = fmaf(t2, win[(ph - R + 2 + C) % C][j][k] + win[(ph - R - 2 + 2 * C) % C][j][k], a);
+                                v[j][k] = a;
+                            }
+                    }
+                    op(ys + i - 2 * R, gx, v, lane_ok);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[k] = wn[k];
+            }
+        }
     }
 }
 
-// ------------------------------------------------------------------ pass A: maxima / sums
+// strip task -> (xs, ys, rows)
+template <int R>
+__device__ __forceinline__ void strip_of(const UvParams &p, int task, int &xs, int &ys, int &rows) {
+    constexpr int SW = R ? 120 : 128;
+    const int sy = task / p.strips_x, sx = task - sy * p.strips_x;
+    xs = sx * SW;
+    ys = sy * UV_RH;
+    rows = min(UV_RH, p.io.H - ys);
+}
+
+// ------------------------------------------------------------------ mapper quantities
+template <int QS>
+__device__ __forceinline__ void quantities(const float (&c)[3], float (&q)[UV_NH]) {
+    if (QS == QS_OPP) {
+        // uv_mappers.py:55-60
+        const float O1 = c[2] - c[1], O2 = c[1] - c[0];
+        q[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        q[1] = __fdiv_rn(__fadd_rn(__fadd_rn(c[0], c[1]), c[2]), 3.0f);
+        q[2] = 0.f;
+    } else {
+        q[0] = c[0]; q[1] = c[1]; q[2] = c[2];
+    }
+}
+template <int QS>
+struct QCount { static constexpr int value = QS == QS_OPP ? 2 : (QS == QS_UBG ? 3 : 1); };
+
+__device__ __forceinline__ int bin_of(float v, float inv_w) {
+    return min(UV_BINS - 1, max(0, __float2int_rd(v * inv_w)));
+}
+
+// ------------------------------------------------------------------ stats: maxima / sums of raw catches
 __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __ldg(p.lut + i);
     __syncthreads();
     const int frame = blockIdx.y;
     const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
-    Catcher cat{lut_s, &p};
+    Catcher cat;
+    cat.init_raw(p, lut_s);
     float mx[3] = {0.f, 0.f, 0.f};
     double sm[3] = {0.0, 0.0, 0.0};
-    const int W = p.io.W;
-    const long long npx = (long long)p.io.H * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
-        float u, b, g;
-        cat.raw(src + (int64_t)y * p.io.in_rs + 3 * x, u, b, g);
-        if (p.dbg_catches) {
-            float *d = p.dbg_catches + ((int64_t)frame * npx + i) * 3;
-            d[0] = u; d[1] = b; d[2] = g;
+    const int W = p.io.W, H = p.io.H;
+    const int groups = (W + 3) >> 2;
+    for (int y = blockIdx.x; y < H; y += gridDim.x) {
+        const uint8_t *row = src + (int64_t)y * p.io.in_rs;
+        float rs[3] = {0.f, 0.f, 0.f};
+        for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+            const int gx = 4 * gi;
+            float c[4][3];
+            int npx = min(4, W - gx);
+            if (p.aligned_in && npx == 4) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 3 * gx);
+                const uint32_t w[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)};
+                catches4(cat, w, c);
+            } else {
+                for (int j = 0; j < npx; ++j) cat(row[3 * (gx + j)], row[3 * (gx + j) + 1], row[3 * (gx + j) + 2], c[j][0], c[j][1], c[j][2]);
+            }
+            for (int j = 0; j < npx; ++j) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    mx[k] = fmaxf(mx[k], c[j][k]);
+                    rs[k] += c[j][k];
+                }
+                if (p.dbg_catches) {
+                    float *d = p.dbg_catches + (((int64_t)frame * H + y) * W + gx + j) * 3;
+                    d[0] = c[j][0]; d[1] = c[j][1]; d[2] = c[j][2];
+                }
+            }
         }
-        mx[0] = fmaxf(mx[0], u); mx[1] = fmaxf(mx[1], b); mx[2] = fmaxf(mx[2], g);
-        sm[0] += u; sm[1] += b; sm[2] += g;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sm[k] += (double)rs[k];     // float partial per (thread,row): <= ~W/1024 terms
     }
     UvFrameStats &st = p.stats[frame];
 #pragma unroll
@@ -124,281 +342,561 @@ __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ U
         double s = sm[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            s += __shfl_xor_sync(0xffffffffu, s, o);
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+            s += __shfl_xor_sync(FULL, s, o);
         }
         if ((threadIdx.x & 31) == 0) {
-            if (p.adapt == 1) atomicMax(&st.max_bits[k], __float_as_uint(fmaxf(m, 0.f)));
-            if (p.adapt == 2) atomicAdd(&st.sum[k], s);
+            atomicMax(&st.max_bits[k], __float_as_uint(fmaxf(m, 0.f)));
+            atomicAdd(&st.sum[k], s);
         }
     }
 }
 
-// ------------------------------------------------------------------ tile machinery for passes B*, C
-// A CTA owns a UV_TW x UV_TH tile; adapted catches for the tile plus a blur_r halo (REFLECT_101)
-// go to shared memory, then every thread blurs and maps its pixels.
-struct UvTile {
-    float *pl;       // [3][TH+2r][TW+2r] planes
-    int pw, ph, r;
-};
-
-template <int PASS>   // 1,2,3: histogram level; 4: map + encode
-__global__ void __launch_bounds__(UV_THREADS) uv_tile_kernel(const __grid_constant__ UvParams p) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    float *lut_s = reinterpret_cast<float *>(smem_raw);
-    float *pl = lut_s + 256;
-    const int r = p.blur_r;
-    const int pw = UV_TW + 2 * r, ph = UV_TH + 2 * r;
-    uint32_t *tail = reinterpret_cast<uint32_t *>(pl + 3 * pw * ph);   // histograms (B) or encode table + stage (C)
-
-    const int tid = threadIdx.x;
-    const int frame = blockIdx.z;
-    const int H = p.io.H, W = p.io.W;
-    const int x0 = blockIdx.x * UV_TW, y0 = blockIdx.y * UV_TH;
-    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
+// ------------------------------------------------------------------ prep: adaptation + bin widths
+template <int QS>
+__global__ void uv_prep_kernel(const __grid_constant__ UvParams p) {
+    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= p.io.n) return;
     UvFrameStats &st = p.stats[frame];
-    const long long npx = (long long)H * W;
-
-    for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
-    constexpr int NH = (PASS == 1) ? 2 : 4;
-    if (PASS <= 3) {
-        for (int i = tid; i < NH * UV_BINS; i += UV_THREADS) tail[i] = 0;
+    const double npx = (double)p.io.H * (double)p.io.W;
+    float ub[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float mx = __uint_as_float(st.max_bits[k]);
+        float s = 1.0f;
+        if (p.adapt == 1) s = fmaxf(mx, p.eps);                                  // uv_helpers.py:195-199
+        else if (p.adapt == 2) s = fmaxf((float)(st.sum[k] / npx), p.eps);       // uv_helpers.py:202-206
+        st.scale[k] = s;
+        st.rcp[k] = __frcp_rn(s);
+        ub[k] = mx / s * 1.001f + 1e-30f;
+    }
+    float hb[UV_NH];
+    if (QS == QS_OPP) {
+        const float a = fmaxf(ub[2], ub[1]), b = fmaxf(ub[1], ub[0]);
+        hb[0] = sqrtf(a * a + b * b) * 1.001f;
+        hb[1] = (ub[0] + ub[1] + ub[2]) * (1.001f / 3.0f);
+        hb[2] = 1.f;
     } else {
-        copy_to_smem(tail, p.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.enc + 2)));
+        hb[0] = ub[0]; hb[1] = ub[1]; hb[2] = ub[2];
     }
-    __syncthreads();
-
-    float ws[3];
-    adapt_scales(p, st, npx, ws);
-    Catcher cat{lut_s, &p};
-    for (int i = tid; i < pw * ph; i += UV_THREADS) {
-        const int ty = i / pw, tx = i - ty * pw;
-        const int y = reflect101(y0 - r + ty, H), x = reflect101(x0 - r + tx, W);
-        float u, b, g;
-        cat.raw(src + (int64_t)y * p.io.in_rs + 3 * x, u, b, g);
-        pl[i] = __fdiv_rn(u, ws[0]);
-        pl[pw * ph + i] = __fdiv_rn(b, ws[1]);
-        pl[2 * pw * ph + i] = __fdiv_rn(g, ws[2]);
-    }
-    __syncthreads();
-
-    float pr = 0.f, pL = 0.f;
-    EncTable enc{};
-    uint8_t *stage = nullptr;
-    if (PASS == 4) {
-        pr = st.pct[0] + p.eps;      // uv_mappers.py:61-62: percentile + eps, float32
-        pL = st.pct[1] + p.eps;
-        enc = enc_view(tail);
-        stage = reinterpret_cast<uint8_t *>(tail + AVB_ENC_TABLE_MAX);
-    }
-    uint32_t pre[2][2];
-    if (PASS == 2 || PASS == 3) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int t = 0; t < 2; ++t) pre[q][t] = st.prefix[q][t];
-    }
+    for (int h = 0; h < UV_NH; ++h) st.inv_w[h] = (float)UV_BINS / fmaxf(hb[h], 1e-30f);
+}
 
-    for (int i = tid; i < UV_TW * UV_TH; i += UV_THREADS) {
-        const int ty = i / UV_TW, tx = i - ty * UV_TW;
-        const int y = y0 + ty, x = x0 + tx;
-        const bool inside = (y < H) && (x < W);
-        float c[3];
+// ------------------------------------------------------------------ hist
+template <int QS>
+struct HistOp {
+    uint32_t *hs;
+    float inv_w[UV_NH];
+    int W;
+    __device__ __forceinline__ void operator()(int /*y*/, int gx, const float (&v)[4][3], bool ok) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float *q = pl + k * pw * ph + (ty + r) * pw + (tx + r);
-            if (r == 0) {
-                c[k] = q[0];
-            } else {
-                // separable correlation, rows (x) first then columns, as cv2.GaussianBlur does
-                float acc = 0.f;
-                for (int dy = -r; dy <= r; ++dy) {
-                    float row = 0.f;
-                    for (int dx = -r; dx <= r; ++dx) row = fmaf(p.blur_taps[dx + r], q[dy * pw + dx], row);
-                    acc = fmaf(p.blur_taps[dy + r], row, acc);
-                }
-                c[k] = acc;
+        for (int j = 0; j < 4; ++j) {
+            if (ok && gx + j < W) {
+                float q[UV_NH];
+                quantities<QS>(v[j], q);
+#pragma unroll
+                for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[h], inv_w[h])], 1u);
             }
         }
-        // uv_mappers.py:53-60
-        const float U = c[0], B = c[1], G = c[2];
-        const float O1 = G - B, O2 = B - U;
-        const float L = __fdiv_rn(__fadd_rn(__fadd_rn(U, B), G), 3.0f);
-        const float radius = sqrtf(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
-        if (PASS <= 3) {
-            if (inside) {
-                const uint32_t bits[2] = {__float_as_uint(fmaxf(radius, 0.f)), __float_as_uint(fmaxf(L, 0.f))};
+    }
+};
+
+template <int QS, int R>
+__global__ void __launch_bounds__(UV_THREADS, 2) uv_hist_kernel(const __grid_constant__ UvParams p) {
+    __shared__ float lut_s[256];
+    __shared__ uint32_t hs[QCount<QS>::value * UV_BINS];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
+    for (int i = tid; i < QCount<QS>::value * UV_BINS; i += UV_THREADS) hs[i] = 0u;
+    __syncthreads();
+    const UvFrameStats &st = p.stats[frame];
+    Catcher cat;
+    cat.init_adapted(p, st, lut_s);
+    HistOp<QS> op;
+    op.hs = hs;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (PASS == 1) {
-                        atomicAdd(&tail[q * UV_BINS + (bits[q] >> 20)], 1u);
-                    } else {
+    for (int h = 0; h < UV_NH; ++h) op.inv_w[h] = st.inv_w[h];
+    op.W = p.io.W;
+    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
+    const int tasks = p.strips_x * p.strips_y;
+    for (int task = blockIdx.x * UV_WARPS + (tid >> 5); task < tasks; task += gridDim.x * UV_WARPS) {
+        int xs, ys, rows;
+        strip_of<R>(p, task, xs, ys, rows);
+        uv_walk<R>(p, cat, src, xs, ys, rows, op);
+    }
+    __syncthreads();
+    uint32_t *gh = p.hist + (int64_t)frame * UV_NH * UV_BINS;
+    for (int i = tid; i < QCount<QS>::value * UV_BINS; i += UV_THREADS) {
+        const uint32_t c = hs[i];
+        if (c) atomicAdd(gh + i, c);
+    }
+}
+
+// ------------------------------------------------------------------ scan: counts -> candidate bins
+__global__ void __launch_bounds__(256) uv_scan_kernel(const __grid_constant__ UvParams p) {
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    UvFrameStats &st = p.stats[frame];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t res[4];      // bin_lo, below_lo, bin_hi, unused
+    constexpr int PER = UV_BINS / 256;
+    for (int r = 0; r < p.n_req; ++r) {
+        const uint32_t *h = p.hist + ((int64_t)frame * UV_NH + p.req_hist[r]) * UV_BINS;
+        const uint32_t k_lo = (uint32_t)p.k_lo[r], k_hi = (uint32_t)p.k_hi[r];
+        uint32_t loc[PER], s = 0;
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (PASS == 2) {
-                                if ((bits[q] >> 20) == pre[q][t]) atomicAdd(&tail[(q * 2 + t) * UV_BINS + ((bits[q] >> 9) & 0x7ffu)], 1u);
-                            } else {
-                                if ((bits[q] >> 9) == pre[q][t]) atomicAdd(&tail[(q * 2 + t) * UV_BINS + (bits[q] & 0x1ffu)], 1u);
-                            }
-                        }
+        for (int j = 0; j < PER; ++j) { loc[j] = h[tid * PER + j]; s += loc[j]; }
+        part[tid] = s;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int i = 0; i < 256; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        }
+        __syncthreads();
+        uint32_t run = part[tid];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (k_lo >= run && k_lo < run + loc[j]) { res[0] = tid * PER + j; res[1] = run; }
+            if (k_hi >= run && k_hi < run + loc[j]) res[2] = tid * PER + j;
+            run += loc[j];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            st.bin_lo[r] = res[0];
+            st.bin_hi[r] = res[2];
+            st.rank_lo[r] = k_lo - res[1];
+            st.rank_hi[r] = k_hi - res[1];
+            st.cand_count[r] = 0u;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ collect
+template <int QS>
+struct CollectOp {
+    UvFrameStats *st;
+    float *cand;                 // this frame's [n_req][cap]
+    long long cap;
+    float inv_w[UV_NH];
+    int n_req, W;
+    int req_hist[UV_NR];
+    int lo[UV_NR], hi[UV_NR];
+    __device__ __forceinline__ void operator()(int /*y*/, int gx, const float (&v)[4][3], bool ok) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool valid = ok && gx + j < W;
+            float q[UV_NH];
+            quantities<QS>(v[j], q);
+            int bins[UV_NH];
+#pragma unroll
+            for (int h = 0; h < UV_NH; ++h) bins[h] = bin_of(q[h], inv_w[h]);
+#pragma unroll
+            for (int r = 0; r < UV_NR; ++r) {
+                if (r < n_req) {
+                    const int h = req_hist[r];
+                    const int b = h == 0 ? bins[0] : (h == 1 ? bins[1] : bins[2]);
+                    const float val = h == 0 ? q[0] : (h == 1 ? q[1] : q[2]);
+                    const bool hit = valid && b >= lo[r] && b <= hi[r];
+                    const unsigned m = __ballot_sync(FULL, hit);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(&st->cand_count[r], (uint32_t)__popc(m));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (hit) cand[(long long)r * cap + base + __popc(m & ((1u << lane) - 1u))] = fmaxf(val, 0.f) + 0.f;
                     }
                 }
             }
-        } else {
-            // hue / sat / val and hsv_to_rgb (uv_mappers.py:14-26, :57-64)
-            const float PI_F = 3.14159274101257324f;          // float32(np.pi)
-            const float hue = __fdiv_rn(__fadd_rn(atan2f(O2, O1), PI_F), 6.28318548202514648f);
-            const float sat = __saturatef(__fdiv_rn(radius, pr));
-            const float val = __saturatef(__fdiv_rn(L, pL));
-            const float h6 = __fmul_rn(hue, 6.0f);
-            const float fl = floorf(h6);
-            const float f = h6 - fl;
-            int sext = (int)fl % 6;
-            if (sext < 0) sext += 6;
-            // NumPy promotes f = h*6 - int32 to float64, so q and t are float64 products rounded
-            // once by the final astype(float32); p stays float32 (uv_mappers.py:18-21, :64)
-            const float pp_ = __fmul_rn(val, __fsub_rn(1.0f, sat));
-            const float qq = (float)((double)val * (1.0 - (double)f * (double)sat));
-            const float tt = (float)((double)val * (1.0 - (1.0 - (double)f) * (double)sat));
-            float R_, G_, B_;
-            switch (sext) {
-                case 0: R_ = val; G_ = tt; B_ = pp_; break;
-                case 1: R_ = qq; G_ = val; B_ = pp_; break;
-                case 2: R_ = pp_; G_ = val; B_ = tt; break;
-                case 3: R_ = pp_; G_ = qq; B_ = val; break;
-                case 4: R_ = tt; G_ = pp_; B_ = val; break;
-                default: R_ = val; G_ = pp_; B_ = qq; break;
-            }
-            stage[i * 3 + 0] = (uint8_t)encode_u8(enc, R_);
-            stage[i * 3 + 1] = (uint8_t)encode_u8(enc, G_);
-            stage[i * 3 + 2] = (uint8_t)encode_u8(enc, B_);
         }
     }
-    __syncthreads();
+};
 
-    if (PASS <= 3) {
-        uint32_t *gh = (PASS == 1) ? &st.hist1[0][0] : &st.hist23[PASS - 2][0][0][0];
-        for (int i = tid; i < NH * UV_BINS; i += UV_THREADS) {
-            const uint32_t v = tail[i];
-            if (v) atomicAdd(gh + i, v);
+template <int QS, int R>
+__global__ void __launch_bounds__(UV_THREADS, 2) uv_collect_kernel(const __grid_constant__ UvParams p) {
+    __shared__ float lut_s[256];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
+    __syncthreads();
+    UvFrameStats &st = p.stats[frame];
+    Catcher cat;
+    cat.init_adapted(p, st, lut_s);
+    CollectOp<QS> op;
+    op.st = &st;
+    op.cand = p.cand + (long long)frame * p.n_req * p.cap;
+    op.cap = p.cap;
+    op.n_req = p.n_req;
+    op.W = p.io.W;
+#pragma unroll
+    for (int h = 0; h < UV_NH; ++h) op.inv_w[h] = st.inv_w[h];
+#pragma unroll
+    for (int r = 0; r < UV_NR; ++r) {
+        op.req_hist[r] = p.req_hist[r];
+        op.lo[r] = (int)st.bin_lo[r];
+        op.hi[r] = (int)st.bin_hi[r];
+    }
+    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
+    const int tasks = p.strips_x * p.strips_y;
+    for (int task = blockIdx.x * UV_WARPS + (tid >> 5); task < tasks; task += gridDim.x * UV_WARPS) {
+        int xs, ys, rows;
+        strip_of<R>(p, task, xs, ys, rows);
+        uv_walk<R>(p, cat, src, xs, ys, rows, op);
+    }
+}
+
+// ------------------------------------------------------------------ select: exact order statistics
+// One CTA per (request, frame): three-level radix select (11 + 11 + 10 bits of the non-negative
+// float patterns) for the lower order statistic, one more sweep for the upper one, then the linear
+// interpolation numpy.percentile does.
+constexpr int SEL_THREADS = 1024;
+
+__device__ __forceinline__ void sel_find(const uint32_t *h, int nbins, uint32_t rank, uint32_t *scratch, uint32_t *out /*bin, rem*/) {
+    // h: smem histogram (nbins <= 2048); every thread owns 2 bins; block-wide exclusive scan
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t a = (2 * tid < nbins) ? h[2 * tid] : 0u, b = (2 * tid + 1 < nbins) ? h[2 * tid + 1] : 0u;
+    uint32_t s = a + b, inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = scratch[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, iv, o);
+            if (lane >= o) iv += t;
         }
+        scratch[lane] = iv - v;          // exclusive warp offsets
+    }
+    __syncthreads();
+    const uint32_t run = scratch[wid] + inc - s;
+    if (rank >= run && rank < run + a) { out[0] = 2 * tid; out[1] = rank - run; }
+    else if (rank >= run + a && rank < run + s) { out[0] = 2 * tid + 1; out[1] = rank - run - a; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) uv_select_kernel(const __grid_constant__ UvParams p) {
+    const int r = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    UvFrameStats &st = p.stats[frame];
+    __shared__ uint32_t h[UV_BINS];
+    __shared__ uint32_t scratch[32];
+    __shared__ uint32_t found[2];
+    __shared__ uint32_t cnt_le, min_gt;
+    const uint32_t cnt = st.cand_count[r];
+    const uint32_t *vals = reinterpret_cast<const uint32_t *>(p.cand + ((long long)frame * p.n_req + r) * p.cap);
+    uint32_t rank = st.rank_lo[r];
+    uint32_t prefix = 0;
+    const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
+    for (int lv = 0; lv < 3; ++lv) {
+        for (int i = tid; i < UV_BINS; i += SEL_THREADS) h[i] = 0u;
+        __syncthreads();
+        const int sh = shifts[lv], nb = nbits[lv];
+        const uint32_t mask = (1u << nb) - 1u;
+        for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+            const uint32_t b = vals[i];
+            if (lv == 0 || (b >> (sh + nb)) == prefix) atomicAdd(&h[(b >> sh) & mask], 1u);
+        }
+        __syncthreads();
+        sel_find(h, 1 << nb, rank, scratch, found);
+        prefix = (prefix << nb) | found[0];
+        rank = found[1];
+        __syncthreads();
+    }
+    const uint32_t a_bits = prefix;
+    if (tid == 0) { cnt_le = 0u; min_gt = 0xffffffffu; }
+    __syncthreads();
+    uint32_t le = 0, mg = 0xffffffffu;
+    for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+        const uint32_t b = vals[i];
+        if (b <= a_bits) ++le; else mg = min(mg, b);
+    }
+    atomicAdd(&cnt_le, le);
+    atomicMin(&min_gt, mg);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t b_bits = a_bits;
+        if (st.rank_hi[r] >= cnt_le && min_gt != 0xffffffffu) b_bits = min_gt;
+        const double a = (double)__uint_as_float(a_bits), b = (double)__uint_as_float(b_bits);
+        st.pct[r] = (float)(a + (b - a) * p.gamma[r]);      // numpy _lerp with a float64 weight
+    }
+}
+
+// ------------------------------------------------------------------ map
+struct MapConsts {
+    float pr, pL;                 // opponent: percentile + eps
+    float d95[3], d98;            // falsecolor / purple: max(percentile, eps)
+    float c0[3], c1[3], pd[3];    // purple / warm anchors (linear light, host-computed) and accent direction
+    float m[9];
+    float alpha;
+};
+
+__device__ __forceinline__ void falsecolor(const float (&c)[3], const MapConsts &k, float (&rgb)[3]) {
+    // uv_mappers.py:29-43 (python-float coefficients act as float32)
+    const float Un = __fdiv_rn(c[0], k.d95[0]), Bn = __fdiv_rn(c[1], k.d95[1]), Gn = __fdiv_rn(c[2], k.d95[2]);
+    rgb[0] = __saturatef(__fadd_rn(__fmul_rn(0.85f, Un), __fmul_rn(0.10f, Gn)));
+    rgb[1] = __saturatef(__fadd_rn(__fmul_rn(0.80f, Gn), __fmul_rn(0.20f, Bn)));
+    rgb[2] = __saturatef(__fadd_rn(__fmul_rn(0.70f, Bn), __fmul_rn(0.40f, Un)));
+}
+
+__device__ __forceinline__ void purple_soft(float U, const MapConsts &k, float (&rgb)[3]) {
+    // uv_mappers.py:90-132 with the defaults u_gamma .90, accent_gamma .85, accent_strength .05
+    const float u = powf(__saturatef(__fdiv_rn(U, k.d98)), 0.90f);
+    const float w = powf(u, 0.85f);
+    float y = 0.f;
+    const float yc[3] = {0.2126f, 0.7152f, 0.0722f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, u), k.c0[i]), __fmul_rn(u, k.c1[i]));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(0.05f, w), k.pd[i]));
+        rgb[i] = v;
+    }
+    y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(yc[0], rgb[0]), __fmul_rn(yc[1], rgb[1])), __fmul_rn(yc[2], rgb[2])), 1e-8f);
+    const float yt = __saturatef(__fadd_rn(0.22f, __fmul_rn(0.55f, u)));
+    const float gain = fminf(fmaxf(__fdiv_rn(yt, y), 0.6f), 1.6f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float v = __fmul_rn(rgb[i], gain);
+        rgb[i] = __saturatef(__fdiv_rn(v, __fadd_rn(1.0f, __fmul_rn(0.6f, v))));
+    }
+}
+
+template <int MAPPER>
+__device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &k, float (&rgb)[3]) {
+    if (MAPPER == MAP_OPPONENT) {
+        // uv_mappers.py:53-64 and hsv_to_rgb :14-26
+        const float U = c[0], B = c[1], G = c[2];
+        const float O1 = G - B, O2 = B - U;
+        const float L = __fdiv_rn(__fadd_rn(__fadd_rn(U, B), G), 3.0f);
+        const float radius = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        const float PI_F = 3.14159274101257324f;          // float32(np.pi)
+        const float hue = __fdiv_rn(__fadd_rn(atan2f(O2, O1), PI_F), 6.28318548202514648f);
+        const float sat = __saturatef(__fdiv_rn(radius, k.pr));
+        const float val = __saturatef(__fdiv_rn(L, k.pL));
+        const float h6 = __fmul_rn(hue, 6.0f);
+        const float fl = floorf(h6);
+        const float f = h6 - fl;                           // exact
+        int sext = (int)fl % 6;
+        if (sext < 0) sext += 6;
+        // NumPy evaluates q and t in float64 (f = h*6 - int32 promotes) and rounds once; one fused
+        // multiply-add keeps the float32 evaluation within an ulp of that
+        const float pp = __fmul_rn(val, __fsub_rn(1.0f, sat));
+        const float qq = __fmul_rn(val, fmaf(-f, sat, 1.0f));
+        const float tt = __fmul_rn(val, fmaf(-(1.0f - f), sat, 1.0f));
+        switch (sext) {
+            case 0: rgb[0] = val; rgb[1] = tt; rgb[2] = pp; break;
+            case 1: rgb[0] = qq; rgb[1] = val; rgb[2] = pp; break;
+            case 2: rgb[0] = pp; rgb[1] = val; rgb[2] = tt; break;
+            case 3: rgb[0] = pp; rgb[1] = qq; rgb[2] = val; break;
+            case 4: rgb[0] = tt; rgb[1] = pp; rgb[2] = val; break;
+            default: rgb[0] = val; rgb[1] = pp; rgb[2] = qq; break;
+        }
+    } else if (MAPPER == MAP_FALSECOLOR) {
+        falsecolor(c, k, rgb);
+    } else if (MAPPER == MAP_MATRIX) {
+        // uv_mappers.py:45-50: [U,B,G] @ M.T
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rgb[i] = k.m[3 * i] * c[0] + k.m[3 * i + 1] * c[1] + k.m[3 * i + 2] * c[2];
+    } else if (MAPPER == MAP_PURPLE) {
+        purple_soft(c[0], k, rgb);
     } else {
-        uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs;
-        const bool vec_ok = (x0 + UV_TW <= W) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
-        if (vec_ok) {
-            constexpr int VPR = UV_TW * 3 / 16;
-            for (int i = tid; i < UV_TH * VPR; i += UV_THREADS) {
-                const int ty = i / VPR, q = i - ty * VPR;
-                if (y0 + ty < H)
-                    *reinterpret_cast<uint4 *>(dst + (int64_t)(y0 + ty) * p.io.out_rs + (int64_t)x0 * 3 + q * 16) =
-                        reinterpret_cast<const uint4 *>(stage + ty * UV_TW * 3)[q];
-            }
+        // uv_mappers.py:135-144; the trailing P99 normalisation divides by max(1, p99) and every
+        // mixed value is <= 1, so it is the identity
+        float a[3], b[3];
+        falsecolor(c, k, a);
+        purple_soft(c[0], k, b);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rgb[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, k.alpha), a[i]), __fmul_rn(k.alpha, b[i]));
+    }
+}
+
+template <int MAPPER>
+struct MapOp {
+    MapConsts k;
+    EncTable enc;
+    uint8_t *dst;
+    int64_t out_rs;
+    int W;
+    bool aligned;
+    __device__ __forceinline__ void operator()(int y, int gx, const float (&v)[4][3], bool ok) {
+        if (!ok || gx >= W) return;
+        uint32_t by[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float rgb[3];
+            map_pixel<MAPPER>(v[j], k, rgb);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) by[3 * j + i] = encode_u8(enc, rgb[i]);
+        }
+        uint8_t *o = dst + (int64_t)y * out_rs + 3 * gx;
+        if (aligned && gx + 3 < W) {
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
         } else {
-            const int nbytes = min(UV_TW, W - x0) * 3;
-            for (int i = tid; i < UV_TH * UV_TW * 3; i += UV_THREADS) {
-                const int ty = i / (UV_TW * 3), b = i - ty * (UV_TW * 3);
-                if (y0 + ty < H && b < nbytes) dst[(int64_t)(y0 + ty) * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[i];
-            }
+            const int nb = 3 * min(4, W - gx);
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                if (q < nb) o[q] = (uint8_t)by[q];
         }
     }
-}
+};
 
-// ------------------------------------------------------------------ scan: counts -> next prefix
-// One CTA per frame.  LEVEL 1: from hist1 pick, for each quantity and each of the two ranks, the
-// bin holding that rank.  LEVEL 2/3: same inside hist23.  After LEVEL 3 the full 31-bit patterns
-// of both order statistics are known and the percentile is their linear interpolation
-// (numpy.percentile, method "linear").
-template <int LEVEL>
-__global__ void __launch_bounds__(256) uv_scan_kernel(const __grid_constant__ UvParams p) {
-    UvFrameStats &st = p.stats[blockIdx.x];
-    __shared__ uint32_t part[256];
-    __shared__ uint32_t found_bin[2][2], found_rem[2][2];
-    const int tid = threadIdx.x;
-    constexpr int PER = UV_BINS / 256;
-    for (int q = 0; q < 2; ++q)
-        for (int t = 0; t < 2; ++t) {
-            const uint32_t *h = (LEVEL == 1) ? st.hist1[q] : st.hist23[LEVEL - 2][q][t];
-            const uint32_t rank = (LEVEL == 1) ? (uint32_t)(t == 0 ? p.k_lo : p.k_hi) : st.remaining[q][t];
-            uint32_t loc[PER], s = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) { loc[j] = h[tid * PER + j]; s += loc[j]; }
-            part[tid] = s;
-            __syncthreads();
-            // exclusive prefix over the 256 partial sums (serial in one thread: 256 adds, negligible)
-            if (tid == 0) {
-                uint32_t run = 0;
-                for (int i = 0; i < 256; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
-            }
-            __syncthreads();
-            uint32_t run = part[tid];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                if (rank >= run && rank < run + loc[j]) { found_bin[q][t] = tid * PER + j; found_rem[q][t] = rank - run; }
-                run += loc[j];
-            }
-            __syncthreads();
-        }
-    if (tid < 4) {
-        const int q = tid >> 1, t = tid & 1;
-        const uint32_t bin = found_bin[q][t];
-        if (LEVEL == 1) st.prefix[q][t] = bin;
-        else if (LEVEL == 2) st.prefix[q][t] = (st.prefix[q][t] << 11) | bin;
-        else st.prefix[q][t] = (st.prefix[q][t] << 9) | bin;
-        st.remaining[q][t] = found_rem[q][t];
-    }
+template <int MAPPER, int R>
+__global__ void __launch_bounds__(UV_THREADS, 2) uv_map_kernel(const __grid_constant__ UvParams p) {
+    __shared__ float lut_s[256];
+    __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
+    copy_to_smem(enc_s, p.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.enc + 2)));
     __syncthreads();
-    if (LEVEL == 3 && tid < 2) {
-        const double a = (double)__uint_as_float(st.prefix[tid][0]), b = (double)__uint_as_float(st.prefix[tid][1]);
-        st.pct[tid] = (float)(a + (b - a) * p.gamma);
+    const UvFrameStats &st = p.stats[frame];
+    Catcher cat;
+    cat.init_adapted(p, st, lut_s);
+    MapOp<MAPPER> op;
+    op.enc = enc_view(enc_s);
+    op.dst = p.io.out + (int64_t)frame * p.io.out_fs;
+    op.out_rs = p.io.out_rs;
+    op.W = p.io.W;
+    op.aligned = p.aligned_out != 0;
+    MapConsts &k = op.k;
+    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
+    k.pL = st.pct[1] + p.eps;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) k.d95[i] = fmaxf(st.pct[i], p.eps);
+    k.d98 = fmaxf(MAPPER == MAP_PURPLE ? st.pct[0] : st.pct[3], p.eps);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        k.c0[i] = p.anchors[i];
+        k.c1[i] = p.anchors[3 + i];
+        k.pd[i] = __fsub_rn(k.c0[i], 0.5f);
+        k.m[3 * i] = p.map_m[3 * i]; k.m[3 * i + 1] = p.map_m[3 * i + 1]; k.m[3 * i + 2] = p.map_m[3 * i + 2];
+    }
+    k.alpha = p.mix_alpha;
+    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
+    const int tasks = p.strips_x * p.strips_y;
+    for (int task = blockIdx.x * UV_WARPS + (tid >> 5); task < tasks; task += gridDim.x * UV_WARPS) {
+        int xs, ys, rows;
+        strip_of<R>(p, task, xs, ys, rows);
+        uv_walk<R>(p, cat, src, xs, ys, rows, op);
     }
 }
 
-static size_t uv_tile_smem(int r, int pass) {
-    const int pw = UV_TW + 2 * r, ph = UV_TH + 2 * r;
-    size_t s = (256 + 3 * (size_t)pw * ph) * 4;
-    if (pass == 1) s += 2 * UV_BINS * 4;
-    else if (pass <= 3) s += 4 * UV_BINS * 4;
-    else s += AVB_ENC_TABLE_MAX * 4 + UV_TW * UV_TH * 3;
-    return s;
+// ------------------------------------------------------------------ launch plumbing
+static int qset_of(int mapper) {
+    switch (mapper) {
+        case MAP_OPPONENT: return QS_OPP;
+        case MAP_PURPLE: return QS_U;
+        default: return QS_UBG;
+    }
 }
 
-template <int PASS>
-static int launch_tile(const UvParams &p, cudaStream_t st) {
-    const size_t smem = uv_tile_smem(p.blur_r, PASS);
-    AVB_CUDA_OK(cudaFuncSetAttribute(uv_tile_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((p.io.W + UV_TW - 1) / UV_TW, (p.io.H + UV_TH - 1) / UV_TH, p.io.n);
-    static const char *names[5] = {"", "k3_uv_hist1", "k3_uv_hist2", "k3_uv_hist3", "k3_uv_map"};
-    AVB_TIMED(names[PASS], st);
-    uv_tile_kernel<PASS><<<grid, UV_THREADS, smem, st>>>(p);
+static dim3 walk_grid(const UvParams &p, int per_sm) {
+    const int tasks = p.strips_x * p.strips_y;
+    int bx = (tasks + UV_WARPS - 1) / UV_WARPS;
+    const int cap = (sm_count() * per_sm + p.io.n - 1) / p.io.n;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    return dim3(bx, p.io.n);
+}
+
+template <int QS, int R>
+static int launch_percentiles(const UvParams &p, cudaStream_t st) {
+    {
+        AVB_TIMED("k3_uv_hist", st);
+        uv_hist_kernel<QS, R><<<walk_grid(p, 4), UV_THREADS, 0, st>>>(p);
+    }
+    {
+        AVB_TIMED("k3_uv_scan", st);
+        uv_scan_kernel<<<p.io.n, 256, 0, st>>>(p);
+    }
+    {
+        AVB_TIMED("k3_uv_collect", st);
+        uv_collect_kernel<QS, R><<<walk_grid(p, 8), UV_THREADS, 0, st>>>(p);
+    }
+    {
+        AVB_TIMED("k3_uv_select", st);
+        uv_select_kernel<<<dim3(p.n_req, p.io.n), SEL_THREADS, 0, st>>>(p);
+    }
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }
+
+template <int MAPPER, int R>
+static int launch_mapper(const UvParams &p, cudaStream_t st) {
+    constexpr int QS = MAPPER == MAP_OPPONENT ? QS_OPP : (MAPPER == MAP_PURPLE ? QS_U : QS_UBG);
+    {
+        AVB_TIMED("k3_uv_prep", st);
+        uv_prep_kernel<QS><<<(p.io.n + 63) / 64, 64, 0, st>>>(p);
+    }
+    if (p.n_req > 0)
+        if (int e = launch_percentiles<QS, R>(p, st)) return e;
+    {
+        AVB_TIMED("k3_uv_map", st);
+        const int tasks = p.strips_x * p.strips_y;
+        uv_map_kernel<MAPPER, R><<<dim3((tasks + UV_WARPS - 1) / UV_WARPS, p.io.n), UV_THREADS, 0, st>>>(p);
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+template <int R>
+static int dispatch_mapper(const UvParams &p, cudaStream_t st) {
+    switch (p.mapper) {
+        case MAP_OPPONENT: return launch_mapper<MAP_OPPONENT, R>(p, st);
+        case MAP_FALSECOLOR: return launch_mapper<MAP_FALSECOLOR, R>(p, st);
+        case MAP_MATRIX: return launch_mapper<MAP_MATRIX, R>(p, st);
+        case MAP_PURPLE: return launch_mapper<MAP_PURPLE, R>(p, st);
+        default: return launch_mapper<MAP_MIXED, R>(p, st);
+    }
+}
+
+static int n_requests(int mapper) {
+    switch (mapper) {
+        case MAP_OPPONENT: return 2;
+        case MAP_FALSECOLOR: return 3;
+        case MAP_MATRIX: return 0;
+        case MAP_PURPLE: return 1;
+        default: return 4;
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace avb
 
 using namespace avb;
 
-extern "C" int64_t avb_uv_workspace_bytes(int n) { return n > 0 ? (int64_t)n * (int64_t)sizeof(UvFrameStats) : 0; }
+extern "C" int64_t avb_uv_workspace_bytes(int n, int H, int W, int map_mode) {
+    if (n <= 0 || H <= 0 || W <= 0 || map_mode < 0 || map_mode > MAP_MIXED) return 0;
+    const size_t stats = align_up((size_t)n * sizeof(UvFrameStats), 256);
+    const size_t hist = (size_t)n * UV_NH * UV_BINS * sizeof(uint32_t);
+    const size_t cand = (size_t)n * n_requests(map_mode) * (size_t)H * W * sizeof(float);
+    return (int64_t)(stats + hist + cand);
+}
 
-extern "C" int avb_uv_opponent_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
-                                  int64_t in_frame_stride, int64_t in_row_stride,
-                                  int64_t out_frame_stride, int64_t out_row_stride,
-                                  const float *dec_dev, const uint32_t *enc_dev,
-                                  const float *m3_host, const float *bands_dev, int n_bands, float denom_eps,
-                                  int adapt_mode, const float *blur_taps_host, int blur_ksize, float percentile,
-                                  void *workspace_dev, float *dbg_catches_dev, avb_stream_t stream) {
+extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                             int64_t in_frame_stride, int64_t in_row_stride,
+                             int64_t out_frame_stride, int64_t out_row_stride,
+                             const float *dec_dev, const uint32_t *enc_dev,
+                             const float *m3_host, const float *bands_dev, int n_bands, float denom_eps,
+                             int adapt_mode, const float *blur_taps_host, int blur_ksize,
+                             int map_mode, const float *map_params_host, float mix_alpha,
+                             void *workspace_dev, float *dbg_catches_dev, avb_stream_t stream) {
     UvParams p{};
     p.io = FrameIO{in, out, in_frame_stride, in_row_stride, out_frame_stride, out_row_stride, n, H, W};
     AVB_REQUIRE(in && out, "null frame pointer");
     AVB_REQUIRE(n > 0 && H > 0 && W > 0, "bad frame geometry");
+    AVB_REQUIRE(n <= 65535, "batch too large for one launch");
     AVB_REQUIRE(in_row_stride >= 3LL * W && out_row_stride >= 3LL * W, "row stride smaller than 3*W");
     AVB_REQUIRE(dec_dev && enc_dev && m3_host && workspace_dev, "null table / workspace pointer");
     AVB_REQUIRE(n_bands >= 0 && n_bands <= UV_MAX_BANDS && (n_bands == 0 || bands_dev), "bad band table");
     AVB_REQUIRE(adapt_mode >= 0 && adapt_mode <= 2, "adapt_mode must be 0 (none), 1 (white patch) or 2 (gray world)");
-    AVB_REQUIRE(blur_ksize == 0 || ((blur_ksize & 1) && blur_ksize <= 2 * UV_MAX_BLUR_R + 1 && blur_taps_host),
-                "blur ksize must be 0, 3 or 5");
-    AVB_REQUIRE(percentile >= 0.f && percentile <= 100.f, "percentile out of range");
+    AVB_REQUIRE(blur_ksize == 0 || ((blur_ksize == 3 || blur_ksize == 5) && blur_taps_host), "blur ksize must be 0, 3 or 5");
+    AVB_REQUIRE(map_mode >= 0 && map_mode <= MAP_MIXED, "unknown map_mode");
+    AVB_REQUIRE(map_mode == MAP_OPPONENT || map_mode == MAP_FALSECOLOR || map_params_host, "this map_mode needs map_params_host");
     AVB_REQUIRE((long long)H * W < (1LL << 31), "frame too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.lut = dec_dev;
@@ -409,31 +907,57 @@ extern "C" int avb_uv_opponent_u8(const uint8_t *in, uint8_t *out, int n, int H,
     p.denom_eps = denom_eps;
     p.adapt = adapt_mode;
     p.eps = 1e-8f;
-    p.blur_r = blur_ksize / 2;
-    for (int i = 0; i < blur_ksize; ++i) p.blur_taps[i] = blur_taps_host[i];
-    p.stats = static_cast<UvFrameStats *>(workspace_dev);
+    const int R = blur_ksize / 2;
+    p.t0 = 1.f; p.t1 = 0.f; p.t2 = 0.f;
+    if (R >= 1) { p.t0 = blur_taps_host[R]; p.t1 = blur_taps_host[R + 1]; }
+    if (R >= 2) p.t2 = blur_taps_host[R + 2];
+    p.mapper = map_mode;
+    if (map_params_host) {
+        for (int i = 0; i < 9; ++i) p.map_m[i] = map_params_host[i];
+        for (int i = 0; i < 6; ++i) p.anchors[i] = map_params_host[9 + i];
+    }
+    p.mix_alpha = mix_alpha;
     p.dbg_catches = dbg_catches_dev;
-    // numpy.percentile(method="linear"): virtual index q/100 * (N-1)
-    const long long npx = (long long)H * W;
-    const double vi = ((double)percentile / 100.0) * (double)(npx - 1);
-    p.k_lo = (long long)vi;
-    p.k_hi = p.k_lo + 1 < npx ? p.k_lo + 1 : p.k_lo;
-    p.gamma = vi - (double)p.k_lo;
+    p.aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_frame_stride | (uintptr_t)in_row_stride) & 3) == 0;
+    p.aligned_out = ((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_frame_stride | (uintptr_t)out_row_stride) & 3) == 0;
+    const int SW = R ? 120 : 128;
+    p.strips_x = (W + SW - 1) / SW;
+    p.strips_y = (H + UV_RH - 1) / UV_RH;
 
-    AVB_CUDA_OK(cudaMemsetAsync(workspace_dev, 0, sizeof(UvFrameStats) * (size_t)n, st));
-    if (adapt_mode != 0 || dbg_catches_dev) {
-        const long long blocks = (npx + 256 * 8 - 1) / (256 * 8);
-        dim3 grid((unsigned)(blocks < 4096 ? blocks : 4096), n);
+    // workspace: stats | histograms | candidate lists
+    const long long npx = (long long)H * W;
+    uint8_t *ws = static_cast<uint8_t *>(workspace_dev);
+    const size_t stats_bytes = align_up((size_t)n * sizeof(UvFrameStats), 256);
+    const size_t hist_bytes = (size_t)n * UV_NH * UV_BINS * sizeof(uint32_t);
+    p.stats = reinterpret_cast<UvFrameStats *>(ws);
+    p.hist = reinterpret_cast<uint32_t *>(ws + stats_bytes);
+    p.cand = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes);
+    p.cap = npx;
+
+    // percentile requests (numpy.percentile(method="linear"): virtual index q/100 * (N-1))
+    p.n_req = n_requests(map_mode);
+    const int qs = qset_of(map_mode);
+    const double pcts[5][UV_NR] = {{95, 95, 0, 0}, {95, 95, 95, 0}, {0, 0, 0, 0}, {98, 0, 0, 0}, {95, 95, 95, 98}};
+    const int hists[5][UV_NR] = {{0, 1, 0, 0}, {0, 1, 2, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 0}};
+    (void)qs;
+    for (int r = 0; r < p.n_req; ++r) {
+        const double vi = (pcts[map_mode][r] / 100.0) * (double)(npx - 1);
+        p.req_hist[r] = hists[map_mode][r];
+        p.k_lo[r] = (long long)vi;
+        p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
+        p.gamma[r] = vi - (double)p.k_lo[r];
+    }
+
+    AVB_CUDA_OK(cudaMemsetAsync(ws, 0, stats_bytes + hist_bytes, st));
+    {
+        dim3 grid((unsigned)(H < 1024 ? H : 1024), n);
         AVB_TIMED("k3_uv_stats", st);
         uv_stats_kernel<<<grid, 256, 0, st>>>(p);
         AVB_CUDA_OK(cudaGetLastError());
     }
-    if (int e = launch_tile<1>(p, st)) return e;
-    { AVB_TIMED("k3_uv_scan", st); uv_scan_kernel<1><<<n, 256, 0, st>>>(p); }
-    if (int e = launch_tile<2>(p, st)) return e;
-    { AVB_TIMED("k3_uv_scan", st); uv_scan_kernel<2><<<n, 256, 0, st>>>(p); }
-    if (int e = launch_tile<3>(p, st)) return e;
-    { AVB_TIMED("k3_uv_scan", st); uv_scan_kernel<3><<<n, 256, 0, st>>>(p); }
-    AVB_CUDA_OK(cudaGetLastError());
-    return launch_tile<4>(p, st);
+    switch (R) {
+        case 0: return dispatch_mapper<0>(p, st);
+        case 1: return dispatch_mapper<1>(p, st);
+        default: return dispatch_mapper<2>(p, st);
+    }
 }

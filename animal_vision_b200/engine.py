@@ -137,24 +137,30 @@ class Engine:
         check(rc, "avb_cat_u8")
         self.launches += 3 if norm == AVB_NORM_AUTO else 2
 
-    def uv_opponent(self, frames, out, M3: np.ndarray, bands_dev, denom_eps: float, adapt_mode: int,
-                    blur_taps: np.ndarray, percentile: float = 95.0, dbg_catches=None):
+    def uv_map(self, frames, out, M3: np.ndarray, bands_dev, denom_eps: float, adapt_mode: int,
+               blur_taps: np.ndarray, map_mode: int = 0, map_params=None, mix_alpha: float = 0.45, dbg_catches=None):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, ofs, ors = self.check_frames(out, "out")
-        need = int(self.lib.avb_uv_workspace_bytes(n))
+        need = int(self.lib.avb_uv_workspace_bytes(n, h, w, int(map_mode)))
+        if need <= 0:
+            raise AvbError("avb_uv_workspace_bytes: bad arguments")
         ws = self._cache.get("uv_ws")
         if ws is None or ws.numel() < need:
+            self._cache["uv_ws"] = None
             ws = self._cache["uv_ws"] = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
         M3 = np.ascontiguousarray(M3, np.float32)
         taps = np.ascontiguousarray(blur_taps, np.float32)
-        rc = self.lib.avb_uv_opponent_u8(
+        mp = None if map_params is None else np.ascontiguousarray(map_params, np.float32)
+        assert mp is None or mp.size == 15
+        rc = self.lib.avb_uv_map_u8(
             frames.data_ptr(), out.data_ptr(), n, h, w, fs, rs, ofs, ors,
             self.dec_torch.data_ptr(), self.enc.data_ptr(), _fptr(M3),
             None if bands_dev is None else bands_dev.data_ptr(), 0 if bands_dev is None else int(bands_dev.shape[0]),
-            float(denom_eps), int(adapt_mode), _fptr(taps) if taps.size else None, int(taps.size), float(percentile),
+            float(denom_eps), int(adapt_mode), _fptr(taps) if taps.size else None, int(taps.size),
+            int(map_mode), None if mp is None else _fptr(mp), float(mix_alpha),
             ws.data_ptr(), None if dbg_catches is None else dbg_catches.data_ptr(), self.stream_ptr())
-        check(rc, "avb_uv_opponent_u8")
-        self.launches += 8 if adapt_mode else 7
+        check(rc, "avb_uv_map_u8")
+        self.launches += 3 + (4 if map_mode != 2 else 0)      # stats, prep, [hist, scan, collect, select], map
 
     # ------------------------------------------------------------------ NumPy shim staging
     def staging(self, shape, slots: int = 1):

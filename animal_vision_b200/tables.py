@@ -309,6 +309,21 @@ def uv_blur_taps(sigma: float) -> np.ndarray:
     return gaussian_taps(int(2 * np.ceil(3 * sigma) + 1), sigma)
 
 
+def uv_map_params(custom_matrix=None) -> np.ndarray:
+    """15 floats for avb_uv_map_u8: [0:9] the custom 3x3 (uv_mappers.py:45-50, applied as C @ M.T),
+    [9:12] / [12:15] the purple and warm anchors of map_uv_purple_yellow_soft in linear light
+    (uv_mappers.py:107-116, same NumPy expressions)."""
+    out = np.zeros(15, np.float32)
+    if custom_matrix is not None:
+        out[:9] = np.asarray(custom_matrix, np.float32).reshape(9)
+
+    def s2l(v):
+        return np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / (1 + 0.055)) ** 2.4).astype(np.float32)
+    out[9:12] = s2l(np.array([176, 124, 232], np.float32) / 255.0)
+    out[12:15] = s2l(np.array([255, 211, 138], np.float32) / 255.0)
+    return out
+
+
 def bandpass_weights(lam: np.ndarray, lo: float, hi: float) -> np.ndarray:
     """uv_helpers.py:125-139 (uniform 1/B fallback when the band holds no sample / no mass)."""
     wl = lam.astype(np.float32)

@@ -133,30 +133,43 @@ AVB_API int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_cat, 
                        const float *warp_dev, const int32_t *zoom_dev,
                        int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
 
-/* K3 -- the UV path, HoneyBee.visualize with mapping_mode="opponent" (animals/honeybee.py:99-175):
+/* K3 -- the UV path, HoneyBee.visualize (animals/honeybee.py:99-175):
  * RGB -> analytic 31-band spectrum (ml/classic_rgb_to_hsi/classic_rgb_to_hsi.py:47-82) -> x illuminant
  * (uv_helpers.py:187-192) -> three receptor catches (honeybee.py:133-135) -> von Kries adaptation
- * (uv_helpers.py:195-206) -> acuity blur (uv_helpers.py:67-73) -> map_opponent with two global
- * percentiles (uv_mappers.py:53-64, :14-26) -> clip -> OETF -> uint8 (honeybee.py:166-173).
- * The H x W x B cube is never written: catches are (re)computed per pixel in registers.
+ * (uv_helpers.py:195-206) -> acuity blur (uv_helpers.py:67-73) -> (U,B,G) visualisation map with its
+ * global percentiles (uv_mappers.py:29-144) -> clip -> OETF -> uint8 (honeybee.py:166-173).
+ * The H x W x B cube is never written: catches are (re)computed per pixel in registers; the
+ * percentiles are the exact order statistics numpy.percentile(method="linear") interpolates.
  *   dec_dev        256 float32 decode LUT (uint8 -> /255 -> torch sRGB decode)
  *   m3_host        9 floats: catches = M3 @ lin  (spectral chain collapsed to 3x3); used when n_bands == 0
  *   bands_dev      n_bands x 8 float32 rows {g0,g1,g2, E, s0,s1,s2, 0}: lobe of input channel c,
  *                  illuminant, receptor sensitivities; n_bands > 0 selects the per-pixel band loop
  *   denom_eps      lobe normaliser + 1e-8 (float32)
  *   adapt_mode     0 none, 1 white patch (global max), 2 gray world (global mean)
- *   blur_taps_host ksize taps (0, 3 or 5)
- *   percentile     95.0 for the reference's map_opponent
- *   workspace_dev  avb_uv_workspace_bytes(n) bytes of scratch (zeroed by the call)
+ *   blur_taps_host ksize taps (ksize 0, 3 or 5)
+ *   map_mode       AVB_MAP_*: uv_mappers.py map_opponent :53-64 (P95 radius, P95 L), map_falsecolor
+ *                  :29-43 (P95 x3), map_linear_matrix :45-50, map_uv_purple_yellow_soft :90-132 (P98),
+ *                  map_falsecolor_uv_mixed :135-144
+ *   map_params_host 15 floats (may be NULL for opponent / falsecolor): [0:9] row-major matrix of
+ *                  AVB_MAP_MATRIX, [9:12] / [12:15] linear-light purple / warm anchors of the
+ *                  purple-yellow map (uv_mappers.py:107-116, evaluated by the host in NumPy)
+ *   mix_alpha      blend weight of AVB_MAP_MIXED (honeybee.py:161 passes 0.45)
+ *   workspace_dev  avb_uv_workspace_bytes(n, H, W, map_mode) bytes of scratch
  *   dbg_catches_dev NULL, or n*H*W*3 float32: raw receptor catches (test hook for the 1e-5 check) */
-AVB_API int64_t avb_uv_workspace_bytes(int n);
-AVB_API int avb_uv_opponent_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
-                               int64_t in_frame_stride, int64_t in_row_stride,
-                               int64_t out_frame_stride, int64_t out_row_stride,
-                               const float *dec_dev, const uint32_t *enc_dev,
-                               const float *m3_host, const float *bands_dev, int n_bands, float denom_eps,
-                               int adapt_mode, const float *blur_taps_host, int blur_ksize, float percentile,
-                               void *workspace_dev, float *dbg_catches_dev, avb_stream_t stream);
+#define AVB_MAP_OPPONENT 0
+#define AVB_MAP_FALSECOLOR 1
+#define AVB_MAP_MATRIX 2
+#define AVB_MAP_PURPLE_YELLOW 3
+#define AVB_MAP_MIXED 4
+AVB_API int64_t avb_uv_workspace_bytes(int n, int H, int W, int map_mode);
+AVB_API int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
+                          int64_t in_frame_stride, int64_t in_row_stride,
+                          int64_t out_frame_stride, int64_t out_row_stride,
+                          const float *dec_dev, const uint32_t *enc_dev,
+                          const float *m3_host, const float *bands_dev, int n_bands, float denom_eps,
+                          int adapt_mode, const float *blur_taps_host, int blur_ksize,
+                          int map_mode, const float *map_params_host, float mix_alpha,
+                          void *workspace_dev, float *dbg_catches_dev, avb_stream_t stream);
 
 #ifdef __cplusplus
 }

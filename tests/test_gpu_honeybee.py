@@ -74,3 +74,48 @@ def test_bee_options_and_batch():
             srgb = uv.encode_srgb_f32(np.clip(uv.map_opponent(U, B, G), 0.0, 1.0))
             ref = (srgb * 255.0 + 0.5).astype(np.uint8)
             _cmp(out[i].cpu().numpy(), ref, f"{kw}/batch[{i}]")
+
+
+def test_bee_other_mappers_against_golden(golden, golden_meta):
+    """uv_mappers.py falsecolor / purple-yellow / mixed / custom matrix (honeybee.py:150-164)."""
+    from animal_vision_b200.animals import HoneyBee
+    h, w = golden_meta["small_hw"]
+    g = golden("honeybee")
+    fr = dict(frames.parity_set(h, w))
+    n = 0
+    for key, ref in g.items():
+        mode, adapt, case = key.split("/")
+        if mode == "opponent":
+            continue
+        kw = {}
+        if mode == "custom_matrix":
+            kw["custom_matrix"] = np.array([[0.9, 0.1, 0.0], [0.0, 0.3, 0.8], [0.5, 0.5, 0.1]], np.float32)
+        _, out = HoneyBee(mapping_mode=mode, adaptation=adapt, **kw).visualize(fr[case])
+        _cmp(out, ref, key)
+        n += 1
+    assert n >= 10
+
+
+@pytest.mark.parametrize("mode", ["falsecolor", "uv_purple_yellow", "falsecolor_uv_mixed", "custom_matrix"])
+def test_bee_other_mappers_against_oracle(mode):
+    from animal_vision_b200.animals import HoneyBee
+    M = np.array([[0.6, 0.2, 0.1], [0.1, 0.5, 0.3], [0.3, 0.1, 0.6]], np.float32)
+    kw = {"custom_matrix": M} if mode == "custom_matrix" else {}
+    for (h, w) in ((61, 67), (270, 480)):
+        for name, f in frames.parity_set(h, w):
+            _, ref = uv.honeybee_visualize(f, mapping_mode=mode, **kw)
+            _, out = HoneyBee(mapping_mode=mode, **kw).visualize(f)
+            _cmp(out, ref, f"{mode}/{name}/{h}x{w}")
+
+
+def test_bee_degenerate_frames_keep_exact_percentiles():
+    """Constant / two-valued frames put every pixel into one histogram bin: the candidate list then
+    holds the whole frame and the select step must still return numpy's order statistics."""
+    from animal_vision_b200.animals import HoneyBee
+    h, w = 96, 250
+    f = frames.constant(h, w, 97)
+    f[:, : w // 2, 1] = 180
+    for fr in (frames.constant(h, w, 0), frames.constant(h, w, 255), frames.constant(h, w, 97), f):
+        _, ref = uv.honeybee_visualize(fr)
+        _, out = HoneyBee().visualize(fr)
+        _cmp(out, ref, "degenerate")
