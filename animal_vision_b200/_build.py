@@ -25,6 +25,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags():
+    """Extra nvcc flags for experiments (e.g. AVB_NVCC_EXTRA="-DUV_MINB=2"); part of the source hash."""
+    return os.environ.get("AVB_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -40,9 +45,10 @@ def _src_hash() -> str:
     h = hashlib.sha256()
     for f in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
             [os.path.join(os.path.dirname(HERE), "include", "avb200.h"), os.path.abspath(__file__)]:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, HERE).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
+    h.update(" ".join(_extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -66,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, "-c", src, "-o", obj] + [f for f in NVCC_FLAGS if f != "-shared"]
+        cmd = [nvcc, "-c", src, "-o", obj] + [f for f in NVCC_FLAGS if f != "-shared"] + _extra_flags()
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

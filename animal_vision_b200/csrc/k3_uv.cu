@@ -34,6 +34,9 @@ constexpr int UV_NR = 4;                 // percentile requests per frame
 constexpr int UV_MAX_BANDS = 160;
 constexpr int UV_THREADS = 256, UV_WARPS = UV_THREADS / 32;
 constexpr int UV_RH = 64;                // output rows per strip
+#ifndef UV_MINB
+#define UV_MINB 3
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { MAP_OPPONENT = 0, MAP_FALSECOLOR = 1, MAP_MATRIX = 2, MAP_PURPLE = 3, MAP_MIXED = 4 };
@@ -90,7 +93,27 @@ __device__ __forceinline__ float div_by(float x, float s, float r) {
     return fmaf(fmaf(-q, s, x), r, q);
 }
 
+// "bands" mode: classic_rgb_to_hsi.py:70-78, honeybee.py:126-135 in the reference's own order:
+// spec = (g2*c2 + g1*c1 + g0*c0) / (denom+1e-8);  rad = spec * E;  catch += rad * s.
+// Kept out of line: it is the fidelity mode, and inlining it four times per pixel group bloats
+// every walker past the instruction cache.
+__device__ __noinline__ void band_sum(const float4 *bands, int n_bands, float denom_eps, float c0, float c1, float c2,
+                                      float &u, float &b, float &g) {
+    float au = 0.f, ab = 0.f, ag = 0.f;
+    for (int l = 0; l < n_bands; ++l) {
+        const float4 lo = __ldg(bands + 2 * l), hi = __ldg(bands + 2 * l + 1);
+        float spec = __fadd_rn(__fadd_rn(__fmul_rn(lo.z, c2), __fmul_rn(lo.y, c1)), __fmul_rn(lo.x, c0));
+        spec = fmaxf(__fdiv_rn(spec, denom_eps), 0.f);
+        const float rad = __fmul_rn(spec, lo.w);
+        au = fmaf(rad, hi.x, au);
+        ab = fmaf(rad, hi.y, ab);
+        ag = fmaf(rad, hi.z, ag);
+    }
+    u = au; b = ab; g = ag;
+}
+
 // ------------------------------------------------------------------ per-pixel receptor catches
+template <bool BANDS>
 struct Catcher {
     const float *lut_s;
     float m[9];
@@ -119,7 +142,7 @@ struct Catcher {
     }
     __device__ __forceinline__ void operator()(uint32_t b0, uint32_t b1, uint32_t b2, float &u, float &b, float &g) const {
         const float c0 = lut_s[b0], c1 = lut_s[b1], c2 = lut_s[b2];
-        if (n_bands == 0) {
+        if constexpr (!BANDS) {
             u = m[0] * c0 + m[1] * c1 + m[2] * c2;
             b = m[3] * c0 + m[4] * c1 + m[5] * c2;
             g = m[6] * c0 + m[7] * c1 + m[8] * c2;
@@ -129,18 +152,8 @@ struct Catcher {
                 g = div_by(g, sc[2], rc[2]);
             }
         } else {
-            // classic_rgb_to_hsi.py:70-78, honeybee.py:126-135 in the reference's own order:
-            // spec = (g2*c2 + g1*c1 + g0*c0) / (denom+1e-8);  rad = spec * E;  catch += rad * s
-            float au = 0.f, ab = 0.f, ag = 0.f;
-            for (int l = 0; l < n_bands; ++l) {
-                const float4 lo = __ldg(bands + 2 * l), hi = __ldg(bands + 2 * l + 1);
-                float spec = __fadd_rn(__fadd_rn(__fmul_rn(lo.z, c2), __fmul_rn(lo.y, c1)), __fmul_rn(lo.x, c0));
-                spec = fmaxf(__fdiv_rn(spec, denom_eps), 0.f);
-                const float rad = __fmul_rn(spec, lo.w);
-                au = fmaf(rad, hi.x, au);
-                ab = fmaf(rad, hi.y, ab);
-                ag = fmaf(rad, hi.z, ag);
-            }
+            float au, ab, ag;
+            band_sum(bands, n_bands, denom_eps, c0, c1, c2, au, ab, ag);
             if (divide) {      // uv_helpers.py:195-206: divide by the global max / mean
                 au = __fdiv_rn(au, sc[0]);
                 ab = __fdiv_rn(ab, sc[1]);
@@ -154,7 +167,8 @@ struct Catcher {
 __device__ __forceinline__ uint32_t byte_k(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 + k); }
 
 // 4 packed pixels (three 32-bit words) -> catches
-__device__ __forceinline__ void catches4(const Catcher &cat, const uint32_t (&w)[3], float (&c)[4][3]) {
+template <class Cat>
+__device__ __forceinline__ void catches4(const Cat &cat, const uint32_t (&w)[3], float (&c)[4][3]) {
     cat(byte_k(w[0], 0), byte_k(w[0], 1), byte_k(w[0], 2), c[0][0], c[0][1], c[0][2]);
     cat(byte_k(w[0], 3), byte_k(w[1], 0), byte_k(w[1], 1), c[1][0], c[1][1], c[1][2]);
     cat(byte_k(w[1], 2), byte_k(w[1], 3), byte_k(w[2], 0), c[2][0], c[2][1], c[2][2]);
@@ -164,10 +178,9 @@ __device__ __forceinline__ void catches4(const Catcher &cat, const uint32_t (&w)
 // ------------------------------------------------------------------ the strip walk
 // Calls op(y, gx, v, ok) once per output row for every lane: v[j][k] = adapted + blurred catch k of
 // pixel (y, gx + j); ok is false for the two halo lanes.  All 32 lanes call op together.
-template <int R, class Op>
-__device__ __forceinline__ void uv_walk(const UvParams &p, const Catcher &cat, const uint8_t *src, int xs, int ys, int rows, Op &op) {
+template <int R, class Cat, class Op>
+__device__ __forceinline__ void uv_walk(const UvParams &p, const Cat &cat, const uint8_t *src, int xs, int ys, int rows, Op &op) {
     constexpr int OFF = R ? 4 : 0;
-    constexpr int NWIN = 2 * R + 1;
     const int lane = threadIdx.x & 31;
     const int H = p.io.H, W = p.io.W;
     const int gx = xs - OFF + 4 * lane;
@@ -194,72 +207,63 @@ __device__ __forceinline__ void uv_walk(const UvParams &p, const Catcher &cat, c
         }
     };
 
-    float win[NWIN][4][3];
+    // Vertical pass in accumulator ("scatter") form: acc[m] is the partial sum of the output row
+    // that still misses 2R - m input rows.  No rotating window, no per-phase unrolling, so the
+    // per-pixel operator is instantiated once (the unrolled form thrashed the instruction cache).
+    float acc[2 * R + 1][4][3];
+#pragma unroll
+    for (int m = 0; m < 2 * R + 1; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[m][j][k] = 0.f;
     uint32_t w[3], wn[3] = {0u, 0u, 0u};
     const int n_iter = rows + 2 * R;
-    const float t0 = p.t0, t1 = p.t1, t2 = p.t2;
+    const float tp[3] = {p.t0, p.t1, p.t2};
     load(-R, w);
-    for (int i0 = 0; i0 < n_iter; i0 += NWIN) {
+    for (int i = 0; i < n_iter; ++i) {              // iteration i reads input row ys + i - R
+        if (i + 1 < n_iter) load(i + 1 - R, wn);
+        float c[4][3];
+        catches4(cat, w, c);
+        float v[4][3];
+        if constexpr (R == 0) {
 #pragma unroll
-        for (int ph = 0; ph < NWIN; ++ph) {
-            const int i = i0 + ph;                 // iteration i reads input row ys + i - R
-            if (i < n_iter) {
-                if (i + 1 < n_iter) load(i + 1 - R, wn);
-                float c[4][3];
-                catches4(cat, w, c);
-                if (R == 0) {
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                for (int k = 0; k < 3; ++k) v[j][k] = c[j][k];
+        } else {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) win[0][j][k] = c[j][k];
+            for (int k = 0; k < 3; ++k) {
+                // horizontal pass (rows first, as cv2.GaussianBlur): neighbours from adjacent lanes
+                float e[8];
+                e[1] = __shfl_up_sync(FULL, c[3][k], 1);
+                e[6] = __shfl_down_sync(FULL, c[0][k], 1);
+                if (R == 2) {
+                    e[0] = __shfl_up_sync(FULL, c[2][k], 1);
+                    e[7] = __shfl_down_sync(FULL, c[1][k], 1);
                 } else {
-                    // horizontal pass (rows first, as cv2.GaussianBlur): neighbours from adjacent lanes
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        float e[8];
-                        e[1] = __shfl_up_sync(FULL, c[3][k], 1);
-                        e[6] = __shfl_down_sync(FULL, c[0][k], 1);
-                        if (R == 2) {
-                            e[0] = __shfl_up_sync(FULL, c[2][k], 1);
-                            e[7] = __shfl_down_sync(FULL, c[1][k], 1);
-                        } else {
-                            e[0] = e[7] = 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) e[2 + j] = c[j][k];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float a = fmaf(t1, e[1 + j] + e[3 + j], t0 * e[2 + j]);
-                            if (R == 2) a = fmaf(t2, e[j] + e[4 + j], a);
-                            win[ph][j][k] = a;
-                        }
-                    }
-                }
-                if (i >= 2 * R) {
-                    float v[4][3];
-                    if (R == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) v[j][k] = win[0][j][k];
-                    } else {
-                        constexpr int C = NWIN;   // slot of iteration i - d is (ph - d) mod NWIN
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                float a = fmaf(t1, win[(ph - R + 1 + C) % C][j][k] + win[(ph - R - 1 + 2 * C) % C][j][k],
-                                               t0 * win[(ph - R + C) % C][j][k]);
-                                if (R == 2) a = fmaf(t2, win[(ph - R + 2 + C) % C][j][k] + win[(ph - R - 2 + 2 * C) % C][j][k], a);
-                                v[j][k] = a;
-                            }
-                    }
-                    op(ys + i - 2 * R, gx, v, lane_ok);
+                    e[0] = e[7] = 0.f;
                 }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) w[k] = wn[k];
+                for (int j = 0; j < 4; ++j) e[2 + j] = c[j][k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float h = fmaf(tp[1], e[1 + j] + e[3 + j], tp[0] * e[2 + j]);
+                    if (R == 2) h = fmaf(tp[2], e[j] + e[4 + j], h);
+                    // vertical pass: finish the oldest output row, advance the others
+                    v[j][k] = fmaf(tp[R], h, acc[0][j][k]);
+#pragma unroll
+                    for (int m = 0; m < 2 * R - 1; ++m) {
+                        const int d = (R - 1 - m) < 0 ? -(R - 1 - m) : (R - 1 - m);
+                        acc[m][j][k] = fmaf(tp[d], h, acc[m + 1][j][k]);
+                    }
+                    acc[2 * R - 1][j][k] = tp[R] * h;
+                }
             }
         }
+        if (i >= 2 * R) op(ys + i - 2 * R, gx, v, lane_ok);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = wn[k];
     }
 }
 
@@ -280,7 +284,7 @@ __device__ __forceinline__ void quantities(const float (&c)[3], float (&q)[UV_NH
         // uv_mappers.py:55-60
         const float O1 = c[2] - c[1], O2 = c[1] - c[0];
         q[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
-        q[1] = __fdiv_rn(__fadd_rn(__fadd_rn(c[0], c[1]), c[2]), 3.0f);
+        q[1] = div_by(__fadd_rn(__fadd_rn(c[0], c[1]), c[2]), 3.0f, 0.333333343267440796f);
         q[2] = 0.f;
     } else {
         q[0] = c[0]; q[1] = c[1]; q[2] = c[2];
@@ -294,13 +298,14 @@ __device__ __forceinline__ int bin_of(float v, float inv_w) {
 }
 
 // ------------------------------------------------------------------ stats: maxima / sums of raw catches
+template <bool BANDS>
 __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __ldg(p.lut + i);
     __syncthreads();
     const int frame = blockIdx.y;
     const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
-    Catcher cat;
+    Catcher<BANDS> cat;
     cat.init_raw(p, lut_s);
     float mx[3] = {0.f, 0.f, 0.f};
     double sm[3] = {0.0, 0.0, 0.0};
@@ -309,7 +314,36 @@ __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ U
     for (int y = blockIdx.x; y < H; y += gridDim.x) {
         const uint8_t *row = src + (int64_t)y * p.io.in_rs;
         float rs[3] = {0.f, 0.f, 0.f};
-        for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+        int gi = threadIdx.x;
+        if (p.aligned_in) {
+            // four independent pixel groups per thread in flight (the pass is latency bound otherwise)
+            for (; gi + 3 * (int)blockDim.x < groups - 1; gi += 4 * blockDim.x) {
+                uint32_t w[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(row + 12 * (gi + u * (int)blockDim.x));
+                    w[u][0] = __ldg(q); w[u][1] = __ldg(q + 1); w[u][2] = __ldg(q + 2);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float c[4][3];
+                    catches4(cat, w[u], c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            mx[k] = fmaxf(mx[k], c[j][k]);
+                            rs[k] += c[j][k];
+                        }
+                        if (p.dbg_catches) {
+                            float *d = p.dbg_catches + (((int64_t)frame * H + y) * W + 4 * (gi + u * (int)blockDim.x) + j) * 3;
+                            d[0] = c[j][0]; d[1] = c[j][1]; d[2] = c[j][2];
+                        }
+                    }
+                }
+            }
+        }
+        for (; gi < groups; gi += blockDim.x) {
             const int gx = 4 * gi;
             float c[4][3];
             int npx = min(4, W - gx);
@@ -335,7 +369,10 @@ __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ U
 #pragma unroll
         for (int k = 0; k < 3; ++k) sm[k] += (double)rs[k];     // float partial per (thread,row): <= ~W/1024 terms
     }
-    UvFrameStats &st = p.stats[frame];
+    // block reduction first: one atomic per block and receptor, not one per warp
+    __shared__ float red_m[8][3];
+    __shared__ double red_s[8][3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float m = mx[k];
@@ -345,10 +382,17 @@ __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ U
             m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
             s += __shfl_xor_sync(FULL, s, o);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMax(&st.max_bits[k], __float_as_uint(fmaxf(m, 0.f)));
-            atomicAdd(&st.sum[k], s);
-        }
+        if (lane == 0) { red_m[wid][k] = m; red_s[wid][k] = s; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        float m = 0.f;
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { m = fmaxf(m, red_m[w][k]); s += red_s[w][k]; }
+        UvFrameStats &st = p.stats[frame];
+        atomicMax(&st.max_bits[k], __float_as_uint(fmaxf(m, 0.f)));
+        atomicAdd(&st.sum[k], s);
     }
 }
 
@@ -402,8 +446,8 @@ struct HistOp {
     }
 };
 
-template <int QS, int R>
-__global__ void __launch_bounds__(UV_THREADS, 2) uv_hist_kernel(const __grid_constant__ UvParams p) {
+template <int QS, int R, bool BANDS>
+__global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_hist_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     __shared__ uint32_t hs[QCount<QS>::value * UV_BINS];
     const int tid = threadIdx.x, frame = blockIdx.y;
@@ -411,7 +455,7 @@ __global__ void __launch_bounds__(UV_THREADS, 2) uv_hist_kernel(const __grid_con
     for (int i = tid; i < QCount<QS>::value * UV_BINS; i += UV_THREADS) hs[i] = 0u;
     __syncthreads();
     const UvFrameStats &st = p.stats[frame];
-    Catcher cat;
+    Catcher<BANDS> cat;
     cat.init_adapted(p, st, lut_s);
     HistOp<QS> op;
     op.hs = hs;
@@ -484,20 +528,34 @@ struct CollectOp {
     int lo[UV_NR], hi[UV_NR];
     __device__ __forceinline__ void operator()(int /*y*/, int gx, const float (&v)[4][3], bool ok) {
         const int lane = threadIdx.x & 31;
+        float q[4][UV_NH];
+        int bins[4][UV_NH];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            quantities<QS>(v[j], q[j]);
+#pragma unroll
+            for (int h = 0; h < UV_NH; ++h) bins[j][h] = bin_of(q[j][h], inv_w[h]);
+            if (ok && gx + j < W) {
+#pragma unroll
+                for (int r = 0; r < UV_NR; ++r)
+                    if (r < n_req) {
+                        const int h = req_hist[r];
+                        const int b = h == 0 ? bins[j][0] : (h == 1 ? bins[j][1] : bins[j][2]);
+                        any |= b >= lo[r] && b <= hi[r];
+                    }
+            }
+        }
+        if (!__any_sync(FULL, any)) return;          // the common case: nobody in this warp row hit a candidate bin
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool valid = ok && gx + j < W;
-            float q[UV_NH];
-            quantities<QS>(v[j], q);
-            int bins[UV_NH];
-#pragma unroll
-            for (int h = 0; h < UV_NH; ++h) bins[h] = bin_of(q[h], inv_w[h]);
 #pragma unroll
             for (int r = 0; r < UV_NR; ++r) {
                 if (r < n_req) {
                     const int h = req_hist[r];
-                    const int b = h == 0 ? bins[0] : (h == 1 ? bins[1] : bins[2]);
-                    const float val = h == 0 ? q[0] : (h == 1 ? q[1] : q[2]);
+                    const int b = h == 0 ? bins[j][0] : (h == 1 ? bins[j][1] : bins[j][2]);
+                    const float val = h == 0 ? q[j][0] : (h == 1 ? q[j][1] : q[j][2]);
                     const bool hit = valid && b >= lo[r] && b <= hi[r];
                     const unsigned m = __ballot_sync(FULL, hit);
                     if (m) {
@@ -513,14 +571,14 @@ struct CollectOp {
     }
 };
 
-template <int QS, int R>
-__global__ void __launch_bounds__(UV_THREADS, 2) uv_collect_kernel(const __grid_constant__ UvParams p) {
+template <int QS, int R, bool BANDS>
+__global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_collect_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     const int tid = threadIdx.x, frame = blockIdx.y;
     for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
     __syncthreads();
     UvFrameStats &st = p.stats[frame];
-    Catcher cat;
+    Catcher<BANDS> cat;
     cat.init_adapted(p, st, lut_s);
     CollectOp<QS> op;
     op.st = &st;
@@ -627,8 +685,9 @@ __global__ void __launch_bounds__(SEL_THREADS) uv_select_kernel(const __grid_con
 
 // ------------------------------------------------------------------ map
 struct MapConsts {
-    float pr, pL;                 // opponent: percentile + eps
+    float pr, pL, rpr, rpL;       // opponent: percentile + eps, and reciprocals
     float d95[3], d98;            // falsecolor / purple: max(percentile, eps)
+    float r95[3], r98;            // reciprocals
     float c0[3], c1[3], pd[3];    // purple / warm anchors (linear light, host-computed) and accent direction
     float m[9];
     float alpha;
@@ -636,7 +695,7 @@ struct MapConsts {
 
 __device__ __forceinline__ void falsecolor(const float (&c)[3], const MapConsts &k, float (&rgb)[3]) {
     // uv_mappers.py:29-43 (python-float coefficients act as float32)
-    const float Un = __fdiv_rn(c[0], k.d95[0]), Bn = __fdiv_rn(c[1], k.d95[1]), Gn = __fdiv_rn(c[2], k.d95[2]);
+    const float Un = div_by(c[0], k.d95[0], k.r95[0]), Bn = div_by(c[1], k.d95[1], k.r95[1]), Gn = div_by(c[2], k.d95[2], k.r95[2]);
     rgb[0] = __saturatef(__fadd_rn(__fmul_rn(0.85f, Un), __fmul_rn(0.10f, Gn)));
     rgb[1] = __saturatef(__fadd_rn(__fmul_rn(0.80f, Gn), __fmul_rn(0.20f, Bn)));
     rgb[2] = __saturatef(__fadd_rn(__fmul_rn(0.70f, Bn), __fmul_rn(0.40f, Un)));
@@ -644,7 +703,7 @@ __device__ __forceinline__ void falsecolor(const float (&c)[3], const MapConsts 
 
 __device__ __forceinline__ void purple_soft(float U, const MapConsts &k, float (&rgb)[3]) {
     // uv_mappers.py:90-132 with the defaults u_gamma .90, accent_gamma .85, accent_strength .05
-    const float u = powf(__saturatef(__fdiv_rn(U, k.d98)), 0.90f);
+    const float u = powf(__saturatef(div_by(U, k.d98, k.r98)), 0.90f);
     const float w = powf(u, 0.85f);
     float y = 0.f;
     const float yc[3] = {0.2126f, 0.7152f, 0.0722f};
@@ -670,12 +729,12 @@ __device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &
         // uv_mappers.py:53-64 and hsv_to_rgb :14-26
         const float U = c[0], B = c[1], G = c[2];
         const float O1 = G - B, O2 = B - U;
-        const float L = __fdiv_rn(__fadd_rn(__fadd_rn(U, B), G), 3.0f);
+        const float L = div_by(__fadd_rn(__fadd_rn(U, B), G), 3.0f, 0.333333343267440796f);
         const float radius = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
         const float PI_F = 3.14159274101257324f;          // float32(np.pi)
-        const float hue = __fdiv_rn(__fadd_rn(atan2f(O2, O1), PI_F), 6.28318548202514648f);
-        const float sat = __saturatef(__fdiv_rn(radius, k.pr));
-        const float val = __saturatef(__fdiv_rn(L, k.pL));
+        const float hue = div_by(__fadd_rn(atan2f(O2, O1), PI_F), 6.28318548202514648f, 0.159154936671257019f);
+        const float sat = __saturatef(div_by(radius, k.pr, k.rpr));
+        const float val = __saturatef(div_by(L, k.pL, k.rpL));
         const float h6 = __fmul_rn(hue, 6.0f);
         const float fl = floorf(h6);
         const float f = h6 - fl;                           // exact
@@ -745,8 +804,8 @@ struct MapOp {
     }
 };
 
-template <int MAPPER, int R>
-__global__ void __launch_bounds__(UV_THREADS, 2) uv_map_kernel(const __grid_constant__ UvParams p) {
+template <int MAPPER, int R, bool BANDS>
+__global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_map_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
     const int tid = threadIdx.x, frame = blockIdx.y;
@@ -754,7 +813,7 @@ __global__ void __launch_bounds__(UV_THREADS, 2) uv_map_kernel(const __grid_cons
     copy_to_smem(enc_s, p.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.enc + 2)));
     __syncthreads();
     const UvFrameStats &st = p.stats[frame];
-    Catcher cat;
+    Catcher<BANDS> cat;
     cat.init_adapted(p, st, lut_s);
     MapOp<MAPPER> op;
     op.enc = enc_view(enc_s);
@@ -765,9 +824,12 @@ __global__ void __launch_bounds__(UV_THREADS, 2) uv_map_kernel(const __grid_cons
     MapConsts &k = op.k;
     k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
     k.pL = st.pct[1] + p.eps;
+    k.rpr = __frcp_rn(k.pr);
+    k.rpL = __frcp_rn(k.pL);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) k.d95[i] = fmaxf(st.pct[i], p.eps);
+    for (int i = 0; i < 3; ++i) { k.d95[i] = fmaxf(st.pct[i], p.eps); k.r95[i] = __frcp_rn(k.d95[i]); }
     k.d98 = fmaxf(MAPPER == MAP_PURPLE ? st.pct[0] : st.pct[3], p.eps);
+    k.r98 = __frcp_rn(k.d98);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         k.c0[i] = p.anchors[i];
@@ -802,11 +864,11 @@ static dim3 walk_grid(const UvParams &p, int per_sm) {
     return dim3(bx, p.io.n);
 }
 
-template <int QS, int R>
+template <int QS, int R, bool BANDS>
 static int launch_percentiles(const UvParams &p, cudaStream_t st) {
     {
         AVB_TIMED("k3_uv_hist", st);
-        uv_hist_kernel<QS, R><<<walk_grid(p, 4), UV_THREADS, 0, st>>>(p);
+        uv_hist_kernel<QS, R, BANDS><<<walk_grid(p, 4), UV_THREADS, 0, st>>>(p);
     }
     {
         AVB_TIMED("k3_uv_scan", st);
@@ -814,7 +876,7 @@ static int launch_percentiles(const UvParams &p, cudaStream_t st) {
     }
     {
         AVB_TIMED("k3_uv_collect", st);
-        uv_collect_kernel<QS, R><<<walk_grid(p, 8), UV_THREADS, 0, st>>>(p);
+        uv_collect_kernel<QS, R, BANDS><<<walk_grid(p, 8), UV_THREADS, 0, st>>>(p);
     }
     {
         AVB_TIMED("k3_uv_select", st);
@@ -824,7 +886,7 @@ static int launch_percentiles(const UvParams &p, cudaStream_t st) {
     return AVB_OK;
 }
 
-template <int MAPPER, int R>
+template <int MAPPER, int R, bool BANDS>
 static int launch_mapper(const UvParams &p, cudaStream_t st) {
     constexpr int QS = MAPPER == MAP_OPPONENT ? QS_OPP : (MAPPER == MAP_PURPLE ? QS_U : QS_UBG);
     {
@@ -832,24 +894,24 @@ static int launch_mapper(const UvParams &p, cudaStream_t st) {
         uv_prep_kernel<QS><<<(p.io.n + 63) / 64, 64, 0, st>>>(p);
     }
     if (p.n_req > 0)
-        if (int e = launch_percentiles<QS, R>(p, st)) return e;
+        if (int e = launch_percentiles<QS, R, BANDS>(p, st)) return e;
     {
         AVB_TIMED("k3_uv_map", st);
         const int tasks = p.strips_x * p.strips_y;
-        uv_map_kernel<MAPPER, R><<<dim3((tasks + UV_WARPS - 1) / UV_WARPS, p.io.n), UV_THREADS, 0, st>>>(p);
+        uv_map_kernel<MAPPER, R, BANDS><<<dim3((tasks + UV_WARPS - 1) / UV_WARPS, p.io.n), UV_THREADS, 0, st>>>(p);
     }
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }
 
-template <int R>
+template <int R, bool BANDS>
 static int dispatch_mapper(const UvParams &p, cudaStream_t st) {
     switch (p.mapper) {
-        case MAP_OPPONENT: return launch_mapper<MAP_OPPONENT, R>(p, st);
-        case MAP_FALSECOLOR: return launch_mapper<MAP_FALSECOLOR, R>(p, st);
-        case MAP_MATRIX: return launch_mapper<MAP_MATRIX, R>(p, st);
-        case MAP_PURPLE: return launch_mapper<MAP_PURPLE, R>(p, st);
-        default: return launch_mapper<MAP_MIXED, R>(p, st);
+        case MAP_OPPONENT: return launch_mapper<MAP_OPPONENT, R, BANDS>(p, st);
+        case MAP_FALSECOLOR: return launch_mapper<MAP_FALSECOLOR, R, BANDS>(p, st);
+        case MAP_MATRIX: return launch_mapper<MAP_MATRIX, R, BANDS>(p, st);
+        case MAP_PURPLE: return launch_mapper<MAP_PURPLE, R, BANDS>(p, st);
+        default: return launch_mapper<MAP_MIXED, R, BANDS>(p, st);
     }
 }
 
@@ -950,14 +1012,24 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
 
     AVB_CUDA_OK(cudaMemsetAsync(ws, 0, stats_bytes + hist_bytes, st));
     {
-        dim3 grid((unsigned)(H < 1024 ? H : 1024), n);
+        int bx = (sm_count() * 16 + n - 1) / n;        // ~16 CTAs per SM over the whole batch
+        if (bx > H) bx = H;
+        dim3 grid((unsigned)bx, n);
         AVB_TIMED("k3_uv_stats", st);
-        uv_stats_kernel<<<grid, 256, 0, st>>>(p);
+        if (n_bands) uv_stats_kernel<true><<<grid, 256, 0, st>>>(p);
+        else uv_stats_kernel<false><<<grid, 256, 0, st>>>(p);
         AVB_CUDA_OK(cudaGetLastError());
     }
+    if (n_bands) {
+        switch (R) {
+            case 0: return dispatch_mapper<0, true>(p, st);
+            case 1: return dispatch_mapper<1, true>(p, st);
+            default: return dispatch_mapper<2, true>(p, st);
+        }
+    }
     switch (R) {
-        case 0: return dispatch_mapper<0>(p, st);
-        case 1: return dispatch_mapper<1>(p, st);
-        default: return dispatch_mapper<2>(p, st);
+        case 0: return dispatch_mapper<0, false>(p, st);
+        case 1: return dispatch_mapper<1, false>(p, st);
+        default: return dispatch_mapper<2, false>(p, st);
     }
 }
