@@ -73,6 +73,7 @@ struct DogProducer {
         for (int i = 0; i < 9; ++i) m[i] = pp.M.m[i];
         seen = 0;
     }
+    __device__ __forceinline__ bool all_black(int, int) const { return false; }
     __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
         const uint8_t *q = src + (int64_t)y * rs + 3 * x;
         const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
@@ -90,6 +91,7 @@ struct CatProducer {
     struct Params {
         Mat3 M;             // RGB->LMS, L/M merge, LMS->RGB collapsed into one 3x3 (host, float64 -> f32)
         const float *xl, *xr, *wl, *wr;  // per-column tables, length W (device)
+        const float *ws, *rws;           // per column: wl + wr + 1e-8 (float32) and its correctly rounded reciprocal
         const uint32_t *frame_flags;     // per frame: != 0 when some byte >= 2 (written by frame_flags_kernel)
         int norm_mode;                   // AVB_NORM_DIV255: always /255; AVB_NORM_AUTO: /255 iff flag set
     };
@@ -99,7 +101,7 @@ struct CatProducer {
     int64_t rs;
     int W;
     float m[9];
-    const float *xl, *xr, *wl, *wr;
+    const float *xl, *xr, *wl, *wr, *ws, *rws;
     uint32_t seen;
 
     __device__ __forceinline__ void init(const Params &pp, float *smem, const uint8_t *frame, int64_t row_stride,
@@ -115,8 +117,17 @@ struct CatProducer {
         W = W_;
 #pragma unroll
         for (int i = 0; i < 9; ++i) m[i] = pp.M.m[i];
-        xl = pp.xl; xr = pp.xr; wl = pp.wl; wr = pp.wr;
+        xl = pp.xl; xr = pp.xr; wl = pp.wl; wr = pp.wr; ws = pp.ws; rws = pp.rws;
         seen = 0;
+    }
+    // every column of [xa, xb) has zero weight in both eye views: the strip is black
+    __device__ __forceinline__ bool all_black(int xa, int xb) const {
+        bool any = false;
+        for (int x = xa + (int)threadIdx.x; x < xb; x += blockDim.x) {
+            const int xc = reflect101(x, W);
+            any |= (__ldg(wl + xc) != 0.0f) || (__ldg(wr + xc) != 0.0f);
+        }
+        return !__syncthreads_or(any);
     }
     // cv::remap INTER_LINEAR on a row: map coordinate quantised to 1/32 px, two taps, border 0
     __device__ __forceinline__ void gather(const uint8_t *row, float xs, float &c0, float &c1, float &c2) {
@@ -142,21 +153,32 @@ struct CatProducer {
         c2 = __fadd_rn(__fmul_rn(a2, w0), __fmul_rn(b2, f));
     }
     static __device__ __forceinline__ float decode(float v) {
-        // animals/animal_utils.py:5-11 on float32
-        return v <= 0.04045f ? __fdiv_rn(v, 12.92f) : powf(__fdiv_rn(v + 0.055f, 1.055f), 2.4f);
+        // animals/animal_utils.py:5-11 on float32; the power goes through the SFU (ex2(2.4 lg2 x),
+        // ~5e-7 relative: far inside the 1-LSB budget of the uint8 result)
+        return v <= 0.04045f ? v * (1.0f / 12.92f) : exp2f(2.4f * __log2f((v + 0.055f) * (1.0f / 1.055f)));
     }
     __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
-        const uint8_t *row = src + (int64_t)y * rs;
         const float wL = __ldg(wl + x), wR = __ldg(wr + x);
+        if (wL == 0.0f && wR == 0.0f) {     // outside both eye views: (0*wL + 0*wR)/ws = 0 -> decode(0) = 0
+            o0 = o1 = o2 = 0.f;
+            return;
+        }
+        const uint8_t *row = src + (int64_t)y * rs;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         // a zero weight multiplies a finite sample: skipping the gather leaves the sum unchanged
         if (wL != 0.0f) gather(row, __ldg(xl + x), l0, l1, l2);
         if (wR != 0.0f) gather(row, __ldg(xr + x), r0, r1, r2);
-        const float ws = __fadd_rn(__fadd_rn(wL, wR), 1e-8f);
-        float s0 = __fdiv_rn(__fadd_rn(__fmul_rn(l0, wL), __fmul_rn(r0, wR)), ws);
-        float s1 = __fdiv_rn(__fadd_rn(__fmul_rn(l1, wL), __fmul_rn(r1, wR)), ws);
-        float s2 = __fdiv_rn(__fadd_rn(__fmul_rn(l2, wL), __fmul_rn(r2, wR)), ws);
-        s0 = decode(__saturatef(s0)); s1 = decode(__saturatef(s1)); s2 = decode(__saturatef(s2));
+        // (left*wL + right*wR) / (wL + wR + 1e-8), the quotient correctly rounded from the
+        // per-column reciprocal (one Newton step on the quotient)
+        const float s = __ldg(ws + x), r = __ldg(rws + x);
+        const float n0 = __fadd_rn(__fmul_rn(l0, wL), __fmul_rn(r0, wR));
+        const float n1 = __fadd_rn(__fmul_rn(l1, wL), __fmul_rn(r1, wR));
+        const float n2 = __fadd_rn(__fmul_rn(l2, wL), __fmul_rn(r2, wR));
+        float q0 = __fmul_rn(n0, r), q1 = __fmul_rn(n1, r), q2 = __fmul_rn(n2, r);
+        q0 = fmaf(fmaf(-q0, s, n0), r, q0);
+        q1 = fmaf(fmaf(-q1, s, n1), r, q1);
+        q2 = fmaf(fmaf(-q2, s, n2), r, q2);
+        const float s0 = decode(__saturatef(q0)), s1 = decode(__saturatef(q1)), s2 = decode(__saturatef(q2));
         o0 = m[0] * s0 + m[1] * s1 + m[2] * s2;
         o1 = m[3] * s0 + m[4] * s1 + m[5] * s2;
         o2 = m[6] * s0 + m[7] * s1 + m[8] * s2;
@@ -193,6 +215,20 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     uint8_t *dst_frame = p.io.out + (int64_t)frame * p.io.out_fs;
     const bool vec_ok = (x0 + G_TW <= W) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
+
+    // a strip whose producer is identically zero (the cat's blind middle third) encodes to byte 0
+    if (prod.all_black(x0 - R, x0 + G_TW + R)) {
+        const int nbytes = min(G_TW, W - x0) * 3;
+        for (int y = y_start + warp; y < y_end; y += G_THREADS / 32) {
+            uint8_t *row = dst_frame + (int64_t)y * p.io.out_rs + (int64_t)x0 * 3;
+            if (vec_ok) {
+                if (lane < G_TW * 3 / 16) reinterpret_cast<uint4 *>(row)[lane] = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                for (int b = lane; b < nbytes; b += 32) row[b] = 0;
+            }
+        }
+        return;
+    }
 
     const int n_out_blocks = (y_end - y_start + G_RB - 1) / G_RB;
     const int n_in_blocks = n_out_blocks + C::LAG;
@@ -474,6 +510,7 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
     CatProducer::Params pp{};
     for (int i = 0; i < 9; ++i) pp.M.m[i] = m_host[i];
     pp.xl = warp_dev; pp.xr = warp_dev + W; pp.wl = warp_dev + 2 * W; pp.wr = warp_dev + 3 * W;
+    pp.ws = warp_dev + 4 * W; pp.rws = warp_dev + 5 * W;
     pp.frame_flags = flags_dev;
     pp.norm_mode = norm_mode;
     return dispatch_gauss<CatProducer>(ksize / 2, gc, pp, st);

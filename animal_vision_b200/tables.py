@@ -140,6 +140,15 @@ def cat_warp_tables(W: int, fov_in=100.0, half_fov=105.0, overlap=40.0):
     return xL, xR, wL, wR
 
 
+def cat_warp_device_table(W: int, fov_in=100.0, half_fov=105.0, overlap=40.0) -> np.ndarray:
+    """float32 [6*W] for avb_cat_u8: xL, xR, wL, wR, the blend denominator ws = wL + wR + 1e-8
+    (float32, cat_widevision_utils.py:97) and its correctly rounded reciprocal."""
+    xL, xR, wL, wR = cat_warp_tables(W, fov_in, half_fov, overlap)
+    ws = (wL + wR + 1e-8).astype(np.float32)
+    rws = (np.float32(1.0) / ws).astype(np.float32)
+    return np.concatenate([xL, xR, wL, wR, ws, rws]).astype(np.float32)
+
+
 def resize_axis_table(src: int, dst: int, *, vertical: bool):
     """cv2.resize INTER_LINEAR, uint8: per output index (i0, i1, w0, w1) with 11-bit weights.
     Horizontal: an out-of-range neighbour zeroes the fraction.  Vertical: only indices clamp."""

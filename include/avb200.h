@@ -119,7 +119,8 @@ AVB_API int avb_streak_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, in
  *              1/32-px coordinate quantisation, BORDER_CONSTANT 0, cos^2 blend) fused, as the producer
  *              stage, into the K2 blur kernel: decode (pow) -> collapsed 3x3 (cat.py:95-101) ->
  *              Gaussian sigma=1.0 (9 taps) -> encode.
- *   warp_dev   4*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights)
+ *   warp_dev   6*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights),
+ *              ws = wL + wR + 1e-8 (the blend denominator, float32) and 1/ws (correctly rounded)
  *   zoom_dev   4*W + 4*H int32: xi0, xi1, xw0, xw1, yi0, yi1, yw0, yw1 (source indices incl. crop
  *              origin, 11-bit weights)
  *   enc_dev    encode table built from the float64 tail's thresholds (cat.py runs float64 from
