@@ -1,0 +1,910 @@
+// K4: MST++ RGB -> 31-band hyperspectral inference (reference
+// ml/MST_plus_plus/predict_code/architecture/MST_Plus_Plus.py:88-293), the one dense contraction on
+// the hot path.
+//
+// Layout: every feature map is channels-last [B, H, W, Cp] with the channel count padded to a
+// multiple of 32 (31 -> 32, 62 -> 64, 124 -> 128; FFN hidden 124/248/496 -> 128/256/512); padded
+// channels are exactly zero everywhere (weights are zero padded), so they never leak.  The residual
+// stream, LayerNorm, q/k norms, the spectral Gram matrix and the softmax stay fp32; GEMM operands
+// are bf16 with fp32 accumulation (the 1e-2 budget needs exactly that split).
+//
+// Every convolution / linear layer is one implicit GEMM  Y[pixels, Cout] = gather(X)[pixels, K] W^T
+// through a single kernel template (pointwise, two-source concat, 3x3, 4x4 stride 2; the 2x2
+// transposed conv is a pointwise GEMM with a pixel-shuffle store).  The spectral attention
+// (MS_MSA, :110-139) is algebraically folded: softmax(rescale * K_hat Q_hat^T) is a 31x31 matrix
+// per head that depends on ALL pixels, so each layer is two-phase --
+//   phase 1  q,k,v = x Wqkv^T (one GEMM), Gram + norms reduced over all pixels (fp32 atomics)
+//   phase 2  M = Wproj . blockdiag(attn)  (c x c, per image), out = v M^T + b + pos_emb(v) + x
+// -- i.e. attention-apply and the output projection become ONE pointwise GEMM on v.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "avb_common.cuh"
+
+namespace avb {
+namespace k4 {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int NF = 31;                 // n_feat = dim_head
+constexpr int64_t N_PARAMS = 1619625;  // MST_Plus_Plus().state_dict() element count
+
+static inline int pad32(int c) { return (c + 31) / 32 * 32; }
+
+__device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------------ implicit GEMM
+constexpr int BM = 128, BK = 32, APAD = 8;
+constexpr int GEMM_THREADS = 256;
+
+enum { MODE_PW = 0, MODE_C3 = 1, MODE_C4S2 = 2 };
+enum { OUT_ROWS = 0, OUT_CONVT = 1, OUT_CROP = 2 };
+
+struct GemmP {
+    const void *A1, *A2;       // MODE_PW: [B*rows, lda]; conv modes: feature map [B, Hi, Wi, lda1]
+    int lda1, lda2, K1, K;     // K1: extent of K taken from A1 (the rest from A2), K multiple of 32
+    const bf16 *W;             // [Np][K] row-major (k contiguous)
+    long long w_bstride;       // element stride between batch items (0: shared weights)
+    int Np;
+    int rows;                  // output rows (pixels) per batch item
+    int Hi, Wi, Ho, Wo, Cpin;  // conv geometry
+    const float *bias;         // [Np] or null
+    const float *res1; int ldr1;   // fp32 residual, row-indexed like the output rows
+    const bf16 *res2; int ldr2;    // bf16 residual
+    int gelu;
+    void *out; int ldo; int out_bf16;
+    int out_mode;
+    int Hreal, Wreal, Cpo, crop_top, crop_left;   // OUT_CONVT: Cpo; OUT_CROP: real size + crop origin
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem_ptr) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+// One CTA: 128 output rows x BN output channels, K streamed in chunks of 32 through a two-stage
+// shared-memory ring (global loads of chunk i+1 are in flight while chunk i feeds the tensor cores).
+template <int BN, bool A_BF16, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmP p) {
+    __shared__ __align__(16) bf16 As[2][BM][BK + APAD];
+    __shared__ __align__(16) bf16 Bs[2][BN][BK + APAD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int m_base = blockIdx.x * BM, n_base = blockIdx.y * BN;
+
+    // ---- A loader: thread -> (row, 16-wide half of the 32-wide chunk)
+    const int lr = tid >> 1, lh = tid & 1;
+    const int lm = m_base + lr;
+    const bool row_ok = lm < p.rows;
+    int oy = 0, ox = 0;
+    if (MODE != MODE_PW) { oy = lm / p.Wo; ox = lm - oy * p.Wo; }
+
+    auto a_src = [&](int kbase, bool &ok) -> const void * {
+        ok = row_ok;
+        if (MODE == MODE_PW) {
+            const long long row = (long long)b * p.rows + lm;
+            if (kbase < p.K1) {
+                const long long off = row * p.lda1 + kbase + 16 * lh;
+                return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
+            }
+            const long long off = row * p.lda2 + (kbase - p.K1) + 16 * lh;
+            return A_BF16 ? (const void *)((const bf16 *)p.A2 + off) : (const void *)((const float *)p.A2 + off);
+        }
+        const int tap = kbase / p.Cpin, c0 = kbase - tap * p.Cpin;
+        int yy, xx;
+        if (MODE == MODE_C3) { yy = oy + tap / 3 - 1; xx = ox + tap % 3 - 1; }
+        else { yy = 2 * oy - 1 + (tap >> 2); xx = 2 * ox - 1 + (tap & 3); }
+        ok = row_ok && (unsigned)yy < (unsigned)p.Hi && (unsigned)xx < (unsigned)p.Wi;
+        const long long off = (((long long)b * p.Hi + yy) * p.Wi + xx) * p.lda1 + c0 + 16 * lh;
+        return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
+    };
+    uint4 areg[2];
+    auto a_fetch = [&](int kbase) {
+        bool ok;
+        const void *src = a_src(kbase, ok);
+        if (!ok) { areg[0] = areg[1] = make_uint4(0u, 0u, 0u, 0u); return; }
+        if (A_BF16) {
+            const uint4 *q = (const uint4 *)src;
+            areg[0] = __ldg(q); areg[1] = __ldg(q + 1);
+        } else {
+            const float4 *q = (const float4 *)src;
+            const float4 f0 = __ldg(q), f1 = __ldg(q + 1), f2 = __ldg(q + 2), f3 = __ldg(q + 3);
+            areg[0] = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            areg[1] = make_uint4(pack_bf16(f2.x, f2.y), pack_bf16(f2.z, f2.w), pack_bf16(f3.x, f3.y), pack_bf16(f3.z, f3.w));
+        }
+    };
+    auto a_store = [&](int st) {
+        uint4 *d = reinterpret_cast<uint4 *>(&As[st][lr][16 * lh]);
+        d[0] = areg[0]; d[1] = areg[1];
+    };
+    // ---- B loader: BN rows x 32 k = BN*4 uint4
+    constexpr int B_PER_THREAD = (BN * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
+    const bf16 *Wb = p.W + (long long)b * p.w_bstride;
+    uint4 breg[B_PER_THREAD];
+    auto b_fetch = [&](int kbase) {
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int idx = tid + i * GEMM_THREADS;
+            if (idx < BN * 4) {
+                const int n = idx >> 2, q = idx & 3;
+                breg[i] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K + kbase) + q);
+            }
+        }
+    };
+    auto b_store = [&](int st) {
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int idx = tid + i * GEMM_THREADS;
+            if (idx < BN * 4) *reinterpret_cast<uint4 *>(&Bs[st][idx >> 2][(idx & 3) * 8]) = breg[i];
+        }
+    };
+
+    // ---- warp tiling: 4 (M) x 2 (N) warps, warp tile 32 x BN/2
+    constexpr int WN = BN / 2, NT = WN / 8;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+    const int nk = p.K / BK;
+    a_fetch(0);
+    b_fetch(0);
+    a_store(0);
+    b_store(0);
+    __syncthreads();
+    for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc & 1;
+        if (kc + 1 < nk) { a_fetch((kc + 1) * BK); b_fetch((kc + 1) * BK); }
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 16) {
+            uint32_t af[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) ldmatrix_x4(af[i], &As[st][wm + i * 16 + (lane & 15)][ks + (lane >> 4) * 8]);
+#pragma unroll
+            for (int j = 0; j < NT; j += 2) {
+                uint32_t bfr[4];
+                ldmatrix_x4(bfr, &Bs[st][wn + j * 8 + ((lane >> 4) << 3) + (lane & 7)][ks + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    mma_bf16(acc[i][j], af[i], bfr[0], bfr[1]);
+                    if (j + 1 < NT) mma_bf16(acc[i][j + 1], af[i], bfr[2], bfr[3]);
+                }
+            }
+        }
+        if (kc + 1 < nk) { a_store(st ^ 1); b_store(st ^ 1); }
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias -> GELU -> residuals -> store
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int m = m_base + wm + i * 16 + (lane >> 2) + hrow * 8;
+            if (m >= p.rows) continue;
+            const long long row = (long long)b * p.rows + m;
+            long long obase = 0;
+            int cy = 0, cx = 0;
+            bool crop_ok = true;
+            if (p.out_mode == OUT_ROWS) obase = row * p.ldo;
+            else { cy = m / p.Wo; cx = m - cy * p.Wo; }
+            if (p.out_mode == OUT_CROP) {
+                cy -= p.crop_top; cx -= p.crop_left;
+                crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
+                obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int n = n_base + wn + j * 8 + (lane & 3) * 2;
+                float v0 = acc[i][j][hrow * 2], v1 = acc[i][j][hrow * 2 + 1];
+                if (p.bias) { v0 += __ldg(p.bias + n); v1 += __ldg(p.bias + n + 1); }
+                if (p.gelu) { v0 = gelu(v0); v1 = gelu(v1); }
+                if (p.res1) {
+                    const float2 r = *reinterpret_cast<const float2 *>(p.res1 + row * p.ldr1 + n);
+                    v0 += r.x; v1 += r.y;
+                }
+                if (p.res2) {
+                    const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162 *>(p.res2 + row * p.ldr2 + n);
+                    v0 += __low2float(r); v1 += __high2float(r);
+                }
+                if (p.out_mode == OUT_ROWS) {
+                    if (p.out_bf16) *reinterpret_cast<uint32_t *>((bf16 *)p.out + obase + n) = pack_bf16(v0, v1);
+                    else *reinterpret_cast<float2 *>((float *)p.out + obase + n) = make_float2(v0, v1);
+                } else if (p.out_mode == OUT_CONVT) {
+                    // ConvTranspose2d(k=2, s=2): column block q = dy*2+dx lands on pixel (2y+dy, 2x+dx)
+                    const int q = n / p.Cpo, co = n - q * p.Cpo;
+                    const long long o = ((((long long)b * 2 * p.Ho) + 2 * cy + (q >> 1)) * (2 * p.Wo) + 2 * cx + (q & 1)) * p.ldo + co;
+                    *reinterpret_cast<float2 *>((float *)p.out + o) = make_float2(v0, v1);
+                } else if (crop_ok) {
+                    if (n < NF) ((float *)p.out)[obase + n] = v0;
+                    if (n + 1 < NF) ((float *)p.out)[obase + n + 1] = v1;
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------ conv_in
+// F.pad(reflect, bottom/right to a multiple of 8 -- or the wrapper's centred pad) + Conv2d(3, 31, 3,
+// padding=1, bias=False) (MST_Plus_Plus.py:284-289) -> fp32 [B, Hp, Wp, 32].
+struct ConvInP {
+    const void *in; int in_u8;     // [B, H, W, 3] float32 in [0,1] or uint8 (/255: predict_torch.py:12-19)
+    float *out;                    // [B, Hp, Wp, 32]
+    const float *w;                // [27][32]: (ky*3+kx)*3+ci major, co minor
+    int B, H, W, Hp, Wp, top, left;
+};
+__device__ __forceinline__ int reflect_idx(int i, int n) {   // torch 'reflect' == REFLECT_101
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+__global__ void __launch_bounds__(256) conv_in_kernel(const __grid_constant__ ConvInP p) {
+    __shared__ float ws[27 * 32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = __ldg(p.w + i);
+    __syncthreads();
+    const int co = threadIdx.x & 31;
+    const long long npx = (long long)p.B * p.Hp * p.Wp;
+    for (long long px = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); px < npx; px += (long long)gridDim.x * 8) {
+        const int x = (int)(px % p.Wp);
+        const long long t = px / p.Wp;
+        const int y = (int)(t % p.Hp), b = (int)(t / p.Hp);
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yp = y + ky - 1, xp = x + kx - 1;          // coordinates in the PADDED image
+                if ((unsigned)yp < (unsigned)p.Hp && (unsigned)xp < (unsigned)p.Wp) {   // conv zero padding
+                    const int ys = reflect_idx(yp - p.top, p.H), xs = reflect_idx(xp - p.left, p.W);
+                    const long long o = (((long long)b * p.H + ys) * p.W + xs) * 3;
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float v = p.in_u8 ? __fdiv_rn((float)((const uint8_t *)p.in)[o + ci], 255.0f) : ((const float *)p.in)[o + ci];
+                        acc = fmaf(v, ws[((ky * 3 + kx) * 3 + ci) * 32 + co], acc);
+                    }
+                }
+            }
+        p.out[px * 32 + co] = acc;      // co == 31 has zero weights -> padded channel stays 0
+    }
+}
+
+// ------------------------------------------------------------------------------------ depthwise 3x3
+// Conv2d(C, C, 3, 1, 1, groups=C, bias=False) on channels-last bf16, optional GELU on the result
+// (pos_emb: dw -> GELU -> dw, MST_Plus_Plus.py:104-108; FFN: GELU -> dw -> GELU, :146-153).
+struct DwP {
+    const bf16 *in; int ldi;
+    bf16 *out; int ldo;
+    const float *w;               // [9][Cp]
+    int B, H, W, Cp, gelu_out;
+};
+__global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwP p) {
+    const int groups = p.Cp >> 3;                       // 8 channels per thread
+    const long long total = (long long)p.B * p.H * p.W * groups;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const long long px = idx / groups;
+        const int x = (int)(px % p.W);
+        const long long t = px / p.W;
+        const int y = (int)(t % p.H), b = (int)(t / p.H);
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if ((unsigned)yy >= (unsigned)p.H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = x + kx - 1;
+                if ((unsigned)xx >= (unsigned)p.W) continue;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.in + (((long long)b * p.H + yy) * p.W + xx) * p.ldi + 8 * g));
+                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + (ky * 3 + kx) * p.Cp + 8 * g));
+                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(p.w + (ky * 3 + kx) * p.Cp + 8 * g) + 1);
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[2 * q] = fmaf(__low2float(h2[q]), wv[2 * q], acc[2 * q]);
+                    acc[2 * q + 1] = fmaf(__high2float(h2[q]), wv[2 * q + 1], acc[2 * q + 1]);
+                }
+            }
+        }
+        if (p.gelu_out) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = gelu(acc[c]);
+        }
+        uint4 o;
+        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4 *>(p.out + px * p.ldo + 8 * g) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm
+// nn.LayerNorm(c) over the REAL c channels (eps 1e-5, biased variance; MST_Plus_Plus.py:57-65),
+// fp32 in -> bf16 out (padded channels written as 0).  One warp per pixel.
+struct LnP {
+    const float *in; bf16 *out; const float *gamma, *beta;
+    long long rows; int c, Cp;
+};
+template <int PER>   // channels per lane = Cp / 32
+__global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ LnP p) {
+    const int lane = threadIdx.x & 31;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += (long long)gridDim.x * 8) {
+        float v[PER];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int ch = lane + 32 * i;
+            v[i] = ch < p.c ? p.in[row * p.Cp + ch] : 0.f;
+            s += v[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)p.c;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int ch = lane + 32 * i;
+            const float d = ch < p.c ? v[i] - mean : 0.f;
+            q += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / (float)p.c + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int ch = lane + 32 * i;
+            const float y = ch < p.c ? (v[i] - mean) * rstd * __ldg(p.gamma + ch) + __ldg(p.beta + ch) : 0.f;
+            p.out[row * p.Cp + ch] = __float2bfloat16_rn(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ attention statistics
+// Per image and head: G[i][j] = sum_px k[px][i] q[px][j], nk[i] = sum k^2, nq[j] = sum q^2
+// (MST_Plus_Plus.py:127-129: the L2 normalisation runs over ALL pixels, so the reduction is global).
+// stats layout per (image, head): 32 x 32 floats; row i < 31, col j < 31: G; [i][31] = nk[i];
+// [31][j] = nq[j].
+struct AttnStatP {
+    const bf16 *qkv;     // [B*rows, 3*Cp]: q | k | v
+    float *stats;        // [B][heads][32][32], zeroed
+    int rows, Cp, heads, px_per_cta;
+};
+__global__ void __launch_bounds__(1024) attn_stats_kernel(const __grid_constant__ AttnStatP p) {
+    constexpr int TP = 64;
+    __shared__ float qs[TP][32], ks[TP][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // j, i
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int p0 = blockIdx.x * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
+    const int ld = 3 * p.Cp;
+    const bf16 *base = p.qkv + (long long)b * p.rows * ld + head * NF;
+    float acc = 0.f;
+    for (int t0 = p0; t0 < p1; t0 += TP) {
+        // tile load: TP pixels x 31 channels of q and k (thread -> (pixel, channel) pairs)
+        for (int e = threadIdx.x; e < TP * 32; e += 1024) {
+            const int px = e >> 5, ch = e & 31;
+            float qv = 0.f, kv = 0.f;
+            if (t0 + px < p1 && ch < NF) {
+                const bf16 *r = base + (long long)(t0 + px) * ld + ch;
+                qv = __bfloat162float(r[0]);
+                kv = __bfloat162float(r[p.Cp]);
+            }
+            qs[px][ch] = qv;
+            ks[px][ch] = kv;
+        }
+        __syncthreads();
+        if (ty < NF && tx < NF) {
+#pragma unroll 8
+            for (int px = 0; px < TP; ++px) acc = fmaf(ks[px][ty], qs[px][tx], acc);
+        } else if (ty < NF) {            // tx == 31: |k_i|^2
+#pragma unroll 8
+            for (int px = 0; px < TP; ++px) acc = fmaf(ks[px][ty], ks[px][ty], acc);
+        } else if (tx < NF) {            // ty == 31: |q_j|^2
+#pragma unroll 8
+            for (int px = 0; px < TP; ++px) acc = fmaf(qs[px][tx], qs[px][tx], acc);
+        }
+        __syncthreads();
+    }
+    atomicAdd(p.stats + (((long long)b * p.heads + head) * 32 + ty) * 32 + tx, acc);
+}
+
+// attn = softmax_j(rescale * G_ij / (max(|k_i|,1e-12) max(|q_j|,1e-12)))  (:127-131), then
+// M[co][h*31+j] = sum_i Wproj[co][h*31+i] attn_h[i][j]  -> bf16 [B][Cp][Cp] (zero padded).
+struct AttnFinP {
+    const float *stats; const float *rescale; const float *wproj;   // wproj fp32 [c][c]
+    bf16 *M;             // [B][Cp][Cp]
+    int c, Cp, heads;
+};
+__global__ void __launch_bounds__(1024) attn_finalize_kernel(const __grid_constant__ AttnFinP p) {
+    __shared__ float attn[4][31][32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    // softmax rows: one thread per (head, i)
+    if (tid < p.heads * NF) {
+        const int h = tid / NF, i = tid - h * NF;
+        const float *S = p.stats + ((long long)b * p.heads + h) * 1024;
+        const float nk = fmaxf(sqrtf(S[i * 32 + 31]), 1e-12f);
+        const float rs = __ldg(p.rescale + h);
+        float row[NF], mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const float nq = fmaxf(sqrtf(S[31 * 32 + j]), 1e-12f);
+            row[j] = S[i * 32 + j] / (nk * nq) * rs;
+            mx = fmaxf(mx, row[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) { row[j] = expf(row[j] - mx); sum += row[j]; }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) attn[h][i][j] = row[j] * inv;
+    }
+    __syncthreads();
+    bf16 *M = p.M + (long long)b * p.Cp * p.Cp;
+    for (int e = tid; e < p.Cp * p.Cp; e += 1024) {
+        const int co = e / p.Cp, k = e - co * p.Cp;
+        float v = 0.f;
+        if (co < p.c && k < p.c) {
+            const int h = k / NF, j = k - h * NF;
+            const float *wrow = p.wproj + (long long)co * p.c + h * NF;
+#pragma unroll
+            for (int i = 0; i < NF; ++i) v = fmaf(__ldg(wrow + i), attn[h][i][j], v);
+        }
+        M[e] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------ band projection
+// out[px][r] = sum_b cube[px][b] * w[r][b]  (uv_helpers.py:142-146 integrate_band / np.tensordot;
+// mantis_shrimp.py:49-60 uses ten such bands).  fp32, one thread per (pixel, receptor).
+__global__ void __launch_bounds__(256) band_project_kernel(const float *__restrict__ cube, const float *__restrict__ w, float *__restrict__ out,
+                                                           long long npx, int nb, int nr) {
+    extern __shared__ float wsm[];
+    for (int i = threadIdx.x; i < nb * nr; i += blockDim.x) wsm[i] = __ldg(w + i);
+    __syncthreads();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < npx * nr; e += (long long)gridDim.x * blockDim.x) {
+        const long long px = e / nr;
+        const int r = (int)(e - px * nr);
+        const float *c = cube + px * nb;
+        float acc = 0.f;
+        for (int k = 0; k < nb; ++k) acc = fmaf(__ldg(c + k), wsm[r * nb + k], acc);
+        out[e] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host: weights
+struct MsabW {
+    int c, Cp, heads, Hp;
+    const float *rescale, *wproj_f32, *bproj, *ln_g, *ln_b;       // device fp32
+    const float *pos0, *pos2, *ffn_dw;                            // device fp32 [9][Cp] / [9][Hp]
+    const bf16 *wqkv, *ffn0, *ffn4;                               // device bf16
+};
+struct BodyW {
+    const bf16 *embedding, *mapping;     // [32][9*32]
+    MsabW enc[2], bott, dec[2];
+    const bf16 *down[2];                 // [Cp_out][16*Cp_in]
+    const bf16 *up[2];                   // [4*Cp_out][Cp_in]
+    const float *up_bias[2];             // [4*Cp_out]
+    const bf16 *fuse[2];                 // [Cp_out][2*Cp_out]
+};
+struct Model {
+    int device;
+    void *blob;                          // one device allocation holding every tensor below
+    const float *conv_in;                // [27][32]
+    BodyW body[3];
+    const bf16 *conv_out;                // [32][9*32]
+};
+
+// Builder: appends host-side tensors to one staging buffer (256-byte aligned each) and records
+// where the device pointer must be patched once the blob is uploaded.
+struct Packer {
+    std::vector<uint8_t> host;
+    struct Fix { const void **slot; size_t off; };
+    std::vector<Fix> fixes;
+    size_t reserve(size_t bytes) {
+        const size_t off = (host.size() + 255) / 256 * 256;
+        host.resize(off + bytes, 0);
+        return off;
+    }
+    float *f32(const void **slot, size_t n) {
+        const size_t off = reserve(n * 4);
+        fixes.push_back({slot, off});
+        return reinterpret_cast<float *>(host.data() + off);
+    }
+    uint16_t *b16(const void **slot, size_t n) {
+        const size_t off = reserve(n * 2);
+        fixes.push_back({slot, off});
+        return reinterpret_cast<uint16_t *>(host.data() + off);
+    }
+};
+// NOTE: pointers returned by Packer::f32 / b16 are invalidated by the next reserve(); fill each
+// tensor right after asking for it, addressing through the offset.
+
+static uint16_t f2bf(float f) {          // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+struct Cursor {
+    const float *p; int64_t left;
+    const float *take(int64_t n) {
+        if (n > left) return nullptr;
+        const float *r = p; p += n; left -= n;
+        return r;
+    }
+};
+
+#define TAKE(var, n)                                   \
+    const float *var = cur.take(n);                    \
+    if (!var) return false;
+
+// dense [Cout][Cin] (row-major) -> bf16 [Np][Kp], optional row / column offsets for fused layouts
+static void put_dense(uint16_t *dst, int Kp, const float *w, int cout, int cin, int row0, int col0) {
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i) dst[(size_t)(row0 + o) * Kp + col0 + i] = f2bf(w[(size_t)o * cin + i]);
+}
+
+static bool pack_msab(Packer &pk, Cursor &cur, MsabW &m, int c) {
+    m.c = c; m.Cp = pad32(c); m.heads = c / NF; m.Hp = pad32(4 * c);
+    const int Cp = m.Cp, Hp = m.Hp;
+    TAKE(rescale, m.heads);
+    TAKE(wq, (int64_t)c * c); TAKE(wk, (int64_t)c * c); TAKE(wv, (int64_t)c * c);
+    TAKE(wp, (int64_t)c * c); TAKE(bp, c);
+    TAKE(pos0, (int64_t)c * 9); TAKE(pos2, (int64_t)c * 9);
+    TAKE(f0, (int64_t)4 * c * c); TAKE(f2, (int64_t)4 * c * 9); TAKE(f4, (int64_t)4 * c * c);
+    TAKE(lg, c); TAKE(lb, c);
+    { float *d = pk.f32((const void **)&m.rescale, 4); for (int i = 0; i < m.heads; ++i) d[i] = rescale[i]; }
+    { float *d = pk.f32((const void **)&m.wproj_f32, (size_t)c * c); memcpy(d, wp, sizeof(float) * c * c); }
+    { float *d = pk.f32((const void **)&m.bproj, Cp); for (int i = 0; i < c; ++i) d[i] = bp[i]; }
+    { float *d = pk.f32((const void **)&m.ln_g, Cp); for (int i = 0; i < c; ++i) d[i] = lg[i]; }
+    { float *d = pk.f32((const void **)&m.ln_b, Cp); for (int i = 0; i < c; ++i) d[i] = lb[i]; }
+    // depthwise weights (C,1,3,3) -> [9][Cp]
+    { float *d = pk.f32((const void **)&m.pos0, (size_t)9 * Cp); for (int ch = 0; ch < c; ++ch) for (int t = 0; t < 9; ++t) d[t * Cp + ch] = pos0[ch * 9 + t]; }
+    { float *d = pk.f32((const void **)&m.pos2, (size_t)9 * Cp); for (int ch = 0; ch < c; ++ch) for (int t = 0; t < 9; ++t) d[t * Cp + ch] = pos2[ch * 9 + t]; }
+    { float *d = pk.f32((const void **)&m.ffn_dw, (size_t)9 * Hp); for (int ch = 0; ch < 4 * c; ++ch) for (int t = 0; t < 9; ++t) d[t * Hp + ch] = f2[ch * 9 + t]; }
+    // q | k | v stacked along N: rows [0,c), [Cp,Cp+c), [2Cp,2Cp+c)
+    { uint16_t *d = pk.b16((const void **)&m.wqkv, (size_t)3 * Cp * Cp);
+      put_dense(d, Cp, wq, c, c, 0, 0); put_dense(d, Cp, wk, c, c, Cp, 0); put_dense(d, Cp, wv, c, c, 2 * Cp, 0); }
+    { uint16_t *d = pk.b16((const void **)&m.ffn0, (size_t)Hp * Cp); put_dense(d, Cp, f0, 4 * c, c, 0, 0); }
+    { uint16_t *d = pk.b16((const void **)&m.ffn4, (size_t)Cp * Hp); put_dense(d, Hp, f4, c, 4 * c, 0, 0); }
+    return true;
+}
+
+// Conv2d weight (Cout, Cin, kh, kw) -> bf16 [Np][kh*kw*Cp_in], k = (ky*kw+kx)*Cp_in + ci
+static void put_conv(uint16_t *dst, const float *w, int cout, int cin, int kh, int kw, int Cpin) {
+    const int K = kh * kw * Cpin;
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < kh * kw; ++t) dst[(size_t)o * K + t * Cpin + i] = f2bf(w[((size_t)o * cin + i) * kh * kw + t]);
+}
+
+static bool pack_model(Packer &pk, Model &M, const float *params, int64_t count) {
+    Cursor cur{params, count};
+    {
+        TAKE(w, 31 * 3 * 9);
+        float *d = pk.f32((const void **)&M.conv_in, 27 * 32);
+        for (int co = 0; co < 31; ++co)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int t = 0; t < 9; ++t) d[(t * 3 + ci) * 32 + co] = w[(co * 3 + ci) * 9 + t];
+    }
+    for (int s = 0; s < 3; ++s) {
+        BodyW &B = M.body[s];
+        { TAKE(w, 31 * 31 * 9); uint16_t *d = pk.b16((const void **)&B.embedding, (size_t)32 * 288); put_conv(d, w, 31, 31, 3, 3, 32); }
+        int c = NF;
+        for (int i = 0; i < 2; ++i) {
+            if (!pack_msab(pk, cur, B.enc[i], c)) return false;
+            TAKE(w, (int64_t)2 * c * c * 16);
+            const int Cpi = pad32(c), Cpo = pad32(2 * c);
+            uint16_t *d = pk.b16((const void **)&B.down[i], (size_t)Cpo * 16 * Cpi);
+            put_conv(d, w, 2 * c, c, 4, 4, Cpi);
+            c *= 2;
+        }
+        if (!pack_msab(pk, cur, B.bott, c)) return false;
+        for (int i = 0; i < 2; ++i) {
+            const int co = c / 2, Cpi = pad32(c), Cpo = pad32(co);
+            TAKE(wt, (int64_t)c * co * 4);       // ConvTranspose2d weight (Cin, Cout, 2, 2)
+            TAKE(bt, co);
+            TAKE(wf, (int64_t)co * c);           // fusion 1x1 (Cout=co, Cin=c = [up | skip])
+            { uint16_t *d = pk.b16((const void **)&B.up[i], (size_t)4 * Cpo * Cpi);
+              for (int ci = 0; ci < c; ++ci)
+                  for (int o = 0; o < co; ++o)
+                      for (int q = 0; q < 4; ++q) d[(size_t)(q * Cpo + o) * Cpi + ci] = f2bf(wt[((size_t)ci * co + o) * 4 + q]); }
+            { float *d = pk.f32((const void **)&B.up_bias[i], (size_t)4 * Cpo);
+              for (int q = 0; q < 4; ++q) for (int o = 0; o < co; ++o) d[q * Cpo + o] = bt[o]; }
+            { uint16_t *d = pk.b16((const void **)&B.fuse[i], (size_t)Cpo * 2 * Cpo);
+              for (int o = 0; o < co; ++o) {
+                  for (int k = 0; k < co; ++k) d[(size_t)o * 2 * Cpo + k] = f2bf(wf[(size_t)o * c + k]);                 // up half
+                  for (int k = 0; k < co; ++k) d[(size_t)o * 2 * Cpo + Cpo + k] = f2bf(wf[(size_t)o * c + co + k]);      // skip half
+              } }
+            if (!pack_msab(pk, cur, B.dec[i], co)) return false;
+            c = co;
+        }
+        { TAKE(w, 31 * 31 * 9); uint16_t *d = pk.b16((const void **)&B.mapping, (size_t)32 * 288); put_conv(d, w, 31, 31, 3, 3, 32); }
+    }
+    { TAKE(w, 31 * 31 * 9); uint16_t *d = pk.b16((const void **)&M.conv_out, (size_t)32 * 288); put_conv(d, w, 31, 31, 3, 3, 32); }
+    return cur.left == 0;
+}
+
+// ------------------------------------------------------------------------------------ host: schedule
+struct Workspace {
+    float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0, *stats;
+    bf16 *qkv, *p1, *p2, *ln, *hid1, *hid2, *M;
+    size_t bytes;
+};
+static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
+    const size_t n0 = (size_t)B * Hp * Wp, n1 = n0 / 4, n2 = n0 / 16;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return base ? base + o : nullptr; };
+#define WS_F(name, elems) { float *ptr = (float *)take((elems) * 4); if (w) w->name = ptr; }
+#define WS_B(name, elems) { bf16 *ptr = (bf16 *)take((elems) * 2); if (w) w->name = ptr; }
+    WS_F(x0, n0 * 32) WS_F(hA, n0 * 32) WS_F(hB, n0 * 32) WS_F(f0, n0 * 32) WS_F(f1, n1 * 64) WS_F(f2, n2 * 128)
+    WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32) WS_F(stats, (size_t)B * 4 * 1024)
+    WS_B(qkv, n0 * 96) WS_B(p1, n0 * 32) WS_B(p2, n0 * 32) WS_B(ln, n0 * 32) WS_B(hid1, n0 * 128) WS_B(hid2, n0 * 128)
+    WS_B(M, (size_t)B * 128 * 128)
+#undef WS_F
+#undef WS_B
+    if (w) w->bytes = off;
+    return off;
+}
+
+struct Ctx {
+    cudaStream_t st;
+    int B;
+    int err;
+};
+
+template <int BN, bool A_BF16, int MODE>
+static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
+    dim3 grid((p.rows + BM - 1) / BM, p.Np / BN, cx.B);
+    AVB_TIMED(name, cx.st);
+    gemm_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
+}
+template <bool A_BF16, int MODE>
+static void launch_gemm(Ctx &cx, const GemmP &p, const char *name) {
+    if (p.Np % 128 == 0) launch_gemm_t<128, A_BF16, MODE>(cx, p, name);
+    else if (p.Np % 64 == 0) launch_gemm_t<64, A_BF16, MODE>(cx, p, name);
+    else launch_gemm_t<32, A_BF16, MODE>(cx, p, name);
+}
+
+static GemmP gemm_defaults() {
+    GemmP p{};
+    p.out_mode = OUT_ROWS;
+    return p;
+}
+
+static void conv3x3(Ctx &cx, const float *in, const bf16 *w, float *out, const float *res, int H, int W) {
+    GemmP p = gemm_defaults();
+    p.A1 = in; p.lda1 = 32; p.K1 = p.K = 288; p.W = w; p.Np = 32; p.rows = H * W;
+    p.Hi = p.Ho = H; p.Wi = p.Wo = W; p.Cpin = 32;
+    p.res1 = res; p.ldr1 = 32; p.out = out; p.ldo = 32;
+    launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
+}
+
+static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const float *w, int H, int W, int Cp, int gelu_out, const char *name) {
+    DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out};
+    const long long total = (long long)cx.B * H * W * (Cp / 8);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    AVB_TIMED(name, cx.st);
+    dwconv_kernel<<<blocks, 256, 0, cx.st>>>(p);
+}
+
+// MSAB with num_blocks = 1 (MST_Plus_Plus.py:160-186), in place on x (fp32 [B*rows, Cp]).
+static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws) {
+    const int rows = H * W, Cp = m.Cp, Hp = m.Hp;
+    // q | k | v
+    {
+        GemmP p = gemm_defaults();
+        p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.Np = 3 * Cp; p.rows = rows;
+        p.out = ws.qkv; p.ldo = 3 * Cp; p.out_bf16 = 1;
+        launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_qkv");
+    }
+    // Gram + norms over all pixels
+    cudaMemsetAsync(ws.stats, 0, sizeof(float) * (size_t)cx.B * m.heads * 1024, cx.st);
+    {
+        AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
+        int ctas = std::max(1, std::min((rows + 511) / 512, sm_count() * 2 / std::max(1, cx.B * m.heads)));
+        p.px_per_cta = ((rows + ctas - 1) / ctas + 63) / 64 * 64;
+        ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
+        AVB_TIMED("k4_attn_stats", cx.st);
+        attn_stats_kernel<<<dim3(ctas, m.heads, cx.B), 1024, 0, cx.st>>>(p);
+    }
+    {
+        AttnFinP p{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
+        AVB_TIMED("k4_attn_finalize", cx.st);
+        attn_finalize_kernel<<<cx.B, 1024, 0, cx.st>>>(p);
+    }
+    // pos_emb(v): dw3x3 -> GELU -> dw3x3
+    dwconv(cx, ws.qkv + 2 * Cp, 3 * Cp, ws.p1, Cp, m.pos0, H, W, Cp, 1, "k4_dw_pos");
+    dwconv(cx, ws.p1, Cp, ws.p2, Cp, m.pos2, H, W, Cp, 0, "k4_dw_pos");
+    // x = v M^T + b + pos + x
+    {
+        GemmP p = gemm_defaults();
+        p.A1 = ws.qkv + 2 * Cp; p.lda1 = 3 * Cp; p.K1 = p.K = Cp; p.W = ws.M; p.w_bstride = (long long)Cp * Cp; p.Np = Cp; p.rows = rows;
+        p.bias = m.bproj; p.res1 = x; p.ldr1 = Cp; p.res2 = ws.p2; p.ldr2 = Cp; p.out = x; p.ldo = Cp;
+        launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_attn_proj");
+    }
+    // FFN: x = W4 GELU(dw(GELU(W0 LN(x)))) + x
+    {
+        LnP p{x, ws.ln, m.ln_g, m.ln_b, (long long)cx.B * rows, m.c, Cp};
+        const int blocks = (int)std::min<long long>((p.rows + 7) / 8, (long long)sm_count() * 16);
+        AVB_TIMED("k4_layernorm", cx.st);
+        if (Cp == 32) layernorm_kernel<1><<<blocks, 256, 0, cx.st>>>(p);
+        else if (Cp == 64) layernorm_kernel<2><<<blocks, 256, 0, cx.st>>>(p);
+        else layernorm_kernel<4><<<blocks, 256, 0, cx.st>>>(p);
+    }
+    {
+        GemmP p = gemm_defaults();
+        p.A1 = ws.ln; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.ffn0; p.Np = Hp; p.rows = rows;
+        p.gelu = 1; p.out = ws.hid1; p.ldo = Hp; p.out_bf16 = 1;
+        launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_ffn0");
+    }
+    dwconv(cx, ws.hid1, Hp, ws.hid2, Hp, m.ffn_dw, H, W, Hp, 1, "k4_dw_ffn");
+    {
+        GemmP p = gemm_defaults();
+        p.A1 = ws.hid2; p.lda1 = Hp; p.K1 = p.K = Hp; p.W = m.ffn4; p.Np = Cp; p.rows = rows;
+        p.res1 = x; p.ldr1 = Cp; p.out = x; p.ldo = Cp;
+        launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_ffn4");
+    }
+}
+
+// MST body (MST_Plus_Plus.py:240-268): in -> out (both fp32 [B, H, W, 32])
+static void mst_body(Ctx &cx, const BodyW &Bw, const float *in, float *out, int H, int W, Workspace &ws) {
+    conv3x3(cx, in, Bw.embedding, ws.f0, nullptr, H, W);
+    float *lvl[3] = {ws.f0, ws.f1, ws.f2};
+    int h = H, w = W, c = NF;
+    for (int i = 0; i < 2; ++i) {
+        msab(cx, Bw.enc[i], lvl[i], h, w, ws);
+        GemmP p = gemm_defaults();       // Conv2d(c, 2c, 4, 2, 1)
+        p.A1 = lvl[i]; p.lda1 = pad32(c); p.Cpin = pad32(c); p.K1 = p.K = 16 * pad32(c); p.W = Bw.down[i]; p.Np = pad32(2 * c);
+        p.Hi = h; p.Wi = w; p.Ho = h / 2; p.Wo = w / 2; p.rows = (h / 2) * (w / 2);
+        p.out = lvl[i + 1]; p.ldo = pad32(2 * c);
+        launch_gemm<false, MODE_C4S2>(cx, p, "k4_conv4x4s2");
+        h /= 2; w /= 2; c *= 2;
+    }
+    msab(cx, Bw.bott, ws.f2, h, w, ws);
+    float *cur = ws.f2;
+    float *ups[2] = {ws.u1, ws.u0}, *decs[2] = {ws.d1, ws.d0}, *skips[2] = {ws.f1, ws.f0};
+    for (int i = 0; i < 2; ++i) {
+        const int co = c / 2, Cpi = pad32(c), Cpo = pad32(co);
+        {   // ConvTranspose2d(c, c/2, 2, 2) + bias
+            GemmP p = gemm_defaults();
+            p.A1 = cur; p.lda1 = Cpi; p.K1 = p.K = Cpi; p.W = Bw.up[i]; p.Np = 4 * Cpo; p.rows = h * w;
+            p.Ho = h; p.Wo = w; p.bias = Bw.up_bias[i]; p.out = ups[i]; p.ldo = Cpo; p.out_mode = OUT_CONVT; p.Cpo = Cpo;
+            launch_gemm<false, MODE_PW>(cx, p, "k4_convT2x2");
+        }
+        h *= 2; w *= 2;
+        {   // 1x1 fusion of cat([up, skip])
+            GemmP p = gemm_defaults();
+            p.A1 = ups[i]; p.lda1 = Cpo; p.A2 = skips[i]; p.lda2 = Cpo; p.K1 = Cpo; p.K = 2 * Cpo; p.W = Bw.fuse[i]; p.Np = Cpo; p.rows = h * w;
+            p.out = decs[i]; p.ldo = Cpo;
+            launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_fuse");
+        }
+        msab(cx, Bw.dec[i], decs[i], h, w, ws);
+        cur = decs[i];
+        c = co;
+    }
+    conv3x3(cx, cur, Bw.mapping, out, in, H, W);      // mapping(fea) + x
+}
+
+}  // namespace k4
+}  // namespace avb
+
+using namespace avb;
+using namespace avb::k4;
+
+extern "C" int avb_mstpp_create(const float *params_host, int64_t count, void **handle) {
+    AVB_REQUIRE(params_host && handle, "null pointer");
+    if (count != N_PARAMS) {
+        set_error("avb_mstpp_create: expected %lld float32 parameters (MST_Plus_Plus state_dict order), got %lld",
+                  (long long)N_PARAMS, (long long)count);
+        return AVB_E_ARG;
+    }
+    Model *M = new Model();
+    Packer pk;
+    pk.host.reserve(8u << 20);
+    if (!pack_model(pk, *M, params_host, count)) {
+        delete M;
+        set_error("avb_mstpp_create: parameter blob does not match the MST++ architecture");
+        return AVB_E_ARG;
+    }
+    cudaError_t e = cudaGetDevice(&M->device);
+    if (e == cudaSuccess) e = cudaMalloc(&M->blob, pk.host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(M->blob, pk.host.data(), pk.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete M;
+        return cuda_fail(e, "avb_mstpp_create upload");
+    }
+    for (auto &f : pk.fixes) *f.slot = static_cast<uint8_t *>(M->blob) + f.off;
+    *handle = M;
+    return AVB_OK;
+}
+
+extern "C" int avb_mstpp_destroy(void *handle) {
+    if (!handle) return AVB_OK;
+    Model *M = static_cast<Model *>(handle);
+    cudaFree(M->blob);
+    delete M;
+    return AVB_OK;
+}
+
+static void padded_geometry(int H, int W, int multiple, int centred, int &Hp, int &Wp, int &top, int &left) {
+    const int ph = (multiple - H % multiple) % multiple, pw = (multiple - W % multiple) % multiple;
+    Hp = H + ph; Wp = W + pw;
+    top = centred ? ph / 2 : 0;
+    left = centred ? pw / 2 : 0;
+}
+
+extern "C" int64_t avb_mstpp_workspace_bytes(int n, int H, int W, int pad_multiple, int centred) {
+    if (n <= 0 || H <= 1 || W <= 1 || pad_multiple <= 0 || pad_multiple % 8) return 0;
+    int Hp, Wp, top, left;
+    padded_geometry(H, W, pad_multiple, centred, Hp, Wp, top, left);
+    return (int64_t)carve(nullptr, nullptr, n, Hp, Wp);
+}
+
+extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, float *out, int n, int H, int W,
+                                 int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream) {
+    AVB_REQUIRE(handle && in && out && workspace_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && n <= 65535 && H > 1 && W > 1, "bad geometry");
+    AVB_REQUIRE(pad_multiple > 0 && pad_multiple % 8 == 0, "pad_multiple must be a positive multiple of 8");
+    Model *M = static_cast<Model *>(handle);
+    int Hp, Wp, top, left;
+    padded_geometry(H, W, pad_multiple, centred, Hp, Wp, top, left);
+    AVB_REQUIRE(Hp - H < H && Wp - W < W, "frame too small for reflect padding");
+    Workspace ws{};
+    carve(&ws, static_cast<uint8_t *>(workspace_dev), n, Hp, Wp);
+    Ctx cx{static_cast<cudaStream_t>(stream), n, 0};
+    {
+        ConvInP p{in, in_is_u8, ws.x0, M->conv_in, n, H, W, Hp, Wp, top, left};
+        const long long npx = (long long)n * Hp * Wp;
+        const int blocks = (int)std::min<long long>((npx + 7) / 8, (long long)sm_count() * 16);
+        AVB_TIMED("k4_conv_in", cx.st);
+        conv_in_kernel<<<blocks, 256, 0, cx.st>>>(p);
+    }
+    const float *hin = ws.x0;
+    float *pp[2] = {ws.hA, ws.hB};
+    for (int s = 0; s < 3; ++s) {
+        mst_body(cx, M->body[s], hin, pp[s & 1], Hp, Wp, ws);
+        hin = pp[s & 1];
+    }
+    {   // conv_out(h) + conv_in(x), cropped to the input size, NHWC with 31 packed channels
+        GemmP p = gemm_defaults();
+        p.A1 = hin; p.lda1 = 32; p.K1 = p.K = 288; p.W = M->conv_out; p.Np = 32; p.rows = Hp * Wp;
+        p.Hi = p.Ho = Hp; p.Wi = p.Wo = Wp; p.Cpin = 32;
+        p.res1 = ws.x0; p.ldr1 = 32; p.out = out; p.out_mode = OUT_CROP; p.Hreal = H; p.Wreal = W; p.crop_top = top; p.crop_left = left;
+        launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_band_project_f32(const float *cube_dev, const float *weights_dev, float *out_dev,
+                                    int64_t npx, int n_bands, int n_receptors, avb_stream_t stream) {
+    AVB_REQUIRE(cube_dev && weights_dev && out_dev, "null pointer");
+    AVB_REQUIRE(npx > 0 && n_bands > 0 && n_receptors > 0 && n_bands * n_receptors <= 8192, "bad projection geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = npx * n_receptors;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    AVB_TIMED("k4_band_project", st);
+    band_project_kernel<<<blocks, 256, sizeof(float) * n_bands * n_receptors, st>>>(cube_dev, weights_dev, out_dev, npx, n_bands, n_receptors);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}

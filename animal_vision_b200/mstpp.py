@@ -1,0 +1,172 @@
+"""MST++ RGB -> hyperspectral inference on the GPU -- host side of K4.
+
+Mirrors the reference's two entry points:
+  * `MSTPlusPlus.forward(x)`            <-> MST_Plus_Plus.forward (architecture/MST_Plus_Plus.py:279-293):
+                                            NCHW float32 in [0,1] -> NCHW float32, 31 bands
+  * `MSTPlusPlus.predict_rgb_to_hsi(im)` <-> predict_rgb_to_hsi_torch (predict_torch.py:249-310):
+                                            HWC uint8/float frame -> HWC float32 cube (centred reflect pad
+                                            to a multiple of 16, crop), without fp16 autocast / OOM tiling
+Weights are handed over as the reference's own state_dict (the names of MST_Plus_Plus().state_dict());
+the reference ships none (model_zoo is git-ignored), so callers load a checkpoint themselves exactly
+as architecture/__init__.py:36-40 does and pass the dict.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Mapping
+
+import numpy as np
+
+from . import tables
+from ._abi import AvbError, check
+from .engine import get_engine
+
+N_FEAT = 31
+N_PARAMS = 1619625
+
+
+def param_order() -> "OrderedDict[str, tuple]":
+    """Names and shapes of MST_Plus_Plus().state_dict() in registration order (227 tensors)."""
+    sh: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def msab(prefix, dim, heads):
+        p = f"{prefix}.blocks.0."
+        sh[p + "0.rescale"] = (heads, 1, 1)
+        for n in ("to_q", "to_k", "to_v"):
+            sh[p + f"0.{n}.weight"] = (N_FEAT * heads, dim)
+        sh[p + "0.proj.weight"] = (dim, N_FEAT * heads)
+        sh[p + "0.proj.bias"] = (dim,)
+        sh[p + "0.pos_emb.0.weight"] = (dim, 1, 3, 3)
+        sh[p + "0.pos_emb.2.weight"] = (dim, 1, 3, 3)
+        sh[p + "1.fn.net.0.weight"] = (dim * 4, dim, 1, 1)
+        sh[p + "1.fn.net.2.weight"] = (dim * 4, 1, 3, 3)
+        sh[p + "1.fn.net.4.weight"] = (dim, dim * 4, 1, 1)
+        sh[p + "1.norm.weight"] = (dim,)
+        sh[p + "1.norm.bias"] = (dim,)
+
+    sh["conv_in.weight"] = (N_FEAT, 3, 3, 3)
+    for s in range(3):
+        b = f"body.{s}."
+        sh[b + "embedding.weight"] = (N_FEAT, N_FEAT, 3, 3)
+        dim = N_FEAT
+        for i in range(2):
+            msab(b + f"encoder_layers.{i}.0", dim, dim // N_FEAT)
+            sh[b + f"encoder_layers.{i}.1.weight"] = (dim * 2, dim, 4, 4)
+            dim *= 2
+        msab(b + "bottleneck", dim, dim // N_FEAT)
+        for i in range(2):
+            sh[b + f"decoder_layers.{i}.0.weight"] = (dim, dim // 2, 2, 2)
+            sh[b + f"decoder_layers.{i}.0.bias"] = (dim // 2,)
+            sh[b + f"decoder_layers.{i}.1.weight"] = (dim // 2, dim, 1, 1)
+            msab(b + f"decoder_layers.{i}.2", dim // 2, (dim // 2) // N_FEAT)
+            dim //= 2
+        sh[b + "mapping.weight"] = (N_FEAT, N_FEAT, 3, 3)
+    sh["conv_out.weight"] = (N_FEAT, N_FEAT, 3, 3)
+    return sh
+
+
+def flatten_state_dict(state_dict: Mapping[str, object]) -> np.ndarray:
+    """float32 vector of every parameter in registration order; tolerates the `module.` prefix of
+    DataParallel checkpoints like the reference loader (architecture/__init__.py:38-39)."""
+    sd = {k.replace("module.", "", 1) if k.startswith("module.") else k: v for k, v in state_dict.items()}
+    parts = []
+    for name, shape in param_order().items():
+        if name not in sd:
+            raise KeyError(f"state_dict is missing {name}")
+        t = sd[name]
+        a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+        parts.append(np.ascontiguousarray(a, np.float32).ravel())
+    flat = np.concatenate(parts)
+    assert flat.size == N_PARAMS
+    return flat
+
+
+class MSTPlusPlus:
+    def __init__(self, state_dict: Mapping[str, object], device=None):
+        self.eng = get_engine(device)
+        flat = flatten_state_dict(state_dict)
+        h = C.c_void_p()
+        with self.eng.torch.cuda.device(self.eng.device):
+            rc = self.eng.lib.avb_mstpp_create(flat.ctypes.data_as(C.c_void_p), flat.size, C.byref(h))
+        check(rc, "avb_mstpp_create")
+        self._h = h
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.eng.lib.avb_mstpp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _run(self, frames, pad_multiple: int, centred: bool):
+        """frames: CUDA tensor [N,H,W,3] float32 (in [0,1]) or uint8 -> float32 [N,H,W,31]."""
+        t = self.eng.torch
+        if not (isinstance(frames, t.Tensor) and frames.is_cuda and frames.dim() == 4 and frames.shape[3] == 3
+                and frames.dtype in (t.float32, t.uint8)):
+            raise AvbError("MSTPlusPlus: expected a CUDA tensor [N,H,W,3] of float32 or uint8")
+        frames = frames.contiguous()
+        n, h, w, _ = frames.shape
+        need = int(self.eng.lib.avb_mstpp_workspace_bytes(n, h, w, pad_multiple, int(centred)))
+        if need <= 0:
+            raise AvbError("avb_mstpp_workspace_bytes: bad geometry")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = t.empty(need, dtype=t.uint8, device=self.eng.device)
+        out = t.empty((n, h, w, N_FEAT), dtype=t.float32, device=self.eng.device)
+        rc = self.eng.lib.avb_mstpp_forward(self._h, frames.data_ptr(), int(frames.dtype == t.uint8), out.data_ptr(),
+                                            n, h, w, pad_multiple, int(centred), self._ws.data_ptr(), self.eng.stream_ptr())
+        check(rc, "avb_mstpp_forward")
+        return out
+
+    def forward_nhwc(self, frames):
+        """Model-direct semantics on channels-last frames: [N,H,W,3] -> [N,H,W,31]."""
+        return self._run(frames, 8, False)
+
+    def forward(self, x):
+        """MST_Plus_Plus.forward: NCHW float32 CUDA tensor [b,3,h,w] -> [b,31,h,w]."""
+        return self._run(x.permute(0, 2, 3, 1), 8, False).permute(0, 3, 1, 2)
+
+    __call__ = forward
+
+    def predict_rgb_to_hsi(self, image: np.ndarray) -> np.ndarray:
+        """predict_rgb_to_hsi_torch: HWC uint8 / float frame -> HWC float32 cube."""
+        t = self.eng.torch
+        a = np.asarray(image)
+        assert a.ndim == 3 and a.shape[2] == 3, "Input must be HxWx3"
+        if not np.issubdtype(a.dtype, np.integer):              # predict_torch.py:12-19
+            a = a.astype(np.float32)
+            if a.max() > 1.001:
+                a = np.clip(a / 255.0, 0.0, 1.0)
+            dev = t.from_numpy(np.ascontiguousarray(a)).to(self.eng.device)
+        else:
+            dev = t.from_numpy(np.ascontiguousarray(a.astype(np.uint8))).to(self.eng.device)
+        return self._run(dev[None], 16, True)[0].cpu().numpy()
+
+    def project_bands(self, cube, weights: np.ndarray):
+        """cube: CUDA float32 [..., B]; weights [R, B] (e.g. tables.mantis_band_matrix) -> [..., R]
+        (np.tensordot over the band axis: uv_helpers.py:142-146)."""
+        t = self.eng.torch
+        w = np.ascontiguousarray(weights, np.float32)
+        assert cube.is_cuda and cube.dtype == t.float32 and cube.shape[-1] == w.shape[1]
+        cube = cube.contiguous()
+        wd = t.from_numpy(w).to(self.eng.device)
+        out = t.empty(tuple(cube.shape[:-1]) + (w.shape[0],), dtype=t.float32, device=self.eng.device)
+        npx = cube.numel() // cube.shape[-1]
+        rc = self.eng.lib.avb_band_project_f32(cube.data_ptr(), wd.data_ptr(), out.data_ptr(), npx, w.shape[1], w.shape[0],
+                                               self.eng.stream_ptr())
+        check(rc, "avb_band_project_f32")
+        return out
+
+
+def mantis_bands(cube, model: MSTPlusPlus, wavelengths=None):
+    """The ten mantis-shrimp bands of animals/mantis_shrimp.py:49-60 integrated over an MST++ cube."""
+    lam = np.linspace(400.0, 700.0, N_FEAT, dtype=np.float32) if wavelengths is None else np.asarray(wavelengths, np.float32)
+    return model.project_bands(cube, tables.mantis_band_matrix(lam))

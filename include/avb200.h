@@ -172,6 +172,30 @@ AVB_API int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
                           int map_mode, const float *map_params_host, float mix_alpha,
                           void *workspace_dev, float *dbg_catches_dev, avb_stream_t stream);
 
+/* K4 -- MST++ RGB -> 31-band hyperspectral inference (reference
+ * ml/MST_plus_plus/predict_code/architecture/MST_Plus_Plus.py:270-293 MST_Plus_Plus.forward, wrapper
+ * semantics of ml/MST_plus_plus/predict_code/predict_torch.py:249-310).
+ *   avb_mstpp_create   params_host: the 1 619 625 float32 values of MST_Plus_Plus().state_dict() (227
+ *                      tensors, registration order, native layouts); padded / permuted / cast to bf16
+ *                      and uploaded once.  Replaces architecture/__init__.py:36-40 (weight loading).
+ *   avb_mstpp_forward  in: device [n,H,W,3] float32 in [0,1] (in_is_u8 = 0) or uint8 (in_is_u8 = 1,
+ *                      divided by 255: predict_torch.py:12-19); out: device float32 [n,H,W,31].
+ *                      pad_multiple / centred choose the reflect padding: (8, 0) = the model's own
+ *                      bottom/right pad (MST_Plus_Plus.py:284-288), (16, 1) = the wrapper's centred pad
+ *                      (predict_torch.py:171-188).
+ *   workspace_dev      avb_mstpp_workspace_bytes(n, H, W, pad_multiple, centred) bytes */
+AVB_API int avb_mstpp_create(const float *params_host, int64_t count, void **handle);
+AVB_API int avb_mstpp_destroy(void *handle);
+AVB_API int64_t avb_mstpp_workspace_bytes(int n, int H, int W, int pad_multiple, int centred);
+AVB_API int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, float *out, int n, int H, int W,
+                              int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream);
+
+/* Spectral band projection out[px][r] = sum_b cube[px][b] * weights[r][b] -- np.tensordot over the band
+ * axis as in uv_helpers.py:142-146 integrate_band and animals/mantis_shrimp.py:49-60 (ten bands);
+ * weights come from the host (uv_helpers.py:125-139 bandpass_weights).  All pointers device float32. */
+AVB_API int avb_band_project_f32(const float *cube_dev, const float *weights_dev, float *out_dev,
+                                 int64_t npx, int n_bands, int n_receptors, avb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""GPU parity for K4 (MST++ RGB -> 31-band cube): <= 1e-2 relative error, norm-wise (max-abs over
+max-abs and relative L2; SURVEY.md 8a-19 explains why element-wise relative error is the wrong gate
+for bf16 operands), against the fp32 reference network with seeded weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mstpp as O
+from oracle import uv
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2      # BASELINE.json north_star: <= 1e-2 relative on MST++ bf16 outputs vs the fp32 model
+
+
+def _rel(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.abs(got - ref).max() / np.abs(ref).max(), np.linalg.norm(got - ref) / np.linalg.norm(ref)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from animal_vision_b200.mstpp import MSTPlusPlus
+    sd = O.make_weights(0)
+    return MSTPlusPlus(sd), sd
+
+
+def test_against_reference_golden(model, golden):
+    """Fixture = the reference's own nn.Module run in place (tools/make_golden.py)."""
+    net, _ = model
+    x = torch.rand(1, 3, 42, 52, generator=torch.Generator().manual_seed(1))
+    y = net(x.cuda()).cpu().numpy()
+    ref = golden("mstpp")["y"]
+    assert y.shape == ref.shape == (1, 31, 42, 52)
+    mx, l2 = _rel(y, ref)
+    assert mx <= TOL and l2 <= TOL, f"max-abs rel {mx:.3e}, rel-L2 {l2:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 72), (2, 40, 88), (3, 17, 33), (1, 130, 94)])
+def test_against_oracle_shapes_and_batches(model, shape):
+    """Batches: the attention statistics are per image, so images must not see each other."""
+    net, sd = model
+    b, h, w = shape
+    x = torch.rand(b, 3, h, w, generator=torch.Generator().manual_seed(10 + h))
+    x[0, :, : h // 2] *= 0.3                       # make the images of a batch statistically different
+    ref = O.forward(x, sd).numpy()
+    y = net(x.cuda()).cpu().numpy()
+    mx, l2 = _rel(y, ref)
+    assert mx <= TOL and l2 <= TOL, f"{shape}: max-abs rel {mx:.3e}, rel-L2 {l2:.3e}"
+    for i in range(b):
+        mxi, l2i = _rel(y[i], ref[i])
+        assert mxi <= TOL and l2i <= TOL, f"{shape} image {i}: {mxi:.3e} {l2i:.3e}"
+
+
+def test_wrapper_route_uint8(model):
+    """predict_rgb_to_hsi_torch semantics: uint8 HWC in, centred reflect pad to x16, HWC cube out."""
+    net, sd = model
+    img = np.random.default_rng(3).integers(0, 256, (45, 70, 3), dtype=np.uint8)
+    ref = O.rgb_to_hsi(img, sd)
+    got = net.predict_rgb_to_hsi(img)
+    assert got.shape == ref.shape == (45, 70, 31) and got.dtype == np.float32
+    mx, l2 = _rel(got, ref)
+    assert mx <= TOL and l2 <= TOL, f"max-abs rel {mx:.3e}, rel-L2 {l2:.3e}"
+    f = img.astype(np.float32) / 255.0
+    mx, l2 = _rel(net.predict_rgb_to_hsi(f), ref)
+    assert mx <= TOL and l2 <= TOL
+
+
+def test_full_patch_482x512_and_mantis_bands(model):
+    """BASELINE configs[3]: a 482x512 patch, then the ten mantis-shrimp bands on the cube."""
+    from animal_vision_b200 import tables
+    net, sd = model
+    x = torch.rand(1, 3, 482, 512, generator=torch.Generator().manual_seed(1))
+    ref = O.forward(x, sd)
+    y = net(x.cuda())
+    mx, l2 = _rel(y.cpu().numpy(), ref.numpy())
+    assert mx <= TOL and l2 <= TOL, f"max-abs rel {mx:.3e}, rel-L2 {l2:.3e}"
+    lam = uv.default_wavelengths()
+    Wm = tables.mantis_band_matrix(lam)
+    assert np.array_equal(Wm, uv.mantis_band_matrix(lam))
+    cube = y[0].permute(1, 2, 0).contiguous()
+    got = net.project_bands(cube, Wm).cpu().numpy()
+    ref_b = uv.project_cube(cube.cpu().numpy(), Wm)              # projection of the SAME cube: fp32 exactness
+    assert np.abs(got - ref_b).max() <= 1e-5 * np.abs(ref_b).max()
+    ref_full = uv.project_cube(ref[0].permute(1, 2, 0).numpy(), Wm)
+    mx, l2 = _rel(got, ref_full)
+    assert mx <= TOL and l2 <= TOL
+
+
+def test_bad_state_dict_is_rejected():
+    from animal_vision_b200.mstpp import MSTPlusPlus
+    sd = O.make_weights(0)
+    sd.pop("conv_out.weight")
+    with pytest.raises(KeyError):
+        MSTPlusPlus(sd)
