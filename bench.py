@@ -112,18 +112,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def make_host_frames(rank: int, n_frames: int, H: int, W: int, pinned: bool):
-    """Per species: a uint8 [n_frames/3, H, W, 3] host tensor; frame s = default_rng(rank*n+s)."""
+def make_host_frames(rank: int, world: int, n_frames: int, H: int, W: int, pinned: bool):
+    """This rank's shard of the world x n_frames synthetic video, grouped per species: a uint8
+    [k, H, W, 3] host tensor each; global frame s is default_rng(s), its species round-robin in s."""
     import torch
-    per = n_frames // len(SPECIES)
+    from animal_vision_b200 import sharding
+    plan = sharding.shard_plan(world * n_frames, rank, world, SPECIES)
     out = {}
-    for k, sp in enumerate(SPECIES):
-        t = torch.empty((per, H, W, 3), dtype=torch.uint8)
+    for sp in SPECIES:
+        idx = [i for i, s in plan if s == sp]
+        t = torch.empty((len(idx), H, W, 3), dtype=torch.uint8)
         if pinned:
             t = t.pin_memory()
         view = t.numpy()
-        for j in range(per):
-            s = rank * n_frames + j * len(SPECIES) + k          # round-robin position in the video
+        for j, s in enumerate(idx):
             view[j] = np.random.default_rng(s).integers(0, 256, (H, W, 3), dtype=np.uint8)
         out[sp] = t
     return out
@@ -231,6 +233,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -258,7 +262,7 @@ def run_b200(args):
         return float(t.item())
 
     t_gen = time.time()
-    host = make_host_frames(rank, nf, H, W, pinned=True)
+    host = make_host_frames(rank, world, nf, H, W, pinned=True)
     log(f"[rank {rank}] generated {nf} host frames {W}x{H} in {time.time() - t_gen:.1f}s")
     dev_in = {sp: host[sp].to(dev, non_blocking=True) for sp in SPECIES}
     dev_out = {sp: ((torch.empty_like(dev_in[sp]), torch.empty_like(dev_in[sp])) if sp == "Cat" else torch.empty_like(dev_in[sp]))
