@@ -17,6 +17,7 @@
 //   phase 2  M = Wproj . blockdiag(attn)  (c x c, per image), out = v M^T + b + pos_emb(v) + x
 // -- i.e. attention-apply and the output projection become ONE pointwise GEMM on v.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -240,6 +241,264 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
         }
 }
 
+// ------------------------------------------------------------------------------------ tcgen05 implicit GEMM
+// Same tiling, loaders and epilogue contract as gemm_kernel, but the contraction runs on the
+// 5th-generation tensor cores: one elected thread issues tcgen05.mma (M = 128 rows, N = BN, K = 16
+// per instruction) on shared-memory operands described by UMMA descriptors, the fp32 accumulator
+// lives in TMEM (BN columns x 128 lanes) and comes back through tcgen05.ld for the epilogue.
+//
+// Operand layout in shared memory: canonical K-major, no swizzle -- 8x8 "core matrices" (8 rows x
+// 16 bytes, rows 16 B apart) tiled  [k-chunk of 8][row-block of 8]:
+//     offset(row, kchunk) = kchunk * LBO + (row / 8) * 128 + (row % 8) * 16,   SBO = 128 B,
+//     LBO = (rows / 8) * 128 B.
+// The loaders are ordinary threads (they convert fp32 -> bf16 and do the conv gathers), so each
+// stage is published to the async proxy with fence.proxy.async before the MMA is issued; a stage
+// is recycled when the tcgen05.commit mbarrier of the MMAs that read it has completed.
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46) (all >> 4), version = 1 at
+    // [46,48), layout type SWIZZLE_NONE = 0 at [61,64)
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, bool A_BF16, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmP p) {
+    constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;        // bytes between k-chunks of 8
+    constexpr int A_STAGE = (BK / 8) * A_LBO, B_STAGE = (BK / 8) * B_LBO;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    __shared__ __align__(1024) uint8_t As[2][A_STAGE];
+    __shared__ __align__(1024) uint8_t Bs[2][B_STAGE];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int m_base = blockIdx.x * BM, n_base = blockIdx.y * BN;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- A loader: thread -> (row, 16-wide half of the 32-wide chunk), as in gemm_kernel
+    const int lr = tid >> 1, lh = tid & 1;
+    const int lm = m_base + lr;
+    const bool row_ok = lm < p.rows;
+    int oy = 0, ox = 0;
+    if (MODE != MODE_PW) { oy = lm / p.Wo; ox = lm - oy * p.Wo; }
+    auto a_src = [&](int kbase, bool &ok) -> const void * {
+        ok = row_ok;
+        if (MODE == MODE_PW) {
+            const long long row = (long long)b * p.rows + lm;
+            if (kbase < p.K1) {
+                const long long off = row * p.lda1 + kbase + 16 * lh;
+                return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
+            }
+            const long long off = row * p.lda2 + (kbase - p.K1) + 16 * lh;
+            return A_BF16 ? (const void *)((const bf16 *)p.A2 + off) : (const void *)((const float *)p.A2 + off);
+        }
+        const int tap = kbase / p.Cpin, c0 = kbase - tap * p.Cpin;
+        int yy, xx;
+        if (MODE == MODE_C3) { yy = oy + tap / 3 - 1; xx = ox + tap % 3 - 1; }
+        else { yy = 2 * oy - 1 + (tap >> 2); xx = 2 * ox - 1 + (tap & 3); }
+        ok = row_ok && (unsigned)yy < (unsigned)p.Hi && (unsigned)xx < (unsigned)p.Wi;
+        const long long off = (((long long)b * p.Hi + yy) * p.Wi + xx) * p.lda1 + c0 + 16 * lh;
+        return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
+    };
+    uint4 areg[2];
+    auto a_fetch = [&](int kbase) {
+        bool ok;
+        const void *src = a_src(kbase, ok);
+        if (!ok) { areg[0] = areg[1] = make_uint4(0u, 0u, 0u, 0u); return; }
+        if (A_BF16) {
+            const uint4 *q = (const uint4 *)src;
+            areg[0] = __ldg(q); areg[1] = __ldg(q + 1);
+        } else {
+            const float4 *q = (const float4 *)src;
+            const float4 f0 = __ldg(q), f1 = __ldg(q + 1), f2 = __ldg(q + 2), f3 = __ldg(q + 3);
+            areg[0] = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            areg[1] = make_uint4(pack_bf16(f2.x, f2.y), pack_bf16(f2.z, f2.w), pack_bf16(f3.x, f3.y), pack_bf16(f3.z, f3.w));
+        }
+    };
+    auto a_store = [&](int st) {      // k-chunks 2*lh and 2*lh+1 of row lr
+        uint8_t *d = &As[st][(2 * lh) * A_LBO + (lr >> 3) * 128 + (lr & 7) * 16];
+        *reinterpret_cast<uint4 *>(d) = areg[0];
+        *reinterpret_cast<uint4 *>(d + A_LBO) = areg[1];
+    };
+    constexpr int B_PER_THREAD = (BN * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
+    const bf16 *Wb = p.W + (long long)b * p.w_bstride;
+    uint4 breg[B_PER_THREAD];
+    auto b_fetch = [&](int kbase) {
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int idx = tid + i * GEMM_THREADS;
+            if (idx < BN * 4) {
+                const int n = idx >> 2, q = idx & 3;
+                breg[i] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K + kbase) + q);
+            }
+        }
+    };
+    auto b_store = [&](int st) {
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int idx = tid + i * GEMM_THREADS;
+            if (idx < BN * 4) {
+                const int n = idx >> 2, q = idx & 3;
+                *reinterpret_cast<uint4 *>(&Bs[st][q * B_LBO + (n >> 3) * 128 + (n & 7) * 16]) = breg[i];
+            }
+        }
+    };
+
+    const int nk = p.K / BK;
+    a_fetch(0);
+    b_fetch(0);
+    a_store(0);
+    b_store(0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc & 1;
+        if (kc + 1 < nk) { a_fetch((kc + 1) * BK); b_fetch((kc + 1) * BK); }
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(&As[st][0]), b0 = smem_u32(&Bs[st][0]);
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j)
+                mma_f16(tmem_d, make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128), IDESC,
+                        (kc > 0 || j > 0) ? 1u : 0u);
+            mma_commit(&mbar[st]);          // arrives when every MMA issued so far has finished reading smem
+        }
+        if (kc + 1 < nk) {
+            if (kc >= 1) mbar_wait(&mbar[st ^ 1], (uint32_t)(((kc - 1) >> 1) & 1));    // chunk kc-1 done with stage st^1
+            a_store(st ^ 1);
+            b_store(st ^ 1);
+            fence_async_smem();
+        }
+        __syncthreads();
+    }
+    mbar_wait(&mbar[(nk - 1) & 1], (uint32_t)(((nk - 1) >> 1) & 1));
+    tc_fence_after();
+
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4).. (rows) and column half w/4
+    constexpr int HALF = BN / 2;
+    const int m = m_base + 32 * (warp & 3) + lane;
+    const int col0 = (warp >> 2) * HALF;
+    const long long row = (long long)b * p.rows + m;
+    long long obase = 0;
+    int cy = 0, cx = 0;
+    bool crop_ok = true;
+    if (p.out_mode == OUT_ROWS) obase = row * p.ldo;
+    else { cy = m / p.Wo; cx = m - cy * p.Wo; }
+    if (p.out_mode == OUT_CROP) {
+        cy -= p.crop_top; cx -= p.crop_left;
+        crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
+        obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
+    }
+#pragma unroll 1
+    for (int c = 0; c < HALF; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col0 + c), v);     // all lanes: .sync.aligned
+        if (m < p.rows) {
+            const int n0 = n_base + col0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (p.bias) v[i] += __ldg(p.bias + n0 + i);
+                if (p.gelu) v[i] = gelu(v[i]);
+            }
+            if (p.res1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 r = *reinterpret_cast<const float4 *>(p.res1 + row * p.ldr1 + n0 + i);
+                    v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                }
+            }
+            if (p.res2) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0 + i);
+                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { v[i + 2 * q] += __low2float(h2[q]); v[i + 2 * q + 1] += __high2float(h2[q]); }
+                }
+            }
+            if (p.out_mode == OUT_ROWS) {
+                if (p.out_bf16) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8)
+                        *reinterpret_cast<uint4 *>((bf16 *)p.out + obase + n0 + i) =
+                            make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4 *>((float *)p.out + obase + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            } else if (p.out_mode == OUT_CONVT) {
+                const int q = n0 / p.Cpo, co = n0 - q * p.Cpo;       // 16-column groups never straddle a (dy,dx) block
+                const long long o = ((((long long)b * 2 * p.Ho) + 2 * cy + (q >> 1)) * (2 * p.Wo) + 2 * cx + (q & 1)) * p.ldo + co;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4 *>((float *)p.out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else if (crop_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + i < NF) ((float *)p.out)[obase + n0 + i] = v[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+
 // ------------------------------------------------------------------------------------ conv_in
 // F.pad(reflect, bottom/right to a multiple of 8 -- or the wrapper's centred pad) + Conv2d(3, 31, 3,
 // padding=1, bias=False) (MST_Plus_Plus.py:284-289) -> fp32 [B, Hp, Wp, 32].
@@ -387,18 +646,27 @@ struct AttnStatP {
     float *stats;        // [B][heads][32][32], zeroed
     int rows, Cp, heads, px_per_cta;
 };
-__global__ void __launch_bounds__(1024) attn_stats_kernel(const __grid_constant__ AttnStatP p) {
-    constexpr int TP = 64;
-    __shared__ float qs[TP][32], ks[TP][32];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // j, i
+// 256 threads = 4 pixel groups x (8 x 8) threads, each thread a 4 x 4 register tile of G: per pixel
+// two LDS.128 feed 16 FMAs, so the kernel is bound by the FP32 pipe / HBM, not by shared memory.
+__global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__ AttnStatP p) {
+    constexpr int TP = 128;
+    __shared__ __align__(16) float qs[TP][32];
+    __shared__ __align__(16) float ks[TP][32];
+    const int tid = threadIdx.x;
+    const int grp = tid >> 6, t = tid & 63, ti = t >> 3, tj = t & 7;
     const int head = blockIdx.y, b = blockIdx.z;
     const int p0 = blockIdx.x * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
     const int ld = 3 * p.Cp;
     const bf16 *base = p.qkv + (long long)b * p.rows * ld + head * NF;
-    float acc = 0.f;
+    float acc[4][4], nk[4], nq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        nk[i] = nq[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
     for (int t0 = p0; t0 < p1; t0 += TP) {
-        // tile load: TP pixels x 31 channels of q and k (thread -> (pixel, channel) pairs)
-        for (int e = threadIdx.x; e < TP * 32; e += 1024) {
+        for (int e = tid; e < TP * 32; e += 256) {
             const int px = e >> 5, ch = e & 31;
             float qv = 0.f, kv = 0.f;
             if (t0 + px < p1 && ch < NF) {
@@ -410,19 +678,45 @@ __global__ void __launch_bounds__(1024) attn_stats_kernel(const __grid_constant_
             ks[px][ch] = kv;
         }
         __syncthreads();
-        if (ty < NF && tx < NF) {
-#pragma unroll 8
-            for (int px = 0; px < TP; ++px) acc = fmaf(ks[px][ty], qs[px][tx], acc);
-        } else if (ty < NF) {            // tx == 31: |k_i|^2
-#pragma unroll 8
-            for (int px = 0; px < TP; ++px) acc = fmaf(ks[px][ty], ks[px][ty], acc);
-        } else if (tx < NF) {            // ty == 31: |q_j|^2
-#pragma unroll 8
-            for (int px = 0; px < TP; ++px) acc = fmaf(qs[px][tx], qs[px][tx], acc);
+#pragma unroll 4
+        for (int px = grp; px < TP; px += 4) {
+            const float4 kv = *reinterpret_cast<const float4 *>(&ks[px][4 * ti]);
+            const float4 qv = *reinterpret_cast<const float4 *>(&qs[px][4 * tj]);
+            const float ka[4] = {kv.x, kv.y, kv.z, kv.w}, qa[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ka[i], qa[j], acc[i][j]);
+                nk[i] = fmaf(ka[i], ka[i], nk[i]);
+                nq[i] = fmaf(qa[i], qa[i], nq[i]);
+            }
         }
         __syncthreads();
     }
-    atomicAdd(p.stats + (((long long)b * p.heads + head) * 32 + ty) * 32 + tx, acc);
+    // reduce the four pixel groups through shared memory (reusing the tiles), then one atomic per entry
+    float *red = &qs[0][0];                       // [4][32][32] floats = 16 KB = qs
+    float *rn = &ks[0][0];                        // [4][2][32]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(grp * 32 + 4 * ti + i) * 32 + 4 * tj + j] = acc[i][j];
+    if (tj == 0)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rn[(grp * 2 + 0) * 32 + 4 * ti + i] = nk[i];
+    if (ti == 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rn[(grp * 2 + 1) * 32 + 4 * tj + j] = nq[j];
+    __syncthreads();
+    float *out = p.stats + ((long long)b * p.heads + head) * 1024;
+    for (int e = tid; e < 1024; e += 256) {
+        const int i = e >> 5, j = e & 31;
+        float v;
+        if (i < NF && j < NF) v = red[e] + red[1024 + e] + red[2048 + e] + red[3072 + e];
+        else if (i < NF) v = rn[i] + rn[64 + i] + rn[128 + i] + rn[192 + i];                  // [i][31] = |k_i|^2
+        else if (j < NF) v = rn[32 + j] + rn[96 + j] + rn[160 + j] + rn[224 + j];             // [31][j] = |q_j|^2
+        else v = 0.f;
+        atomicAdd(out + e, v);
+    }
 }
 
 // attn = softmax_j(rescale * G_ij / (max(|k_i|,1e-12) max(|q_j|,1e-12)))  (:127-131), then
@@ -669,14 +963,15 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 struct Ctx {
     cudaStream_t st;
     int B;
-    int err;
+    int legacy;      // AVB_K4_LEGACY_MMA=1: mma.sync (HMMA) GEMM core instead of tcgen05 (bring-up / A-B timing only)
 };
 
 template <int BN, bool A_BF16, int MODE>
 static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
     dim3 grid((p.rows + BM - 1) / BM, p.Np / BN, cx.B);
     AVB_TIMED(name, cx.st);
-    gemm_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
+    if (cx.legacy) gemm_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
+    else tc::gemm_tc_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
 }
 template <bool A_BF16, int MODE>
 static void launch_gemm(Ctx &cx, const GemmP &p, const char *name) {
@@ -721,11 +1016,11 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
     cudaMemsetAsync(ws.stats, 0, sizeof(float) * (size_t)cx.B * m.heads * 1024, cx.st);
     {
         AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
-        int ctas = std::max(1, std::min((rows + 511) / 512, sm_count() * 2 / std::max(1, cx.B * m.heads)));
-        p.px_per_cta = ((rows + ctas - 1) / ctas + 63) / 64 * 64;
+        int ctas = std::max(1, std::min((rows + 511) / 512, sm_count() * 4 / std::max(1, cx.B * m.heads)));
+        p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
         AVB_TIMED("k4_attn_stats", cx.st);
-        attn_stats_kernel<<<dim3(ctas, m.heads, cx.B), 1024, 0, cx.st>>>(p);
+        attn_stats_kernel<<<dim3(ctas, m.heads, cx.B), 256, 0, cx.st>>>(p);
     }
     {
         AttnFinP p{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
@@ -871,7 +1166,8 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
     AVB_REQUIRE(Hp - H < H && Wp - W < W, "frame too small for reflect padding");
     Workspace ws{};
     carve(&ws, static_cast<uint8_t *>(workspace_dev), n, Hp, Wp);
-    Ctx cx{static_cast<cudaStream_t>(stream), n, 0};
+    const char *leg = getenv("AVB_K4_LEGACY_MMA");
+    Ctx cx{static_cast<cudaStream_t>(stream), n, (leg && leg[0] == '1') ? 1 : 0};
     {
         ConvInP p{in, in_is_u8, ws.x0, M->conv_in, n, H, W, Hp, Wp, top, left};
         const long long npx = (long long)n * Hp * Wp;
