@@ -38,7 +38,7 @@ static inline int pad32(int c) { return (c + 31) / 32 * 32; }
 __device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------ implicit GEMM
-constexpr int BM = 128, BK = 32, APAD = 8;
+constexpr int BM = 128, BK = 32;
 constexpr int GEMM_THREADS = 256;
 
 enum { MODE_PW = 0, MODE_C3 = 1, MODE_C4S2 = 2 };
@@ -61,189 +61,15 @@ struct GemmP {
     int Hreal, Wreal, Cpo, crop_top, crop_left;   // OUT_CONVT: Cpo; OUT_CROP: real size + crop origin
 };
 
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem_ptr) {
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&t);
 }
 
+// ------------------------------------------------------------------------------------ tcgen05 implicit GEMM
 // One CTA: 128 output rows x BN output channels, K streamed in chunks of 32 through a two-stage
 // shared-memory ring (global loads of chunk i+1 are in flight while chunk i feeds the tensor cores).
-template <int BN, bool A_BF16, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmP p) {
-    __shared__ __align__(16) bf16 As[2][BM][BK + APAD];
-    __shared__ __align__(16) bf16 Bs[2][BN][BK + APAD];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int m_base = blockIdx.x * BM, n_base = blockIdx.y * BN;
-
-    // ---- A loader: thread -> (row, 16-wide half of the 32-wide chunk)
-    const int lr = tid >> 1, lh = tid & 1;
-    const int lm = m_base + lr;
-    const bool row_ok = lm < p.rows;
-    int oy = 0, ox = 0;
-    if (MODE != MODE_PW) { oy = lm / p.Wo; ox = lm - oy * p.Wo; }
-
-    auto a_src = [&](int kbase, bool &ok) -> const void * {
-        ok = row_ok;
-        if (MODE == MODE_PW) {
-            const long long row = (long long)b * p.rows + lm;
-            if (kbase < p.K1) {
-                const long long off = row * p.lda1 + kbase + 16 * lh;
-                return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
-            }
-            const long long off = row * p.lda2 + (kbase - p.K1) + 16 * lh;
-            return A_BF16 ? (const void *)((const bf16 *)p.A2 + off) : (const void *)((const float *)p.A2 + off);
-        }
-        const int tap = kbase / p.Cpin, c0 = kbase - tap * p.Cpin;
-        int yy, xx;
-        if (MODE == MODE_C3) { yy = oy + tap / 3 - 1; xx = ox + tap % 3 - 1; }
-        else { yy = 2 * oy - 1 + (tap >> 2); xx = 2 * ox - 1 + (tap & 3); }
-        ok = row_ok && (unsigned)yy < (unsigned)p.Hi && (unsigned)xx < (unsigned)p.Wi;
-        const long long off = (((long long)b * p.Hi + yy) * p.Wi + xx) * p.lda1 + c0 + 16 * lh;
-        return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
-    };
-    uint4 areg[2];
-    auto a_fetch = [&](int kbase) {
-        bool ok;
-        const void *src = a_src(kbase, ok);
-        if (!ok) { areg[0] = areg[1] = make_uint4(0u, 0u, 0u, 0u); return; }
-        if (A_BF16) {
-            const uint4 *q = (const uint4 *)src;
-            areg[0] = __ldg(q); areg[1] = __ldg(q + 1);
-        } else {
-            const float4 *q = (const float4 *)src;
-            const float4 f0 = __ldg(q), f1 = __ldg(q + 1), f2 = __ldg(q + 2), f3 = __ldg(q + 3);
-            areg[0] = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
-            areg[1] = make_uint4(pack_bf16(f2.x, f2.y), pack_bf16(f2.z, f2.w), pack_bf16(f3.x, f3.y), pack_bf16(f3.z, f3.w));
-        }
-    };
-    auto a_store = [&](int st) {
-        uint4 *d = reinterpret_cast<uint4 *>(&As[st][lr][16 * lh]);
-        d[0] = areg[0]; d[1] = areg[1];
-    };
-    // ---- B loader: BN rows x 32 k = BN*4 uint4
-    constexpr int B_PER_THREAD = (BN * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
-    const bf16 *Wb = p.W + (long long)b * p.w_bstride;
-    uint4 breg[B_PER_THREAD];
-    auto b_fetch = [&](int kbase) {
-#pragma unroll
-        for (int i = 0; i < B_PER_THREAD; ++i) {
-            const int idx = tid + i * GEMM_THREADS;
-            if (idx < BN * 4) {
-                const int n = idx >> 2, q = idx & 3;
-                breg[i] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K + kbase) + q);
-            }
-        }
-    };
-    auto b_store = [&](int st) {
-#pragma unroll
-        for (int i = 0; i < B_PER_THREAD; ++i) {
-            const int idx = tid + i * GEMM_THREADS;
-            if (idx < BN * 4) *reinterpret_cast<uint4 *>(&Bs[st][idx >> 2][(idx & 3) * 8]) = breg[i];
-        }
-    };
-
-    // ---- warp tiling: 4 (M) x 2 (N) warps, warp tile 32 x BN/2
-    constexpr int WN = BN / 2, NT = WN / 8;
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
-    float acc[2][NT][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
-
-    const int nk = p.K / BK;
-    a_fetch(0);
-    b_fetch(0);
-    a_store(0);
-    b_store(0);
-    __syncthreads();
-    for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc & 1;
-        if (kc + 1 < nk) { a_fetch((kc + 1) * BK); b_fetch((kc + 1) * BK); }
-#pragma unroll
-        for (int ks = 0; ks < BK; ks += 16) {
-            uint32_t af[2][4];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) ldmatrix_x4(af[i], &As[st][wm + i * 16 + (lane & 15)][ks + (lane >> 4) * 8]);
-#pragma unroll
-            for (int j = 0; j < NT; j += 2) {
-                uint32_t bfr[4];
-                ldmatrix_x4(bfr, &Bs[st][wn + j * 8 + ((lane >> 4) << 3) + (lane & 7)][ks + ((lane >> 3) & 1) * 8]);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    mma_bf16(acc[i][j], af[i], bfr[0], bfr[1]);
-                    if (j + 1 < NT) mma_bf16(acc[i][j + 1], af[i], bfr[2], bfr[3]);
-                }
-            }
-        }
-        if (kc + 1 < nk) { a_store(st ^ 1); b_store(st ^ 1); }
-        __syncthreads();
-    }
-
-    // ---- epilogue: bias -> GELU -> residuals -> store
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-            const int m = m_base + wm + i * 16 + (lane >> 2) + hrow * 8;
-            if (m >= p.rows) continue;
-            const long long row = (long long)b * p.rows + m;
-            long long obase = 0;
-            int cy = 0, cx = 0;
-            bool crop_ok = true;
-            if (p.out_mode == OUT_ROWS) obase = row * p.ldo;
-            else { cy = m / p.Wo; cx = m - cy * p.Wo; }
-            if (p.out_mode == OUT_CROP) {
-                cy -= p.crop_top; cx -= p.crop_left;
-                crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
-                obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int n = n_base + wn + j * 8 + (lane & 3) * 2;
-                float v0 = acc[i][j][hrow * 2], v1 = acc[i][j][hrow * 2 + 1];
-                if (p.bias) { v0 += __ldg(p.bias + n); v1 += __ldg(p.bias + n + 1); }
-                if (p.gelu) { v0 = gelu(v0); v1 = gelu(v1); }
-                if (p.res1) {
-                    const float2 r = *reinterpret_cast<const float2 *>(p.res1 + row * p.ldr1 + n);
-                    v0 += r.x; v1 += r.y;
-                }
-                if (p.res2) {
-                    const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162 *>(p.res2 + row * p.ldr2 + n);
-                    v0 += __low2float(r); v1 += __high2float(r);
-                }
-                if (p.out_mode == OUT_ROWS) {
-                    if (p.out_bf16) *reinterpret_cast<uint32_t *>((bf16 *)p.out + obase + n) = pack_bf16(v0, v1);
-                    else *reinterpret_cast<float2 *>((float *)p.out + obase + n) = make_float2(v0, v1);
-                } else if (p.out_mode == OUT_CONVT) {
-                    // ConvTranspose2d(k=2, s=2): column block q = dy*2+dx lands on pixel (2y+dy, 2x+dx)
-                    const int q = n / p.Cpo, co = n - q * p.Cpo;
-                    const long long o = ((((long long)b * 2 * p.Ho) + 2 * cy + (q >> 1)) * (2 * p.Wo) + 2 * cx + (q & 1)) * p.ldo + co;
-                    *reinterpret_cast<float2 *>((float *)p.out + o) = make_float2(v0, v1);
-                } else if (crop_ok) {
-                    if (n < NF) ((float *)p.out)[obase + n] = v0;
-                    if (n + 1 < NF) ((float *)p.out)[obase + n + 1] = v1;
-                }
-            }
-        }
-}
-
-// ------------------------------------------------------------------------------------ tcgen05 implicit GEMM
-// Same tiling, loaders and epilogue contract as gemm_kernel, but the contraction runs on the
-// 5th-generation tensor cores: one elected thread issues tcgen05.mma (M = 128 rows, N = BN, K = 16
+// The contraction runs on the 5th-generation tensor cores: one elected thread issues tcgen05.mma (M = 128 rows, N = BN, K = 16
 // per instruction) on shared-memory operands described by UMMA descriptors, the fp32 accumulator
 // lives in TMEM (BN columns x 128 lanes) and comes back through tcgen05.ld for the epilogue.
 //
@@ -319,7 +145,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // ---- A loader: thread -> (row, 16-wide half of the 32-wide chunk), as in gemm_kernel
+    // ---- A loader: thread -> (row, 16-wide half of the 32-wide chunk)
     const int lr = tid >> 1, lh = tid & 1;
     const int lm = m_base + lr;
     const bool row_ok = lm < p.rows;
@@ -550,48 +376,84 @@ struct DwP {
     const bf16 *in; int ldi;
     bf16 *out; int ldo;
     const float *w;               // [9][Cp]
-    int B, H, W, Cp, gelu_out;
+    int B, H, W, Cp, gelu_out, seg;
 };
-__global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwP p) {
-    const int groups = p.Cp >> 3;                       // 8 channels per thread
-    const long long total = (long long)p.B * p.H * p.W * groups;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % groups);
-        const long long px = idx / groups;
-        const int x = (int)(px % p.W);
-        const long long t = px / p.W;
-        const int y = (int)(t % p.H), b = (int)(t / p.H);
-        float acc[8];
+// Thread = (image, column x, group of 8 channels); it walks down a segment of rows keeping the
+// 3 x 3 x 8 input window (fp32) and its 72 weights in registers: three 16-byte loads per output
+// instead of nine plus eighteen weight loads.
+__device__ __forceinline__ void dw_unpack(const uint4 &raw, float (&f)[8]) {
+    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int q = 0; q < 4; ++q) { f[2 * q] = __low2float(h2[q]); f[2 * q + 1] = __high2float(h2[q]); }
+}
+__global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP p) {
+    const int groups = p.Cp >> 3;
+    const int segs = (p.H + p.seg - 1) / p.seg;
+    const long long total = (long long)p.B * segs * p.W * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    long long t = idx / groups;
+    const int x = (int)(t % p.W);
+    t /= p.W;
+    const int sg = (int)(t % segs), b = (int)(t / segs);
+    const int y0 = sg * p.seg, y1 = min(p.H, y0 + p.seg);
+
+    float w[9][8];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int yy = y + ky - 1;
-            if ((unsigned)yy >= (unsigned)p.H) continue;
+    for (int k = 0; k < 9; ++k) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + 8 * g));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + 8 * g) + 1);
+        w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+        w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+    }
+    const bf16 *base = p.in + (long long)b * p.H * p.W * p.ldi + 8 * g;
+    const bool has_l = x > 0, has_r = x + 1 < p.W;
+    auto load_row = [&](int y, uint4 (&raw)[3]) {
+        raw[0] = raw[1] = raw[2] = make_uint4(0u, 0u, 0u, 0u);        // conv zero padding
+        if ((unsigned)y < (unsigned)p.H) {
+            const bf16 *r = base + ((long long)y * p.W + x) * p.ldi;
+            if (has_l) raw[0] = __ldg(reinterpret_cast<const uint4 *>(r - p.ldi));
+            raw[1] = __ldg(reinterpret_cast<const uint4 *>(r));
+            if (has_r) raw[2] = __ldg(reinterpret_cast<const uint4 *>(r + p.ldi));
+        }
+    };
+    float win[3][3][8];               // [row slot][dx][channel]
+    uint4 raw[3];
+    load_row(y0 - 1, raw);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = x + kx - 1;
-                if ((unsigned)xx >= (unsigned)p.W) continue;
-                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.in + (((long long)b * p.H + yy) * p.W + xx) * p.ldi + 8 * g));
-                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + (ky * 3 + kx) * p.Cp + 8 * g));
-                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(p.w + (ky * 3 + kx) * p.Cp + 8 * g) + 1);
-                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[0][d]);
+    load_row(y0, raw);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    acc[2 * q] = fmaf(__low2float(h2[q]), wv[2 * q], acc[2 * q]);
-                    acc[2 * q + 1] = fmaf(__high2float(h2[q]), wv[2 * q + 1], acc[2 * q + 1]);
+    for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[1][d]);
+    load_row(y0 + 1, raw);
+    for (int yb = y0; yb < y1; yb += 3) {
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {           // static rotation of the three row slots
+            const int y = yb + ph;
+            if (y < y1) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[(ph + 2) % 3][d]);      // row y + 1
+                if (y + 1 < y1) load_row(y + 2, raw);
+                float acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[c] = fmaf(win[(ph + ky) % 3][kx][c], w[ky * 3 + kx][c], acc[c]);
+                if (p.gelu_out) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = gelu(acc[c]);
                 }
+                uint4 o;
+                o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+                o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+                *reinterpret_cast<uint4 *>(p.out + (((long long)b * p.H + y) * p.W + x) * p.ldo + 8 * g) = o;
             }
         }
-        if (p.gelu_out) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = gelu(acc[c]);
-        }
-        uint4 o;
-        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-        *reinterpret_cast<uint4 *>(p.out + px * p.ldo + 8 * g) = o;
     }
 }
 
@@ -963,15 +825,13 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 struct Ctx {
     cudaStream_t st;
     int B;
-    int legacy;      // AVB_K4_LEGACY_MMA=1: mma.sync (HMMA) GEMM core instead of tcgen05 (bring-up / A-B timing only)
 };
 
 template <int BN, bool A_BF16, int MODE>
 static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
     dim3 grid((p.rows + BM - 1) / BM, p.Np / BN, cx.B);
     AVB_TIMED(name, cx.st);
-    if (cx.legacy) gemm_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
-    else tc::gemm_tc_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
+    tc::gemm_tc_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, 0, cx.st>>>(p);
 }
 template <bool A_BF16, int MODE>
 static void launch_gemm(Ctx &cx, const GemmP &p, const char *name) {
@@ -995,11 +855,13 @@ static void conv3x3(Ctx &cx, const float *in, const bf16 *w, float *out, const f
 }
 
 static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const float *w, int H, int W, int Cp, int gelu_out, const char *name) {
-    DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out};
-    const long long total = (long long)cx.B * H * W * (Cp / 8);
-    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    // rows per thread: long enough to amortise the 2 halo rows, short enough to fill the machine
+    const long long items = (long long)cx.B * H * W * (Cp / 8);
+    const int seg = (int)std::max<long long>(4, std::min<long long>(32, items / ((long long)sm_count() * 1024)));
+    DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out, seg};
+    const long long total = (long long)cx.B * ((H + seg - 1) / seg) * W * (Cp / 8);
     AVB_TIMED(name, cx.st);
-    dwconv_kernel<<<blocks, 256, 0, cx.st>>>(p);
+    dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, cx.st>>>(p);
 }
 
 // MSAB with num_blocks = 1 (MST_Plus_Plus.py:160-186), in place on x (fp32 [B*rows, Cp]).
@@ -1166,8 +1028,7 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
     AVB_REQUIRE(Hp - H < H && Wp - W < W, "frame too small for reflect padding");
     Workspace ws{};
     carve(&ws, static_cast<uint8_t *>(workspace_dev), n, Hp, Wp);
-    const char *leg = getenv("AVB_K4_LEGACY_MMA");
-    Ctx cx{static_cast<cudaStream_t>(stream), n, (leg && leg[0] == '1') ? 1 : 0};
+    Ctx cx{static_cast<cudaStream_t>(stream), n};
     {
         ConvInP p{in, in_is_u8, ws.x0, M->conv_in, n, H, W, Hp, Wp, top, left};
         const long long npx = (long long)n * Hp * Wp;
