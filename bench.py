@@ -223,6 +223,45 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- K4 leg
+MSTPP_FLOP_PER_PATCH = 169.2e9      # 482x512 patch, 2 x MAC, unpadded channel counts
+
+
+def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
+    """MST++ (K4) throughput on `--mstpp-batch` 482x512 patches per GPU, seeded weights; reported as an
+    extra object beside the headline metric (the 4K video workload has no MST++ species)."""
+    import torch
+    if args.mstpp_batch <= 0:
+        return None
+    from animal_vision_b200.mstpp import MSTPlusPlus
+    from oracle import mstpp as O                       # only for the seeded synthetic weights
+    net = MSTPlusPlus(O.make_weights(0), dev)
+    nb = args.mstpp_batch
+    x = torch.rand(nb, 482, 512, 3, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+    for _ in range(3):
+        net.forward_nhwc(x)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        net.forward_nhwc(x)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / iters)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak = float(json.load(fh)["bf16_tflops_sustained"]); src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    tf = MSTPP_FLOP_PER_PATCH * nb * world / (ms * 1e-3) / 1e12
+    return {"workload": f"MST++ forward, {nb} x 3x482x512 patches per GPU (BASELINE configs[3]), seeded weights, bf16 operands / fp32 accumulate",
+            "patches_per_s": nb * world / (ms * 1e-3), "ms_per_forward": ms, "batch_per_gpu": nb,
+            "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,
+                         "peak_source": src, "algorithmic_flop_per_patch": MSTPP_FLOP_PER_PATCH,
+                         "note": "whole forward (176 launches), not one kernel; the network is launch/HBM bound at C=31 (SURVEY.md section 7)"}}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -337,6 +376,9 @@ def run_b200(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     barrier()
 
+    # ---- K4 leg (BASELINE configs[3]): MST++ forward on 482x512 patches, tensor-pipe roofline
+    mstpp = run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier)
+
     # sanity: the e2e outputs equal the device-resident outputs (same kernels, same inputs)
     ok = bool(torch.equal(host_out["Dog"][0][:2], dev_out["Dog"][:2].cpu()))
 
@@ -364,6 +406,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    line["mstpp"] = mstpp
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         rows = args.cpu_rows
@@ -392,6 +435,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline chunk in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the 3840-wide CPU-baseline sample frames")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mstpp-batch", type=int, default=4, help="482x512 patches per GPU in the MST++ leg (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
