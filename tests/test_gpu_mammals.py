@@ -82,3 +82,26 @@ def test_streak_1080p_batch_and_strides():
         wide[:, :, 39:1959] = batch                      # unaligned rows: scalar store path
         _, out2 = cls().visualize_batch(wide[:, :, 39:1959])
         assert torch.equal(out2, out)
+
+
+def test_host_batch_pipeline_matches_device_path():
+    """e2e route of bench.py: pinned host frames -> H2D || kernels || D2H -> pinned host frames."""
+    import torch
+    from animal_vision_b200.animals import Cat, Dog, HoneyBee
+    from animal_vision_b200.pipeline import HostBatchPipeline
+    fs = np.stack([frames.noise(144, 256, s) for s in range(7)])
+    host = torch.from_numpy(fs).pin_memory()
+    pipe = HostBatchPipeline(chunk_frames=3)
+    jobs, outs = [], {}
+    for sp in (Dog(), Cat(), HoneyBee()):
+        o = pipe.pinned_like(host, pipe.n_outputs(sp))
+        outs[type(sp).__name__] = (sp, o)
+        jobs.append((sp, host, o))
+    h2d, d2h = pipe.run(jobs)
+    assert h2d == 3 * fs.nbytes and d2h == 4 * fs.nbytes
+    dev = host.cuda()
+    for name, (sp, o) in outs.items():
+        ref = sp.visualize_batch(dev)
+        ref = ref if name == "Cat" else (ref[1],)
+        for a, b in zip(o, ref):
+            assert torch.equal(a, b.cpu()), name

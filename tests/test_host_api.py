@@ -1,0 +1,61 @@
+"""Host-side plugin API (CPU): registry shape, constructor contracts, the batched frame feed."""
+import numpy as np
+import pytest
+
+
+def test_registry_matches_reference_shape():
+    from animal_vision_b200 import registry
+    from animal_vision_b200.animals import Animal
+    ch = registry.animal_choices()
+    assert [c["name"] for c in ch][:3] == ["Cat", "Dog", "Sheep"] and len(ch) == 21
+    assert all(set(c) == {"name", "value"} and isinstance(c["value"], Animal) for c in ch)
+    assert all(callable(getattr(c["value"], "visualize")) and callable(getattr(c["value"], "visualize_batch")) for c in ch)
+
+
+def test_honeybee_constructor_contract():
+    from animal_vision_b200.animals import HoneyBee
+    b = HoneyBee()                                        # honeybee.py:47-66 defaults
+    assert b.mapping_mode == "opponent" and b.adaptation == "white_patch" and b.blur_sigma_px == 0.2
+    assert b.lambdas.shape == (31,) and b.lambdas[0] == 400.0 and b.lambdas[-1] == 700.0
+    for c in (b.UV_curve, b.Blue_curve, b.Green_curve):
+        assert abs(float(c.sum()) - 1.0) < 1e-5
+    with pytest.raises(ValueError):
+        HoneyBee(mapping_mode="nope")
+    with pytest.raises(ValueError):
+        HoneyBee(adaptation="nope")
+    with pytest.raises(AssertionError):
+        HoneyBee(mapping_mode="custom_matrix")           # honeybee.py:153-156 asserts a 3x3 matrix
+
+
+def test_bad_frames_assert_before_any_gpu_work():
+    from animal_vision_b200.animals import Cat, Dog, HoneyBee
+    for sp in (Dog(), Cat(), HoneyBee()):
+        with pytest.raises(AssertionError):
+            sp.visualize(np.zeros((4, 4), np.uint8))      # dog.py:33 / cat.py:24 / honeybee.py:102-103
+        with pytest.raises(AssertionError):
+            sp.visualize(np.zeros((4, 4, 4), np.uint8))
+
+
+class _FakeVideo:
+    """get_image() contract of renderers/video.py:82-96: RGB uint8 HxWx3 or None at end of stream."""
+
+    def __init__(self, n, h=6, w=8):
+        self.frames = [np.full((h, w, 3), i, np.uint8) for i in range(n)]
+        self.i = 0
+
+    def get_image(self):
+        if self.i >= len(self.frames):
+            return None
+        self.i += 1
+        return self.frames[self.i - 1]
+
+
+def test_batch_feed_gathers_frames_in_order():
+    from animal_vision_b200.renderers.video import BatchFeed
+    feed = BatchFeed(_FakeVideo(7), batch=3, pinned=False)
+    sizes, seen = [], []
+    while (b := feed.get_batch()) is not None:
+        sizes.append(b.shape[0])
+        seen += [int(f[0, 0, 0]) for f in b]
+        assert b.shape[1:] == (6, 8, 3) and b.dtype == np.uint8
+    assert sizes == [3, 3, 1] and seen == list(range(7))
