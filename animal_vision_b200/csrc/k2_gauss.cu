@@ -1,15 +1,19 @@
 // K2: fused  producer -> separable Gaussian (REFLECT_101) -> clip -> sRGB encode -> uint8.
 //
-// One CTA owns a vertical strip of TW pixels and streams down a segment of rows in blocks of RB=8
-// rows.  Per block:  produce (decode + 3x3 into a planar fp32 staging tile with an R-pixel x halo)
-// -> horizontal pass -> vertical pass over a window of horizontally-blurred rows that each thread
-// keeps in REGISTERS for the whole segment (no ring buffer, 8 new values per block) -> encode -> packed uint8 staging -> 128-bit stores.  The fp32 intermediate never leaves
-// shared memory: HBM sees the uint8 frame once in and once out (6 B/px).
-//
-// Both passes are register blocked: a thread produces 8 consecutive outputs from an (8+2R)-wide
-// window held in registers, so shared-memory traffic is (8+2R)/8 loads per 2R+1 FMAs and the
-// kernel is bound by the FP32 FMA pipe, not by LDS.  Taps live in the kernel-parameter constant
-// bank and feed FFMA directly.
+// One CTA (384 threads) owns a vertical strip of 128 pixels and streams down a segment of rows in
+// blocks of 8 input rows.  Per block:
+//   produce   decode + 3x3 into a planar fp32 tile with an R-pixel x halo.  Interior strips of the
+//             LUT producer take a vector path: 16-byte loads of the packed rows into a raw byte
+//             tile, then 4 pixels (12 bytes) per thread; border strips and the cat warp producer
+//             go pixel by pixel;
+//   H pass    8 outputs per thread from an (8+2R)-wide register window (LDS.128), taps from the
+//             kernel-parameter constant bank;
+//   V pass    accumulator ("scatter") form: every thread owns one (column, channel) and keeps the
+//             2R partial sums of the output rows still in flight in registers -- one LDS and 2R+1
+//             FMAs per input row, no window shifting;
+//   encode -> packed uint8 staging -> 128-bit stores.
+// The fp32 intermediate never leaves shared memory: HBM sees the uint8 frame once in and once out
+// (6 B/px).
 //
 // The producer is a policy: DogProducer (LUT decode + 3x3; animals/dog.py:35-48) or CatProducer
 // (binocular wide-FOV gather + blend + pow decode + 3x3; animals/cat_widevision_utils.py:46-99,
@@ -18,25 +22,29 @@
 
 namespace avb {
 
-constexpr int G_TW = 64;        // strip width in pixels
+constexpr int G_TW = 128;       // strip width in pixels
 constexpr int G_RB = 8;         // rows per block
-constexpr int G_THREADS = 192;  // 6 warps: (channel, half-strip)
+constexpr int G_THREADS = 384;  // 12 warps: H pass (channel, row, 8-px group); V pass (channel, column)
 constexpr int G_MAX_TAPS = 33;
 constexpr int G_ENC_SMEM = AVB_ENC_TABLE_MAX;  // uint32 words reserved for the encode table
+constexpr int G_RAW_PITCH = 528;               // bytes per row of the raw tile (>= 16 * 33)
+
+constexpr int g_round_pitch(int v) { return (v % 8 == 4) ? v : (v + ((12 - v % 8) % 8)); }
 
 template <int R>
 struct GaussCfg {
-    static constexpr int LAG = (2 * R + G_RB - 1) / G_RB;             // input blocks an output block waits for
-    static constexpr int VW = (LAG + 1) * G_RB;                       // vertical register window (rows)
-    static constexpr int WIN = G_RB + 2 * R;                          // rows/cols actually used by 8 outputs
+    static constexpr int WIN = G_RB + 2 * R;                          // columns used by 8 H outputs
     static constexpr int NW4 = (WIN + 3) / 4;                         // float4 loads per horizontal window
-    static constexpr int SP0 = (G_TW - 8) + 4 * NW4;
-    static constexpr int S_PITCH = (SP0 % 8 == 4) ? SP0 : SP0 + 4;    // odd multiple of 16 B: conflict-free LDS.128
     static constexpr int IN_W = G_TW + 2 * R;                         // produced columns per row
-    static constexpr int X_PITCH = G_TW + 4;                          // same trick for the STS.128 of the H pass
+    static constexpr int GROUPS = (IN_W + 3) / 4;                     // 4-pixel decode groups per row
+    static constexpr int SP_WIN = (G_TW - 8) + 4 * NW4;               // furthest column the H window reads
+    static constexpr int SP_MIN = SP_WIN > 4 * GROUPS ? SP_WIN : 4 * GROUPS;
+    static constexpr int S_PITCH = g_round_pitch(SP_MIN);             // % 8 == 4: odd multiple of 16 B, conflict-free LDS.128
+    static constexpr int X_PITCH = G_TW + 4;
     static constexpr int S_FLOATS = 3 * G_RB * S_PITCH;
     static constexpr int X_FLOATS = 3 * G_RB * X_PITCH;
     static constexpr int STAGE_BYTES = G_RB * G_TW * 3;
+    static constexpr int RAW_BYTES = G_RB * G_RAW_PITCH;
 };
 
 struct GaussCommon {
@@ -57,6 +65,7 @@ struct DogProducer {
         const float *lut;  // 256-entry decode LUT (device)
     };
     static constexpr int SMEM_FLOATS = 256;
+    static constexpr bool VEC = true;      // has a 4-pixel vector path (three packed 32-bit words -> 4 px)
     const float *lut_s;
     const uint8_t *src;
     int64_t rs;
@@ -74,6 +83,20 @@ struct DogProducer {
         seen = 0;
     }
     __device__ __forceinline__ bool all_black(int, int) const { return false; }
+    __device__ __forceinline__ void px(uint32_t b0, uint32_t b1, uint32_t b2, float &o0, float &o1, float &o2) const {
+        const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
+        o0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
+        o1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
+        o2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+    }
+    // 12 packed bytes (4 pixels) -> planar float4 per channel
+    __device__ __forceinline__ void decode4(uint32_t w0, uint32_t w1, uint32_t w2, float4 &c0, float4 &c1, float4 &c2) {
+        seen |= w0 | w1 | w2;
+        px(__byte_perm(w0, 0, 0x4440), __byte_perm(w0, 0, 0x4441), __byte_perm(w0, 0, 0x4442), c0.x, c1.x, c2.x);
+        px(__byte_perm(w0, 0, 0x4443), __byte_perm(w1, 0, 0x4440), __byte_perm(w1, 0, 0x4441), c0.y, c1.y, c2.y);
+        px(__byte_perm(w1, 0, 0x4442), __byte_perm(w1, 0, 0x4443), __byte_perm(w2, 0, 0x4440), c0.z, c1.z, c2.z);
+        px(__byte_perm(w2, 0, 0x4441), __byte_perm(w2, 0, 0x4442), __byte_perm(w2, 0, 0x4443), c0.w, c1.w, c2.w);
+    }
     __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
         const uint8_t *q = src + (int64_t)y * rs + 3 * x;
         const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
@@ -96,6 +119,7 @@ struct CatProducer {
         int norm_mode;                   // AVB_NORM_DIV255: always /255; AVB_NORM_AUTO: /255 iff flag set
     };
     static constexpr int SMEM_FLOATS = 256;
+    static constexpr bool VEC = false;
     const float *norm_s;
     const uint8_t *src;
     int64_t rs;
@@ -120,6 +144,7 @@ struct CatProducer {
         xl = pp.xl; xr = pp.xr; wl = pp.wl; wr = pp.wr; ws = pp.ws; rws = pp.rws;
         seen = 0;
     }
+    __device__ __forceinline__ void decode4(uint32_t, uint32_t, uint32_t, float4 &, float4 &, float4 &) {}
     // every column of [xa, xb) has zero weight in both eye views: the strip is black
     __device__ __forceinline__ bool all_black(int xa, int xb) const {
         bool any = false;
@@ -186,8 +211,11 @@ struct CatProducer {
 };
 
 // ------------------------------------------------------------------------------------ kernel
+template <int R>
+struct GaussOcc { static constexpr int MIN_BLOCKS = 2; };
+
 template <int R, class Prod>
-__global__ void __launch_bounds__(G_THREADS, 3)
+__global__ void __launch_bounds__(G_THREADS, GaussOcc<R>::MIN_BLOCKS)
 gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant__ typename Prod::Params pp) {
     using C = GaussCfg<R>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -196,6 +224,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     float *prod_smem = X + C::X_FLOATS;
     uint8_t *stage = reinterpret_cast<uint8_t *>(prod_smem + Prod::SMEM_FLOATS);   // [RB][TW*3] encoded bytes
     uint32_t *enc_s = reinterpret_cast<uint32_t *>(stage + C::STAGE_BYTES);
+    uint8_t *rawt = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);               // [RB][RAW_PITCH] packed input rows
 
     const int frame = blockIdx.z;
     if (p.fixup && p.flags[frame] != 0) return;
@@ -207,7 +236,8 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     const int y_end = min(H, y_start + p.seg_h);
 
     Prod prod;
-    prod.init(pp, prod_smem, p.io.in + (int64_t)frame * p.io.in_fs, p.io.in_rs, H, W, frame);
+    const uint8_t *src_frame = p.io.in + (int64_t)frame * p.io.in_fs;
+    prod.init(pp, prod_smem, src_frame, p.io.in_rs, H, W, frame);
     copy_to_smem(enc_s, p.enc, min(G_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
     __syncthreads();
     const EncTable enc = enc_view(enc_s);
@@ -230,29 +260,68 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         return;
     }
 
-    const int n_out_blocks = (y_end - y_start + G_RB - 1) / G_RB;
-    const int n_in_blocks = n_out_blocks + C::LAG;
+    // vector produce: the strip plus its halo (and the over-read of the last 4-pixel group) lies
+    // inside the row, rows are 16-byte aligned
+    const int a_byte = 3 * (x0 - R);                 // first byte of the produced span
+    const int a0 = a_byte & ~15;
+    const int n_chunks = (a_byte - a0 + 12 * C::GROUPS + 15) >> 4;
+    const bool vec_in = Prod::VEC && x0 - R >= 0 && a0 + 16 * n_chunks <= 3 * W && G_RB * n_chunks <= G_THREADS && ((p.io.in_rs & 15) == 0) &&
+                        ((p.io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
 
-    // task coordinates: warp -> (channel, half strip); H pass: lane -> (row, 8-px group);
-    // V pass: lane -> column.  The V window lives in registers for the whole segment.
-    const int ch = warp >> 1;
-    const int h_r = lane & 7, h_xg = ((warp & 1) << 2) + (lane >> 3);
-    const int v_x = ((warp & 1) << 5) + lane;
-    float vw[C::VW];
+    const int n_in_rows = (y_end - y_start) + 2 * R;
+    const int n_in_blocks = (n_in_rows + G_RB - 1) / G_RB;
+
+    // task coordinates.  H pass: thread -> (channel, row, 8-px group); V pass: thread -> (channel, column)
+    const int ch = tid >> 7;                         // 128 threads per channel
+    const int h_r = tid & 7, h_xg = (tid & 127) >> 3;
+    const int v_x = tid & 127;
+    float A[2 * R];                                  // partial sums of the 2R output rows in flight
 #pragma unroll
-    for (int i = 0; i < C::VW; ++i) vw[i] = 0.f;
+    for (int i = 0; i < 2 * R; ++i) A[i] = 0.f;
+
+    // vector path: one 16-byte chunk of the raw tile per thread (8 rows x <= 33 chunks <= 384 threads)
+    const int pf_r = tid / max(n_chunks, 1), pf_q = tid - pf_r * max(n_chunks, 1);
+    uint4 pf = make_uint4(0u, 0u, 0u, 0u);
+    if (vec_in && tid < G_RB * n_chunks)
+        pf = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(y_start - R + pf_r, H) * p.io.in_rs + a0) + pf_q);
 
     for (int ib = 0; ib < n_in_blocks; ++ib) {
-        // ---- produce RB rows x IN_W columns of linear-light values (input rows y_start-R+8*ib ..)
-        const int yb = y_start - R + ib * G_RB;
-        for (int idx = tid; idx < G_RB * C::IN_W; idx += G_THREADS) {
-            const int r = idx / C::IN_W, i = idx - r * C::IN_W;
-            const int y = reflect101(yb + r, H), x = reflect101(x0 - R + i, W);
-            float o0, o1, o2;
-            prod(y, x, o0, o1, o2);
-            S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
-            S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
-            S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+        const int yb = y_start - R + ib * G_RB;      // first input row of this block
+        // ---- produce RB rows x IN_W columns of linear-light values
+        if (vec_in) {
+            // the packed rows of this block were fetched one block ahead (registers); publish them,
+            // then put the next block's loads in flight before any arithmetic
+            if (tid < G_RB * n_chunks) reinterpret_cast<uint4 *>(rawt + pf_r * G_RAW_PITCH)[pf_q] = pf;
+            __syncthreads();
+            if (ib + 1 < n_in_blocks && tid < G_RB * n_chunks)
+                pf = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(yb + G_RB + pf_r, H) * p.io.in_rs + a0) + pf_q);
+            const int sh = (a_byte - a0) & 3, w_off = (a_byte - a0) >> 2;
+            for (int idx = tid; idx < G_RB * C::GROUPS; idx += G_THREADS) {
+                const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * G_RAW_PITCH) + w_off + 3 * g;
+                uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                if (sh) {
+                    const uint32_t w3 = q[3];
+                    w0 = __funnelshift_r(w0, w1, 8 * sh);
+                    w1 = __funnelshift_r(w1, w2, 8 * sh);
+                    w2 = __funnelshift_r(w2, w3, 8 * sh);
+                }
+                float4 c0, c1, c2;
+                prod.decode4(w0, w1, w2, c0, c1, c2);
+                *reinterpret_cast<float4 *>(&S[(0 * G_RB + r) * C::S_PITCH + 4 * g]) = c0;
+                *reinterpret_cast<float4 *>(&S[(1 * G_RB + r) * C::S_PITCH + 4 * g]) = c1;
+                *reinterpret_cast<float4 *>(&S[(2 * G_RB + r) * C::S_PITCH + 4 * g]) = c2;
+            }
+        } else {
+            for (int idx = tid; idx < G_RB * C::IN_W; idx += G_THREADS) {
+                const int r = idx / C::IN_W, i = idx - r * C::IN_W;
+                const int y = reflect101(yb + r, H), x = reflect101(x0 - R + i, W);
+                float o0, o1, o2;
+                prod(y, x, o0, o1, o2);
+                S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
+                S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
+                S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+            }
         }
         __syncthreads();
 
@@ -280,64 +349,59 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         }
         __syncthreads();
 
-        // ---- vertical pass: slide the register window down by 8 rows, emit 8 outputs once it is full
+        // ---- vertical pass, one input row at a time: finish the oldest output row, advance the rest.
+        // Input row i (0-based in the segment) completes output row y_start + i - 2R.
         {
             const float *col = X + ch * G_RB * C::X_PITCH + v_x;
 #pragma unroll
-            for (int j = 0; j < G_RB; ++j) vw[C::VW - G_RB + j] = col[j * C::X_PITCH];
-        }
-        const int ob = ib - C::LAG;
-        if (ob >= 0) {
-            float acc[8];
+            for (int r = 0; r < G_RB; ++r) {
+                const float h = col[r * C::X_PITCH];
+                const float out = fmaf(p.taps[2 * R], h, A[0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k <= 2 * R; ++k) {
-                const float tk = p.taps[k];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(tk, vw[j + k], acc[j]);
+                for (int m = 0; m < 2 * R - 1; ++m) A[m] = fmaf(p.taps[2 * R - 1 - m], h, A[m + 1]);
+                A[2 * R - 1] = p.taps[0] * h;
+                if (ib * G_RB + r >= 2 * R) stage[r * (G_TW * 3) + v_x * 3 + ch] = (uint8_t)encode_u8(enc, out);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) stage[j * (G_TW * 3) + v_x * 3 + ch] = (uint8_t)encode_u8(enc, acc[j]);
         }
-#pragma unroll
-        for (int i = 0; i < C::VW - G_RB; ++i) vw[i] = vw[i + G_RB];
         __syncthreads();
 
-        // ---- store the 8 x (TW*3)-byte block
-        if (ob >= 0) {
-            const int oy = y_start + ob * G_RB;
+        // ---- store the finished rows of this block: input row i = 8*ib + r -> output row y_start + i - 2R
+        {
+            const int oy0 = y_start + ib * G_RB - 2 * R;
             if (vec_ok) {
-                constexpr int V_PER_ROW = G_TW * 3 / 16;       // 12 x 16 B per row
+                constexpr int V_PER_ROW = G_TW * 3 / 16;       // 24 x 16 B per row
                 for (int idx = tid; idx < G_RB * V_PER_ROW; idx += G_THREADS) {
                     const int r = idx / V_PER_ROW, q = idx - r * V_PER_ROW;
-                    if (oy + r < y_end) {
+                    const int oy = oy0 + r;
+                    if (oy >= y_start && oy < y_end) {
                         const uint4 val = reinterpret_cast<const uint4 *>(stage + r * (G_TW * 3))[q];
-                        *reinterpret_cast<uint4 *>(dst_frame + (int64_t)(oy + r) * p.io.out_rs + (int64_t)x0 * 3 + q * 16) = val;
+                        *reinterpret_cast<uint4 *>(dst_frame + (int64_t)oy * p.io.out_rs + (int64_t)x0 * 3 + q * 16) = val;
                     }
                 }
             } else {
                 const int nbytes = min(G_TW, W - x0) * 3;
                 for (int idx = tid; idx < G_RB * G_TW * 3; idx += G_THREADS) {
                     const int r = idx / (G_TW * 3), b = idx - r * (G_TW * 3);
-                    if (oy + r < y_end && b < nbytes)
-                        dst_frame[(int64_t)(oy + r) * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[idx];
+                    const int oy = oy0 + r;
+                    if (oy >= y_start && oy < y_end && b < nbytes)
+                        dst_frame[(int64_t)oy * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[idx];
                 }
             }
         }
-        // hazards: the next produce only writes S (H pass done); X is rewritten after the next
+        // hazards: the next produce writes rawt / S (H pass done); X is rewritten after the next
         // produce barrier (V pass done); stage is rewritten two barriers from here.
     }
 
     if (p.flags != nullptr && !p.fixup) {
-        if (__any_sync(0xffffffffu, (prod.seen & 0xfeu) != 0) && lane == 0) p.flags[frame] = 1u;
+        // vector path ORs whole 32-bit words (4 packed bytes), the scalar path single bytes
+        if (__any_sync(0xffffffffu, (prod.seen & 0xfefefefeu) != 0) && lane == 0) p.flags[frame] = 1u;
     }
 }
 
 template <int R, class Prod>
 static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
     using C = GaussCfg<R>;
-    const size_t smem = (size_t)(C::S_FLOATS + C::X_FLOATS + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::STAGE_BYTES;
+    const size_t smem = (size_t)(C::S_FLOATS + C::X_FLOATS + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::STAGE_BYTES + C::RAW_BYTES;
     auto kern = gauss_stream_kernel<R, Prod>;
     AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
@@ -351,7 +415,7 @@ static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, 
 // 2*RP halo rows re-produced per segment stay a small fraction
 static int pick_seg_h(int n, int H, int W, int radius) {
     const int strips = (W + G_TW - 1) / G_TW;
-    const long target = 4L * 3 * sm_count();                 // ~4 waves at 3 CTAs/SM
+    const long target = 4L * 2 * sm_count();                 // ~4 waves at 2 CTAs/SM
     long segs = (target + (long)strips * n - 1) / ((long)strips * n);
     const int min_h = 16 * radius;                             // halo rows re-produced per segment <= 12.5 %
     long max_segs = (H + min_h - 1) / min_h;
