@@ -97,14 +97,13 @@ struct DogProducer {
         px(__byte_perm(w1, 0, 0x4442), __byte_perm(w1, 0, 0x4443), __byte_perm(w2, 0, 0x4440), c0.z, c1.z, c2.z);
         px(__byte_perm(w2, 0, 0x4441), __byte_perm(w2, 0, 0x4442), __byte_perm(w2, 0, 0x4443), c0.w, c1.w, c2.w);
     }
-    __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
-        const uint8_t *q = src + (int64_t)y * rs + 3 * x;
+    struct Column { int x3; };
+    __device__ __forceinline__ Column column(int x) const { return Column{3 * x}; }
+    __device__ __forceinline__ void at(const Column &c, int y, float &o0, float &o1, float &o2) {
+        const uint8_t *q = src + (int64_t)y * rs + c.x3;
         const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
         seen |= b0 | b1 | b2;
-        const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
-        o0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
-        o1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
-        o2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+        px(b0, b1, b2, o0, o1, o2);
     }
 };
 
@@ -154,55 +153,70 @@ struct CatProducer {
         }
         return !__syncthreads_or(any);
     }
-    // cv::remap INTER_LINEAR on a row: map coordinate quantised to 1/32 px, two taps, border 0
-    __device__ __forceinline__ void gather(const uint8_t *row, float xs, float &c0, float &c1, float &c2) {
+    // ---- per-column state (every map of cat_widevision_utils.py:61-96 depends on the column only):
+    // which eye view is live, its two source columns and bilinear weights, the blend denominator.
+    // cv::remap INTER_LINEAR: map coordinate quantised to 1/32 px, two taps, border constant 0.
+    struct Tap { int ix; float w0, f; bool ok0, ok1; };
+    struct Column { float wL, wR, s, r; Tap L, R; };
+    __device__ __forceinline__ Tap make_tap(float xs) const {
+        Tap t;
         const int sx = __float2int_rn(xs * 32.0f);
-        const int ix = sx >> 5;
-        const float f = (float)(sx & 31) * (1.0f / 32.0f);
-        const float w0 = 1.0f - f;
+        t.ix = sx >> 5;
+        t.f = (float)(sx & 31) * (1.0f / 32.0f);
+        t.w0 = 1.0f - t.f;
+        t.ok0 = (unsigned)t.ix < (unsigned)W;
+        t.ok1 = (unsigned)(t.ix + 1) < (unsigned)W;
+        return t;
+    }
+    __device__ __forceinline__ Column column(int x) const {
+        Column c;
+        c.wL = __ldg(wl + x); c.wR = __ldg(wr + x);
+        c.s = __ldg(ws + x); c.r = __ldg(rws + x);
+        c.L = make_tap(__ldg(xl + x));
+        c.R = make_tap(__ldg(xr + x));
+        return c;
+    }
+    __device__ __forceinline__ void gather(const uint8_t *row, const Tap &t, float &c0, float &c1, float &c2) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-        if ((unsigned)ix < (unsigned)W) {
-            const uint8_t *q = row + 3 * ix;
+        const uint8_t *q = row + 3 * t.ix;
+        if (t.ok0) {
             const uint32_t u0 = q[0], u1 = q[1], u2 = q[2];
             seen |= u0 | u1 | u2;
             a0 = norm_s[u0]; a1 = norm_s[u1]; a2 = norm_s[u2];
         }
-        if ((unsigned)(ix + 1) < (unsigned)W) {
-            const uint8_t *q = row + 3 * (ix + 1);
-            const uint32_t u0 = q[0], u1 = q[1], u2 = q[2];
+        if (t.ok1) {
+            const uint32_t u0 = q[3], u1 = q[4], u2 = q[5];
             seen |= u0 | u1 | u2;
             b0 = norm_s[u0]; b1 = norm_s[u1]; b2 = norm_s[u2];
         }
-        c0 = __fadd_rn(__fmul_rn(a0, w0), __fmul_rn(b0, f));
-        c1 = __fadd_rn(__fmul_rn(a1, w0), __fmul_rn(b1, f));
-        c2 = __fadd_rn(__fmul_rn(a2, w0), __fmul_rn(b2, f));
+        c0 = __fadd_rn(__fmul_rn(a0, t.w0), __fmul_rn(b0, t.f));
+        c1 = __fadd_rn(__fmul_rn(a1, t.w0), __fmul_rn(b1, t.f));
+        c2 = __fadd_rn(__fmul_rn(a2, t.w0), __fmul_rn(b2, t.f));
     }
     static __device__ __forceinline__ float decode(float v) {
         // animals/animal_utils.py:5-11 on float32; the power goes through the SFU (ex2(2.4 lg2 x),
         // ~5e-7 relative: far inside the 1-LSB budget of the uint8 result)
         return v <= 0.04045f ? v * (1.0f / 12.92f) : exp2f(2.4f * __log2f((v + 0.055f) * (1.0f / 1.055f)));
     }
-    __device__ __forceinline__ void operator()(int y, int x, float &o0, float &o1, float &o2) {
-        const float wL = __ldg(wl + x), wR = __ldg(wr + x);
-        if (wL == 0.0f && wR == 0.0f) {     // outside both eye views: (0*wL + 0*wR)/ws = 0 -> decode(0) = 0
+    __device__ __forceinline__ void at(const Column &c, int y, float &o0, float &o1, float &o2) {
+        if (c.wL == 0.0f && c.wR == 0.0f) {     // outside both eye views: (0*wL + 0*wR)/ws = 0 -> decode(0) = 0
             o0 = o1 = o2 = 0.f;
             return;
         }
         const uint8_t *row = src + (int64_t)y * rs;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         // a zero weight multiplies a finite sample: skipping the gather leaves the sum unchanged
-        if (wL != 0.0f) gather(row, __ldg(xl + x), l0, l1, l2);
-        if (wR != 0.0f) gather(row, __ldg(xr + x), r0, r1, r2);
+        if (c.wL != 0.0f) gather(row, c.L, l0, l1, l2);
+        if (c.wR != 0.0f) gather(row, c.R, r0, r1, r2);
         // (left*wL + right*wR) / (wL + wR + 1e-8), the quotient correctly rounded from the
         // per-column reciprocal (one Newton step on the quotient)
-        const float s = __ldg(ws + x), r = __ldg(rws + x);
-        const float n0 = __fadd_rn(__fmul_rn(l0, wL), __fmul_rn(r0, wR));
-        const float n1 = __fadd_rn(__fmul_rn(l1, wL), __fmul_rn(r1, wR));
-        const float n2 = __fadd_rn(__fmul_rn(l2, wL), __fmul_rn(r2, wR));
-        float q0 = __fmul_rn(n0, r), q1 = __fmul_rn(n1, r), q2 = __fmul_rn(n2, r);
-        q0 = fmaf(fmaf(-q0, s, n0), r, q0);
-        q1 = fmaf(fmaf(-q1, s, n1), r, q1);
-        q2 = fmaf(fmaf(-q2, s, n2), r, q2);
+        const float n0 = __fadd_rn(__fmul_rn(l0, c.wL), __fmul_rn(r0, c.wR));
+        const float n1 = __fadd_rn(__fmul_rn(l1, c.wL), __fmul_rn(r1, c.wR));
+        const float n2 = __fadd_rn(__fmul_rn(l2, c.wL), __fmul_rn(r2, c.wR));
+        float q0 = __fmul_rn(n0, c.r), q1 = __fmul_rn(n1, c.r), q2 = __fmul_rn(n2, c.r);
+        q0 = fmaf(fmaf(-q0, c.s, n0), c.r, q0);
+        q1 = fmaf(fmaf(-q1, c.s, n1), c.r, q1);
+        q2 = fmaf(fmaf(-q2, c.s, n2), c.r, q2);
         const float s0 = decode(__saturatef(q0)), s1 = decode(__saturatef(q1)), s2 = decode(__saturatef(q2));
         o0 = m[0] * s0 + m[1] * s1 + m[2] * s2;
         o1 = m[3] * s0 + m[4] * s1 + m[5] * s2;
@@ -313,14 +327,20 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
                 *reinterpret_cast<float4 *>(&S[(2 * G_RB + r) * C::S_PITCH + 4 * g]) = c2;
             }
         } else {
-            for (int idx = tid; idx < G_RB * C::IN_W; idx += G_THREADS) {
-                const int r = idx / C::IN_W, i = idx - r * C::IN_W;
-                const int y = reflect101(yb + r, H), x = reflect101(x0 - R + i, W);
-                float o0, o1, o2;
-                prod(y, x, o0, o1, o2);
-                S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
-                S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
-                S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+            // pixel-by-pixel producer (image borders, unaligned frames, the cat warp): a task is one
+            // column x 4 rows, so per-column state (table loads, tap geometry) is set up once per 4 px
+            for (int idx = tid; idx < 2 * C::IN_W; idx += G_THREADS) {
+                const int half = idx / C::IN_W, i = idx - half * C::IN_W;
+                const typename Prod::Column col = prod.column(reflect101(x0 - R + i, W));
+#pragma unroll
+                for (int rr = 0; rr < G_RB / 2; ++rr) {
+                    const int r = half * (G_RB / 2) + rr;
+                    float o0, o1, o2;
+                    prod.at(col, reflect101(yb + r, H), o0, o1, o2);
+                    S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
+                    S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
+                    S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+                }
             }
         }
         __syncthreads();
@@ -513,25 +533,42 @@ __global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *
 }
 
 // Centre zoom (cat_widevision_utils.py:11-29): crop + cv2.resize(INTER_LINEAR) on uint8, restated
-// in OpenCV's 11-bit fixed point so the result is bit-exact.  tab = xi0,xi1,xw0,xw1 [W] then
-// yi0,yi1,yw0,yw1 [H] (source indices already include the crop origin).
-__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab) {
-    const int W = io.W, H = io.H;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+// in OpenCV's 11-bit fixed point so the result is bit-exact.  tab = W x int4 {xi0, xi1, xw0, xw1}
+// then H x int4 {yi0, yi1, yw0, yw1} (source indices already include the crop origin).
+// One thread = 4 consecutive output pixels of a row (12 bytes = three 32-bit stores).
+__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab, int aligned_out) {
+    const int W = io.W;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
-    if (x >= W) return;
-    const int32_t *tx = tab, *ty = tab + 4 * W;
-    const int xi0 = __ldg(tx + x), xi1 = __ldg(tx + W + x), xw0 = __ldg(tx + 2 * W + x), xw1 = __ldg(tx + 3 * W + x);
-    const int yi0 = __ldg(ty + y), yi1 = __ldg(ty + H + y), yw0 = __ldg(ty + 2 * H + y), yw1 = __ldg(ty + 3 * H + y);
+    if (x4 >= W) return;
+    const int4 ty = __ldg(reinterpret_cast<const int4 *>(tab) + W + y);
     const uint8_t *src = io.in + (int64_t)blockIdx.z * io.in_fs;
-    const uint8_t *r0 = src + (int64_t)yi0 * io.in_rs, *r1 = src + (int64_t)yi1 * io.in_rs;
-    uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y * io.out_rs + 3 * x;
+    const uint8_t *r0 = src + (int64_t)ty.x * io.in_rs, *r1 = src + (int64_t)ty.y * io.in_rs;
+    uint32_t by[12];
+    const int npx = min(4, W - x4);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int s0 = r0[3 * xi0 + c] * xw0 + r0[3 * xi1 + c] * xw1;
-        const int s1 = r1[3 * xi0 + c] * xw0 + r1[3 * xi1 + c] * xw1;
-        const int v = ((((yw0 * (s0 >> 4)) >> 16) + ((yw1 * (s1 >> 4)) >> 16) + 2) >> 2);
-        o[c] = (uint8_t)min(255, max(0, v));
+    for (int j = 0; j < 4; ++j) {
+        if (j < npx) {
+            const int4 tx = __ldg(reinterpret_cast<const int4 *>(tab) + x4 + j);
+            const uint8_t *a0 = r0 + 3 * tx.x, *a1 = r0 + 3 * tx.y, *b0 = r1 + 3 * tx.x, *b1 = r1 + 3 * tx.y;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int s0 = a0[c] * tx.z + a1[c] * tx.w;
+                const int s1 = b0[c] * tx.z + b1[c] * tx.w;
+                const int v = ((((ty.z * (s0 >> 4)) >> 16) + ((ty.w * (s1 >> 4)) >> 16) + 2) >> 2);
+                by[3 * j + c] = (uint32_t)min(255, max(0, v));
+            }
+        } else {
+            by[3 * j] = by[3 * j + 1] = by[3 * j + 2] = 0u;
+        }
+    }
+    uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y * io.out_rs + 3 * x4;
+    if (aligned_out && npx == 4) {
+        uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
+    } else {
+        for (int q = 0; q < 3 * npx; ++q) o[q] = (uint8_t)by[q];
     }
 }
 
@@ -562,9 +599,12 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
     if (out_human) {
         AVB_REQUIRE(human_row_stride >= 3LL * W, "row stride smaller than 3*W");
         FrameIO zio{in, out_human, in_frame_stride, in_row_stride, human_frame_stride, human_row_stride, n, H, W};
-        dim3 grid((W + 255) / 256, H, n);
+        AVB_REQUIRE(H <= 65535 && n <= 65535, "frame height / batch too large for one launch");
+        AVB_REQUIRE((reinterpret_cast<uintptr_t>(zoom_dev) & 15) == 0, "zoom_dev must be 16-byte aligned");
+        dim3 grid((W + 1023) / 1024, H, n);
+        const int aligned_out = ((reinterpret_cast<uintptr_t>(out_human) | (uintptr_t)human_frame_stride | (uintptr_t)human_row_stride) & 3) == 0;
         AVB_TIMED("cat_center_zoom", st);
-        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev);
+        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev, aligned_out);
         AVB_CUDA_OK(cudaGetLastError());
     }
     for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];

@@ -177,12 +177,14 @@ def center_zoom_box(W: int, H: int, scale: float):
 
 
 def center_zoom_tables(W: int, H: int, scale: float) -> np.ndarray:
-    """int32 [4, W] + [4, H] tables (indices already offset by the crop origin), concatenated as
-    one int32 array of length 4*W + 4*H: xi0, xi1, xw0, xw1, yi0, yi1, yw0, yw1."""
+    """int32 table for avb_cat_u8: W rows {xi0, xi1, xw0, xw1} then H rows {yi0, yi1, yw0, yw1}
+    (source indices already offset by the crop origin, 11-bit weights), flattened to 4*W + 4*H."""
     x0, y0, cw, ch = center_zoom_box(W, H, scale)
     xi0, xi1, xw0, xw1 = resize_axis_table(cw, W, vertical=False)
     yi0, yi1, yw0, yw1 = resize_axis_table(ch, H, vertical=True)
-    return np.concatenate([xi0 + x0, xi1 + x0, xw0, xw1, yi0 + y0, yi1 + y0, yw0, yw1]).astype(np.int32)
+    tx = np.stack([xi0 + x0, xi1 + x0, xw0, xw1], axis=1)
+    ty = np.stack([yi0 + y0, yi1 + y0, yw0, yw1], axis=1)
+    return np.concatenate([tx.ravel(), ty.ravel()]).astype(np.int32)
 
 
 # ----------------------------------------------------------------------------- streak blur

@@ -121,8 +121,8 @@ AVB_API int avb_streak_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, in
  *              Gaussian sigma=1.0 (9 taps) -> encode.
  *   warp_dev   6*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights),
  *              ws = wL + wR + 1e-8 (the blend denominator, float32) and 1/ws (correctly rounded)
- *   zoom_dev   4*W + 4*H int32: xi0, xi1, xw0, xw1, yi0, yi1, yw0, yw1 (source indices incl. crop
- *              origin, 11-bit weights)
+ *   zoom_dev   4*W + 4*H int32, 16-byte aligned: W records {xi0, xi1, xw0, xw1} then H records
+ *              {yi0, yi1, yw0, yw1} (source indices incl. crop origin, 11-bit weights)
  *   enc_dev    encode table built from the float64 tail's thresholds (cat.py runs float64 from
  *              LMS_to_RGB on; the device tail is float32)
  *   flags_dev  n uint32 scratch (AVB_NORM_AUTO): filled by a pre-pass over each frame */
