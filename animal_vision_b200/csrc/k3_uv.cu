@@ -9,8 +9,10 @@
 //   stats    raw catches -> per-frame max and sum of each receptor          (white patch / gray world)
 //   prep     (1 thread per frame) fold the adaptation into the receptor matrix, size the bins
 //   hist     adapted + blurred catches -> mapper quantities -> 2048 linear bins per quantity
+//            (+ the quantities themselves, 4 B per pixel, for the compact pass)
 //   scan     locate the bin(s) that hold the two order statistics of every percentile request
-//   collect  recompute, append the values that fall into those bins to a candidate list
+//   compact  read back the quantity planes the hist pass wrote, append the values that fall into
+//            those bins to a candidate list
 //   select   exact radix select among the candidates -> numpy.percentile(method="linear")
 //   map      recompute, apply the mapper, clip -> OETF -> uint8
 // The percentile is EXACT (same order statistics numpy picks), whatever the value distribution:
@@ -24,6 +26,8 @@
 // Receptor catches come either from the per-pixel band sum in registers ("bands" mode, the
 // reference's own order of operations) or from the algebraically identical 3x3 (the whole chain
 // lobes -> illuminant -> sensitivities is linear; SURVEY.md 8a-11: 1.9e-7 relative difference).
+#include <algorithm>
+
 #include "avb_common.cuh"
 
 namespace avb {
@@ -68,6 +72,7 @@ struct UvParams {
     float t0, t1, t2;            // blur taps: centre, +-1, +-2
     UvFrameStats *stats;         // [n]
     uint32_t *hist;              // [n][UV_NH][UV_BINS]
+    float *planes;               // [n][UV_NH][H*W]: mapper quantities written by the hist pass
     float *cand;                 // [n][n_req][cap]
     long long cap;
     const uint32_t *enc;
@@ -431,16 +436,32 @@ __global__ void uv_prep_kernel(const __grid_constant__ UvParams p) {
 template <int QS>
 struct HistOp {
     uint32_t *hs;
+    float *planes;               // this frame's [NQ][H*W] quantity planes (read back by the compact pass)
+    long long npx;
     float inv_w[UV_NH];
     int W;
-    __device__ __forceinline__ void operator()(int /*y*/, int gx, const float (&v)[4][3], bool ok) {
+    bool vec;                    // W % 4 == 0: a lane's 4 pixels are one aligned float4 per plane
+    __device__ __forceinline__ void operator()(int y, int gx, const float (&v)[4][3], bool ok) {
+        if (!ok || gx >= W) return;
+        float q[4][UV_NH];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (ok && gx + j < W) {
-                float q[UV_NH];
-                quantities<QS>(v[j], q);
+            quantities<QS>(v[j], q[j]);
+            if (gx + j < W) {
 #pragma unroll
-                for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[h], inv_w[h])], 1u);
+                for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[j][h], inv_w[h])], 1u);
+            }
+        }
+        const long long o = (long long)y * W + gx;
+#pragma unroll
+        for (int h = 0; h < QCount<QS>::value; ++h) {
+            float *d = planes + h * npx + o;
+            if (vec) {
+                *reinterpret_cast<float4 *>(d) = make_float4(q[0][h], q[1][h], q[2][h], q[3][h]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (gx + j < W) d[j] = q[j][h];
             }
         }
     }
@@ -459,6 +480,9 @@ __global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_hist_kernel(const __gr
     cat.init_adapted(p, st, lut_s);
     HistOp<QS> op;
     op.hs = hs;
+    op.npx = (long long)p.io.H * p.io.W;
+    op.planes = p.planes + (long long)frame * UV_NH * op.npx;
+    op.vec = (p.io.W & 3) == 0;
 #pragma unroll
     for (int h = 0; h < UV_NH; ++h) op.inv_w[h] = st.inv_w[h];
     op.W = p.io.W;
@@ -516,90 +540,53 @@ __global__ void __launch_bounds__(256) uv_scan_kernel(const __grid_constant__ Uv
     }
 }
 
-// ------------------------------------------------------------------ collect
-template <int QS>
-struct CollectOp {
-    UvFrameStats *st;
-    float *cand;                 // this frame's [n_req][cap]
-    long long cap;
-    float inv_w[UV_NH];
-    int n_req, W;
-    int req_hist[UV_NR];
-    int lo[UV_NR], hi[UV_NR];
-    __device__ __forceinline__ void operator()(int /*y*/, int gx, const float (&v)[4][3], bool ok) {
-        const int lane = threadIdx.x & 31;
-        float q[4][UV_NH];
-        int bins[4][UV_NH];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            quantities<QS>(v[j], q[j]);
-#pragma unroll
-            for (int h = 0; h < UV_NH; ++h) bins[j][h] = bin_of(q[j][h], inv_w[h]);
-            if (ok && gx + j < W) {
-#pragma unroll
-                for (int r = 0; r < UV_NR; ++r)
-                    if (r < n_req) {
-                        const int h = req_hist[r];
-                        const int b = h == 0 ? bins[j][0] : (h == 1 ? bins[j][1] : bins[j][2]);
-                        any |= b >= lo[r] && b <= hi[r];
-                    }
-            }
-        }
-        if (!__any_sync(FULL, any)) return;          // the common case: nobody in this warp row hit a candidate bin
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool valid = ok && gx + j < W;
-#pragma unroll
-            for (int r = 0; r < UV_NR; ++r) {
-                if (r < n_req) {
-                    const int h = req_hist[r];
-                    const int b = h == 0 ? bins[j][0] : (h == 1 ? bins[j][1] : bins[j][2]);
-                    const float val = h == 0 ? q[j][0] : (h == 1 ? q[j][1] : q[j][2]);
-                    const bool hit = valid && b >= lo[r] && b <= hi[r];
-                    const unsigned m = __ballot_sync(FULL, hit);
-                    if (m) {
-                        const int leader = __ffs(m) - 1;
-                        uint32_t base = 0;
-                        if (lane == leader) base = atomicAdd(&st->cand_count[r], (uint32_t)__popc(m));
-                        base = __shfl_sync(FULL, base, leader);
-                        if (hit) cand[(long long)r * cap + base + __popc(m & ((1u << lane) - 1u))] = fmaxf(val, 0.f) + 0.f;
-                    }
-                }
-            }
-        }
-    }
-};
-
-template <int QS, int R, bool BANDS>
-__global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_collect_kernel(const __grid_constant__ UvParams p) {
-    __shared__ float lut_s[256];
-    const int tid = threadIdx.x, frame = blockIdx.y;
-    for (int i = tid; i < 256; i += UV_THREADS) lut_s[i] = __ldg(p.lut + i);
-    __syncthreads();
+// ------------------------------------------------------------------ compact
+// Reads the quantity planes the hist pass wrote (4 B per pixel and quantity instead of recomputing
+// catches + blur + mapper quantities) and appends every value whose bin is one of the request's
+// candidate bins to the request's list -- warp-aggregated, one atomic per warp and hit.
+constexpr int CP_PER_THREAD = 16, CP_PER_BLOCK = 256 * CP_PER_THREAD;
+__global__ void __launch_bounds__(256) uv_compact_kernel(const __grid_constant__ UvParams p) {
+    const int r = blockIdx.y, frame = blockIdx.z, lane = threadIdx.x & 31;
     UvFrameStats &st = p.stats[frame];
-    Catcher<BANDS> cat;
-    cat.init_adapted(p, st, lut_s);
-    CollectOp<QS> op;
-    op.st = &st;
-    op.cand = p.cand + (long long)frame * p.n_req * p.cap;
-    op.cap = p.cap;
-    op.n_req = p.n_req;
-    op.W = p.io.W;
+    const long long npx = (long long)p.io.H * p.io.W;
+    const int h = p.req_hist[r];
+    const float inv_w = st.inv_w[h];
+    const int lo = (int)st.bin_lo[r], hi = (int)st.bin_hi[r];
+    const float *src = p.planes + ((long long)frame * UV_NH + h) * npx;
+    float *dst = p.cand + ((long long)frame * p.n_req + r) * p.cap;
+    // thread t of the block owns pixels base + 4*(t + 256*k) .. +3, k = 0..3: four independent
+    // 16-byte loads in flight per thread, coalesced across the warp
+    const long long base = (long long)blockIdx.x * CP_PER_BLOCK;
+    float v[CP_PER_THREAD];
+    unsigned hits = 0;
 #pragma unroll
-    for (int h = 0; h < UV_NH; ++h) op.inv_w[h] = st.inv_w[h];
+    for (int k = 0; k < 4; ++k) {
+        const long long i = base + 4 * (threadIdx.x + 256 * k);
+        if (i + 3 < npx && (npx & 3) == 0) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(src + i));
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        } else {
 #pragma unroll
-    for (int r = 0; r < UV_NR; ++r) {
-        op.req_hist[r] = p.req_hist[r];
-        op.lo[r] = (int)st.bin_lo[r];
-        op.hi[r] = (int)st.bin_hi[r];
+            for (int j = 0; j < 4; ++j) v[4 * k + j] = (i + j < npx) ? __ldg(src + i + j) : -1.f;
+        }
     }
-    const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs;
-    const int tasks = p.strips_x * p.strips_y;
-    for (int task = blockIdx.x * UV_WARPS + (tid >> 5); task < tasks; task += gridDim.x * UV_WARPS) {
-        int xs, ys, rows;
-        strip_of<R>(p, task, xs, ys, rows);
-        uv_walk<R>(p, cat, src, xs, ys, rows, op);
+#pragma unroll
+    for (int e = 0; e < CP_PER_THREAD; ++e) {
+        const int b = bin_of(v[e], inv_w);
+        if (v[e] >= 0.f && b >= lo && b <= hi) hits |= 1u << e;      // v < 0 marks "past the end"
+    }
+    if (!__any_sync(FULL, hits != 0)) return;
+#pragma unroll
+    for (int e = 0; e < CP_PER_THREAD; ++e) {
+        const bool hit = (hits >> e) & 1u;
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t off = 0;
+            if (lane == leader) off = atomicAdd(&st.cand_count[r], (uint32_t)__popc(m));
+            off = __shfl_sync(FULL, off, leader);
+            if (hit) dst[off + __popc(m & ((1u << lane) - 1u))] = v[e] + 0.f;
+        }
     }
 }
 
@@ -875,8 +862,9 @@ static int launch_percentiles(const UvParams &p, cudaStream_t st) {
         uv_scan_kernel<<<p.io.n, 256, 0, st>>>(p);
     }
     {
-        AVB_TIMED("k3_uv_collect", st);
-        uv_collect_kernel<QS, R, BANDS><<<walk_grid(p, 8), UV_THREADS, 0, st>>>(p);
+        AVB_TIMED("k3_uv_compact", st);
+        const long long npx = (long long)p.io.H * p.io.W;
+        uv_compact_kernel<<<dim3((unsigned)((npx + CP_PER_BLOCK - 1) / CP_PER_BLOCK), p.n_req, p.io.n), 256, 0, st>>>(p);
     }
     {
         AVB_TIMED("k3_uv_select", st);
@@ -935,8 +923,9 @@ extern "C" int64_t avb_uv_workspace_bytes(int n, int H, int W, int map_mode) {
     if (n <= 0 || H <= 0 || W <= 0 || map_mode < 0 || map_mode > MAP_MIXED) return 0;
     const size_t stats = align_up((size_t)n * sizeof(UvFrameStats), 256);
     const size_t hist = (size_t)n * UV_NH * UV_BINS * sizeof(uint32_t);
+    const size_t planes = n_requests(map_mode) ? (size_t)n * UV_NH * (size_t)H * W * sizeof(float) : 0;
     const size_t cand = (size_t)n * n_requests(map_mode) * (size_t)H * W * sizeof(float);
-    return (int64_t)(stats + hist + cand);
+    return (int64_t)(stats + hist + planes + cand);
 }
 
 extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int W,
@@ -993,7 +982,9 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
     const size_t hist_bytes = (size_t)n * UV_NH * UV_BINS * sizeof(uint32_t);
     p.stats = reinterpret_cast<UvFrameStats *>(ws);
     p.hist = reinterpret_cast<uint32_t *>(ws + stats_bytes);
-    p.cand = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes);
+    const size_t planes_bytes = n_requests(map_mode) ? (size_t)n * UV_NH * (size_t)npx * sizeof(float) : 0;
+    p.planes = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes);
+    p.cand = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes + planes_bytes);
     p.cap = npx;
 
     // percentile requests (numpy.percentile(method="linear"): virtual index q/100 * (N-1))

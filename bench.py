@@ -46,7 +46,7 @@ SPECIES = ("Dog", "Cat", "HoneyBee")
 ALGO_BYTES_PER_PX = {"Dog": 6, "Cat": 9, "HoneyBee": 6}
 KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
                   "k3_uv_stats": "HoneyBee", "k3_uv_hist1": "HoneyBee", "k3_uv_hist2": "HoneyBee",
-                  "k3_uv_hist3": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_collect": "HoneyBee",
+                  "k3_uv_hist3": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_collect": "HoneyBee", "k3_uv_compact": "HoneyBee",
                   "k3_uv_prep": "HoneyBee", "k3_uv_scan": "HoneyBee", "k3_uv_select": "HoneyBee", "k2_streak": "Dog"}
 
 
