@@ -225,8 +225,14 @@ struct CatProducer {
 };
 
 // ------------------------------------------------------------------------------------ kernel
+#ifndef G_MINB
+#define G_MINB 2
+#endif
+#ifndef G_MINB3_R
+#define G_MINB3_R 8
+#endif
 template <int R>
-struct GaussOcc { static constexpr int MIN_BLOCKS = 2; };
+struct GaussOcc { static constexpr int MIN_BLOCKS = (R <= G_MINB3_R) ? 3 : G_MINB; };
 
 template <int R, class Prod>
 __global__ void __launch_bounds__(G_THREADS, GaussOcc<R>::MIN_BLOCKS)

@@ -37,9 +37,12 @@ constexpr int UV_NH = 3;                 // histograms (mapper quantities) per f
 constexpr int UV_NR = 4;                 // percentile requests per frame
 constexpr int UV_MAX_BANDS = 160;
 constexpr int UV_THREADS = 256, UV_WARPS = UV_THREADS / 32;
-constexpr int UV_RH = 64;                // output rows per strip
+#ifndef UV_RH_ROWS
+#define UV_RH_ROWS 64
+#endif
+constexpr int UV_RH = UV_RH_ROWS;        // output rows per strip
 #ifndef UV_MINB
-#define UV_MINB 3
+#define UV_MINB 4
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 
