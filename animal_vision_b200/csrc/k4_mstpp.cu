@@ -378,16 +378,26 @@ struct DwP {
     const float *w;               // [9][Cp]
     int B, H, W, Cp, gelu_out, seg;
 };
-// Thread = (image, column x, group of 8 channels); it walks down a segment of rows keeping the
-// 3 x 3 x 8 input window (fp32) and its 72 weights in registers: three 16-byte loads per output
-// instead of nine plus eighteen weight loads.
-__device__ __forceinline__ void dw_unpack(const uint4 &raw, float (&f)[8]) {
+// Thread = (image, column x, group of CPT channels); it walks down a segment of rows keeping the
+// 3 x 3 x CPT input window (fp32) and its 9 x CPT weights in registers: three vector loads per
+// output instead of nine plus the weight loads.  CPT = 4 keeps the register count low enough for
+// 5 CTAs per SM (the 8-channel variant ran at 2 and was latency bound).
+#ifndef DW_CPT
+#define DW_CPT 4
+#endif
+template <int CPT> struct DwVec;
+template <> struct DwVec<8> { typedef uint4 T; };
+template <> struct DwVec<4> { typedef uint2 T; };
+template <int CPT>
+__device__ __forceinline__ void dw_unpack(const typename DwVec<CPT>::T &raw, float (&f)[CPT]) {
     const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { f[2 * q] = __low2float(h2[q]); f[2 * q + 1] = __high2float(h2[q]); }
+    for (int q = 0; q < CPT / 2; ++q) { f[2 * q] = __low2float(h2[q]); f[2 * q + 1] = __high2float(h2[q]); }
 }
+template <int CPT>
 __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP p) {
-    const int groups = p.Cp >> 3;
+    typedef typename DwVec<CPT>::T V;
+    const int groups = p.Cp / CPT;
     const int segs = (p.H + p.seg - 1) / p.seg;
     const long long total = (long long)p.B * segs * p.W * groups;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,33 +409,33 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
     const int sg = (int)(t % segs), b = (int)(t / segs);
     const int y0 = sg * p.seg, y1 = min(p.H, y0 + p.seg);
 
-    float w[9][8];
+    float w[9][CPT];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + 8 * g));
-        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + 8 * g) + 1);
-        w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
-        w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
-    }
-    const bf16 *base = p.in + (long long)b * p.H * p.W * p.ldi + 8 * g;
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int c = 0; c < CPT; c += 4) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + CPT * g + c));
+            w[k][c] = w0.x; w[k][c + 1] = w0.y; w[k][c + 2] = w0.z; w[k][c + 3] = w0.w;
+        }
+    const bf16 *base = p.in + (long long)b * p.H * p.W * p.ldi + CPT * g;
     const bool has_l = x > 0, has_r = x + 1 < p.W;
-    auto load_row = [&](int y, uint4 (&raw)[3]) {
-        raw[0] = raw[1] = raw[2] = make_uint4(0u, 0u, 0u, 0u);        // conv zero padding
+    auto load_row = [&](int y, V (&raw)[3]) {
+        raw[0] = raw[1] = raw[2] = V{};                               // conv zero padding
         if ((unsigned)y < (unsigned)p.H) {
             const bf16 *r = base + ((long long)y * p.W + x) * p.ldi;
-            if (has_l) raw[0] = __ldg(reinterpret_cast<const uint4 *>(r - p.ldi));
-            raw[1] = __ldg(reinterpret_cast<const uint4 *>(r));
-            if (has_r) raw[2] = __ldg(reinterpret_cast<const uint4 *>(r + p.ldi));
+            if (has_l) raw[0] = __ldg(reinterpret_cast<const V *>(r - p.ldi));
+            raw[1] = __ldg(reinterpret_cast<const V *>(r));
+            if (has_r) raw[2] = __ldg(reinterpret_cast<const V *>(r + p.ldi));
         }
     };
-    float win[3][3][8];               // [row slot][dx][channel]
-    uint4 raw[3];
+    float win[3][3][CPT];             // [row slot][dx][channel]
+    V raw[3];
     load_row(y0 - 1, raw);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[0][d]);
+    for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[0][d]);
     load_row(y0, raw);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[1][d]);
+    for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[1][d]);
     load_row(y0 + 1, raw);
     for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
@@ -433,25 +443,27 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
             const int y = yb + ph;
             if (y < y1) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) dw_unpack(raw[d], win[(ph + 2) % 3][d]);      // row y + 1
+                for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[(ph + 2) % 3][d]);      // row y + 1
                 if (y + 1 < y1) load_row(y + 2, raw);
-                float acc[8];
+                float acc[CPT];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+                for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[c] = fmaf(win[(ph + ky) % 3][kx][c], w[ky * 3 + kx][c], acc[c]);
+                        for (int c = 0; c < CPT; ++c) acc[c] = fmaf(win[(ph + ky) % 3][kx][c], w[ky * 3 + kx][c], acc[c]);
                 if (p.gelu_out) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[c] = gelu(acc[c]);
+                    for (int c = 0; c < CPT; ++c) acc[c] = gelu(acc[c]);
                 }
-                uint4 o;
-                o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-                o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-                *reinterpret_cast<uint4 *>(p.out + (((long long)b * p.H + y) * p.W + x) * p.ldo + 8 * g) = o;
+                uint32_t o[CPT / 2];
+#pragma unroll
+                for (int q = 0; q < CPT / 2; ++q) o[q] = pack_bf16(acc[2 * q], acc[2 * q + 1]);
+                bf16 *dst = p.out + (((long long)b * p.H + y) * p.W + x) * p.ldo + CPT * g;
+                if (CPT == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[CPT / 2 - 2], o[CPT / 2 - 1]);
+                else *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
             }
         }
     }
@@ -856,12 +868,12 @@ static void conv3x3(Ctx &cx, const float *in, const bf16 *w, float *out, const f
 
 static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const float *w, int H, int W, int Cp, int gelu_out, const char *name) {
     // rows per thread: long enough to amortise the 2 halo rows, short enough to fill the machine
-    const long long items = (long long)cx.B * H * W * (Cp / 8);
+    const long long items = (long long)cx.B * H * W * (Cp / DW_CPT);
     const int seg = (int)std::max<long long>(4, std::min<long long>(32, items / ((long long)sm_count() * 1024)));
     DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out, seg};
-    const long long total = (long long)cx.B * ((H + seg - 1) / seg) * W * (Cp / 8);
+    const long long total = (long long)cx.B * ((H + seg - 1) / seg) * W * (Cp / DW_CPT);
     AVB_TIMED(name, cx.st);
-    dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, cx.st>>>(p);
+    dwconv_kernel<DW_CPT><<<(unsigned)((total + 127) / 128), 128, 0, cx.st>>>(p);
 }
 
 // MSAB with num_blocks = 1 (MST_Plus_Plus.py:160-186), in place on x (fp32 [B*rows, Cp]).

@@ -1,7 +1,6 @@
 #!/bin/bash
-for v in "-DUV_MINB=4 -DUV_RH_ROWS=32" "-DUV_MINB=4 -DUV_RH_ROWS=48" "-DUV_MINB=5 -DUV_RH_ROWS=32"; do
-  AVB_NVCC_EXTRA="$v" python tools/bee_kernels.py HoneyBee 2>&1 | tail -1
-done
-for v in "" "-DG_MINB3_R=8"; do
-  for sp in Squirrel Bear Raccoon Lion; do AVB_NVCC_EXTRA="$v" python tools/bee_kernels.py $sp 2>&1 | tail -1; done
+python -m pytest tests/test_gpu_mstpp.py -x -q 2>&1 | tail -2
+for v in "" "-DDW_CPT=8"; do
+  echo "variant: $v"; AVB_NVCC_EXTRA="$v" python tools/mstpp_bench.py 1 482 512 2>&1 | head -4
+  AVB_NVCC_EXTRA="$v" python tools/mstpp_bench.py 8 482 512 2>&1 | head -1
 done
