@@ -34,12 +34,13 @@ SIGNATURES = {
     "avb_colorimetric_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _p, _p]),
     "avb_dichromat_blur_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _i, _p, _p]),
     "avb_streak_blur_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _f, _i, _p, _p]),
-    "avb_cat_u8": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
+    "avb_cat_u8": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
     "avb_mstpp_create": (_i, [_p, _i64, _p]),
     "avb_mstpp_destroy": (_i, [_p]),
     "avb_mstpp_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "avb_mstpp_forward": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "avb_band_project_f32": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
+    "avb_safe_norm_f32": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
     "avb_uv_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "avb_uv_map_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i, _f, _i, _p, _i, _i, _p, _f, _p, _p, _p]),
 }

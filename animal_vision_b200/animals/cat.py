@@ -25,11 +25,11 @@ class Cat(Animal):
         return (self.CAMERA_HFOV_DEG, self.CAT_PER_EYE_HALF_FOV_DEG, self.CAT_OVERLAP_DEG, self.CAT_TO_HUMAN_RATIO)
 
     def _run(self, eng, frames, out_human, out_cat):
-        if not self.ENABLE_FOV_WARP:
-            raise NotImplementedError("Cat with ENABLE_FOV_WARP=False is not implemented on the GPU path")
         _, H, W, _ = frames.shape
-        warp = eng.cached(("cat_warp", W) + self._geometry_key(), lambda: eng._dev(
-            tables.cat_warp_device_table(W, self.CAMERA_HFOV_DEG, self.CAT_PER_EYE_HALF_FOV_DEG, self.CAT_OVERLAP_DEG)))
+        warp = None                                          # ENABLE_FOV_WARP = False: cat.py:84 skips the warp
+        if self.ENABLE_FOV_WARP:
+            warp = eng.cached(("cat_warp", W) + self._geometry_key(), lambda: eng._dev(
+                tables.cat_warp_device_table(W, self.CAMERA_HFOV_DEG, self.CAT_PER_EYE_HALF_FOV_DEG, self.CAT_OVERLAP_DEG)))
         scale = tables.cat_zoom_scale(self.CAMERA_HFOV_DEG, self.CAT_PER_EYE_HALF_FOV_DEG, self.CAT_TO_HUMAN_RATIO)
         zoom = eng.cached(("cat_zoom", W, H) + self._geometry_key(),
                           lambda: eng._dev(tables.center_zoom_tables(W, H, scale)))

@@ -584,18 +584,20 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
                           int64_t in_frame_stride, int64_t in_row_stride,
                           int64_t human_frame_stride, int64_t human_row_stride,
                           int64_t cat_frame_stride, int64_t cat_row_stride,
+                          const float *dec_dev, const float *dec_raw_dev,
                           const uint32_t *enc_dev, const float *m_host, const float *taps_host, int ksize,
                           const float *warp_dev, const int32_t *zoom_dev,
                           int norm_mode, uint32_t *flags_dev, avb_stream_t stream) {
     GaussCommon gc{};
     gc.io = FrameIO{in, out_cat, in_frame_stride, in_row_stride, cat_frame_stride, cat_row_stride, n, H, W};
     if (int e = check_io(gc.io)) return e;
-    AVB_REQUIRE(enc_dev && m_host && taps_host && warp_dev, "null table pointer");
+    AVB_REQUIRE(enc_dev && m_host && taps_host, "null table pointer");
+    AVB_REQUIRE(warp_dev || (dec_dev && (norm_mode == AVB_NORM_DIV255 || dec_raw_dev)), "without warp_dev the decode LUTs are required");
     AVB_REQUIRE(ksize >= 3 && ksize <= G_MAX_TAPS && (ksize & 1), "ksize must be odd, 3..33");
     AVB_REQUIRE(norm_mode == AVB_NORM_DIV255 || (norm_mode == AVB_NORM_AUTO && flags_dev), "AVB_NORM_AUTO needs flags_dev");
     AVB_REQUIRE((out_human == nullptr) == (zoom_dev == nullptr), "out_human and zoom_dev go together");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (norm_mode == AVB_NORM_AUTO) {
+    if (norm_mode == AVB_NORM_AUTO && warp_dev) {
         AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
         dim3 grid(H < 256 ? H : 256, n);
         AVB_TIMED("frame_flags", st);
@@ -615,6 +617,25 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
     }
     for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];
     gc.enc = enc_dev;
+    if (!warp_dev) {
+        // ENABLE_FOV_WARP = False (cat.py:21, :84): no gather, so the input is plain uint8 and the
+        // LUT producer applies -- decode -> collapsed L/M-merge matrix -> blur -> float64-tail encode
+        DogProducer::Params dp{};
+        for (int i = 0; i < 9; ++i) dp.M.m[i] = m_host[i];
+        dp.lut = dec_dev;
+        if (norm_mode == AVB_NORM_AUTO) {
+            AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
+            gc.flags = flags_dev;
+        }
+        gc.fixup = 0;
+        if (int e = dispatch_gauss<DogProducer>(ksize / 2, gc, dp, st)) return e;
+        if (norm_mode == AVB_NORM_AUTO) {
+            gc.fixup = 1;
+            dp.lut = dec_raw_dev;
+            if (int e = dispatch_gauss<DogProducer>(ksize / 2, gc, dp, st)) return e;
+        }
+        return AVB_OK;
+    }
     gc.flags = nullptr;   // the producer does not see every pixel: normalisation comes from frame_flags_kernel
     gc.fixup = 0;
     CatProducer::Params pp{};

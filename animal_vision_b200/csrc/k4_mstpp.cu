@@ -656,6 +656,45 @@ __global__ void __launch_bounds__(256) band_project_kernel(const float *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------ safe_norm
+// uv_helpers.py:47-53 safe_norm: (x - min) / (max - min) over a whole map, zeros when the range is
+// below 1e-9.  Maps are interleaved: element px of map k is in[px * stride + k].
+__device__ __forceinline__ uint32_t f2ord(float f) {          // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__global__ void __launch_bounds__(256) minmax_kernel(const float *__restrict__ in, long long npx, int stride, int n_maps, uint32_t *mm) {
+    const int k = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(in + i * stride + k);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + k, f2ord(mn));
+        atomicMax(mm + n_maps + k, f2ord(mx));
+    }
+}
+__global__ void __launch_bounds__(256) safe_norm_kernel(const float *__restrict__ in, float *__restrict__ out, long long npx, int stride,
+                                                        int n_maps, const uint32_t *mm) {
+    const int k = blockIdx.y;
+    const float mn = ord2f(mm[k]), mx = ord2f(mm[n_maps + k]);
+    const double range = (double)mx - (double)mn;              // python floats in the reference
+    const float den = (float)range;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(in + i * stride + k);
+        out[i * stride + k] = range < 1e-9 ? 0.f : __fdiv_rn(__fsub_rn(v, mn), den);
+    }
+}
+
 // ------------------------------------------------------------------------------------ host: weights
 struct MsabW {
     int c, Cp, heads, Hp;
@@ -1060,6 +1099,27 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
         p.Hi = p.Ho = Hp; p.Wi = p.Wo = Wp; p.Cpin = 32;
         p.res1 = ws.x0; p.ldr1 = 32; p.out = out; p.out_mode = OUT_CROP; p.Hreal = H; p.Wreal = W; p.crop_top = top; p.crop_left = left;
         launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_safe_norm_f32(const float *in_dev, float *out_dev, int64_t npx, int stride, int n_maps,
+                                 void *scratch_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && scratch_dev, "null pointer");
+    AVB_REQUIRE(npx > 0 && n_maps > 0 && n_maps <= 65535 && stride >= n_maps, "bad map geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t *mm = static_cast<uint32_t *>(scratch_dev);
+    AVB_CUDA_OK(cudaMemsetAsync(mm, 0xff, sizeof(uint32_t) * n_maps, st));            // minima: +inf in ordered form
+    AVB_CUDA_OK(cudaMemsetAsync(mm + n_maps, 0x00, sizeof(uint32_t) * n_maps, st));   // maxima: -inf in ordered form
+    const int bx = (int)std::min<long long>((npx + 255) / 256, (long long)sm_count() * 8);
+    {
+        AVB_TIMED("safe_norm_minmax", st);
+        minmax_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(in_dev, npx, stride, n_maps, mm);
+    }
+    {
+        AVB_TIMED("safe_norm", st);
+        safe_norm_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(in_dev, out_dev, npx, stride, n_maps, mm);
     }
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;

@@ -132,7 +132,9 @@ class Engine:
         taps = np.ascontiguousarray(taps, np.float32)
         rc = self.lib.avb_cat_u8(
             frames.data_ptr(), out_human.data_ptr(), out_cat.data_ptr(), n, h, w, fs, rs, hfs, hrs, cfs, crs,
-            self.enc64.data_ptr(), _fptr(M), _fptr(taps), int(taps.size), warp_dev.data_ptr(), zoom_dev.data_ptr(),
+            self.dec.data_ptr(), self.dec_raw.data_ptr(),
+            self.enc64.data_ptr(), _fptr(M), _fptr(taps), int(taps.size),
+            None if warp_dev is None else warp_dev.data_ptr(), zoom_dev.data_ptr(),
             norm, self.flags(n).data_ptr() if norm == AVB_NORM_AUTO else None, self.stream_ptr())
         check(rc, "avb_cat_u8")
         self.launches += 3 if norm == AVB_NORM_AUTO else 2

@@ -166,6 +166,21 @@ class MSTPlusPlus:
         return out
 
 
+def safe_norm_maps(maps):
+    """uv_helpers.py:47-53 safe_norm applied independently to every map of a CUDA float32 tensor
+    [..., R] (R interleaved maps, e.g. the band projections)."""
+    eng = get_engine(maps.device)
+    t = eng.torch
+    assert maps.is_cuda and maps.dtype == t.float32
+    maps = maps.contiguous()
+    r = maps.shape[-1]
+    out = t.empty_like(maps)
+    scratch = t.empty(2 * r, dtype=t.int32, device=maps.device)
+    rc = eng.lib.avb_safe_norm_f32(maps.data_ptr(), out.data_ptr(), maps.numel() // r, r, r, scratch.data_ptr(), eng.stream_ptr())
+    check(rc, "avb_safe_norm_f32")
+    return out
+
+
 def mantis_bands(cube, model: MSTPlusPlus, wavelengths=None):
     """The ten mantis-shrimp bands of animals/mantis_shrimp.py:49-60 integrated over an MST++ cube."""
     lam = np.linspace(400.0, 700.0, N_FEAT, dtype=np.float32) if wavelengths is None else np.asarray(wavelengths, np.float32)

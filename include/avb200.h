@@ -119,7 +119,9 @@ AVB_API int avb_streak_blur_u8(const uint8_t *in, uint8_t *out, int n, int H, in
  *              1/32-px coordinate quantisation, BORDER_CONSTANT 0, cos^2 blend) fused, as the producer
  *              stage, into the K2 blur kernel: decode (pow) -> collapsed 3x3 (cat.py:95-101) ->
  *              Gaussian sigma=1.0 (9 taps) -> encode.
- *   warp_dev   6*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights),
+ *   dec_dev / dec_raw_dev  decode LUTs as in avb_colorimetric_u8; only read when warp_dev is NULL
+ *   warp_dev   NULL = class switch ENABLE_FOV_WARP False (cat.py:21): no warp, LUT producer; else
+ *              6*W float32: xL, xR, wL, wR (per-column source x of the two eye views, blend weights),
  *              ws = wL + wR + 1e-8 (the blend denominator, float32) and 1/ws (correctly rounded)
  *   zoom_dev   4*W + 4*H int32, 16-byte aligned: W records {xi0, xi1, xw0, xw1} then H records
  *              {yi0, yi1, yw0, yw1} (source indices incl. crop origin, 11-bit weights)
@@ -130,6 +132,7 @@ AVB_API int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_cat, 
                        int64_t in_frame_stride, int64_t in_row_stride,
                        int64_t human_frame_stride, int64_t human_row_stride,
                        int64_t cat_frame_stride, int64_t cat_row_stride,
+                       const float *dec_dev, const float *dec_raw_dev,
                        const uint32_t *enc_dev, const float *m_host, const float *taps_host, int ksize,
                        const float *warp_dev, const int32_t *zoom_dev,
                        int norm_mode, uint32_t *flags_dev, avb_stream_t stream);
@@ -195,6 +198,12 @@ AVB_API int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, float 
  * weights come from the host (uv_helpers.py:125-139 bandpass_weights).  All pointers device float32. */
 AVB_API int avb_band_project_f32(const float *cube_dev, const float *weights_dev, float *out_dev,
                                  int64_t npx, int n_bands, int n_receptors, avb_stream_t stream);
+
+/* uv_helpers.py:47-53 safe_norm on n_maps interleaved float32 maps (element px of map k at
+ * in[px*stride + k]): (x - min) / (max - min) over the whole map, zeros when max - min < 1e-9.
+ * scratch_dev: 2*n_maps uint32.  In place (out_dev == in_dev) is allowed. */
+AVB_API int avb_safe_norm_f32(const float *in_dev, float *out_dev, int64_t npx, int stride, int n_maps,
+                              void *scratch_dev, avb_stream_t stream);
 
 #ifdef __cplusplus
 }

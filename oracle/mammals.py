@@ -254,11 +254,14 @@ def cat_binocular_warp(srgb01: np.ndarray) -> np.ndarray:
     return np.clip(out, 0.0, 1.0).astype(np.float32)
 
 
-def cat_linear(image: np.ndarray) -> np.ndarray:
-    """cat.py:83-102: warped frame -> linear -> LMS (f32) -> L/M merge -> RGB (float64 from here,
-    because LMS_TO_RGB is a float64 matrix) -> 9x9 acuity blur in CV_64F."""
+def cat_linear(image: np.ndarray, fov_warp: bool = True) -> np.ndarray:
+    """cat.py:83-102: [warped] frame -> linear -> LMS (f32) -> L/M merge -> RGB (float64 from here,
+    because LMS_TO_RGB is a float64 matrix) -> 9x9 acuity blur in CV_64F.  fov_warp=False is the
+    class switch ENABLE_FOV_WARP = False (cat.py:21, :84)."""
     H, W = image.shape[:2]
-    s01 = cat_binocular_warp(C.normalize_frame(image).astype(np.float32))
+    s01 = C.normalize_frame(image).astype(np.float32)
+    if fov_warp:
+        s01 = cat_binocular_warp(s01)
     lms = C.decode_srgb(s01).reshape(-1, 3) @ C.RGB_TO_LMS.T
     lm = 0.5 * lms[:, 0] + (1.0 - 0.5) * lms[:, 1]
     merged = np.stack([lm, lm, lms[:, 2]], axis=1)
@@ -266,12 +269,12 @@ def cat_linear(image: np.ndarray) -> np.ndarray:
     return acuity_blur(rgb, 1.0)
 
 
-def cat_visualize(image: np.ndarray):
+def cat_visualize(image: np.ndarray, fov_warp: bool = True):
     """Cat.visualize (cat.py:23-114). Returns (human_zoomed, cat_view) -- NOT the input object."""
     assert isinstance(image, np.ndarray) and image.ndim == 3 and image.shape[2] == 3
     dt = image.dtype
     human = center_zoom(image, cat_zoom_scale())
-    cat_srgb = np.clip(C.encode_srgb(np.clip(cat_linear(image), 0.0, 1.0)), 0.0, 1.0)
+    cat_srgb = np.clip(C.encode_srgb(np.clip(cat_linear(image, fov_warp), 0.0, 1.0)), 0.0, 1.0)
     if np.issubdtype(dt, np.integer):
         if not np.issubdtype(human.dtype, np.integer):  # pragma: no cover
             human = (np.clip(human, 0, 1) * 255.0 + 0.5).astype(dt)

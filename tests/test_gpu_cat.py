@@ -47,3 +47,23 @@ def test_cat_batch():
     for i, f in enumerate(fs):
         ref_h, ref_c = M.cat_visualize(f)
         _check(human[i].cpu().numpy(), cat[i].cpu().numpy(), ref_h, ref_c, f"batch[{i}]")
+
+
+def test_cat_without_fov_warp(golden, golden_meta):
+    """Class switch ENABLE_FOV_WARP = False (cat.py:21): centre zoom + L/M merge + blur, no warp."""
+    from animal_vision_b200.animals import Cat
+    NoWarp = type("NoWarp", (Cat,), {"ENABLE_FOV_WARP": False})
+    h, w = golden_meta["small_hw"]
+    g = golden("cat")
+    fr = dict(frames.parity_set(h, w))
+    n = 0
+    for key in g:
+        if key.startswith("nowarp_cat/"):
+            name = key.split("/")[1]
+            human, cat = NoWarp().visualize(fr[name])
+            _check(human, cat, g[f"nowarp_human/{name}"], g[key], key)
+            n += 1
+    assert n >= 3
+    f = frames.natural(270, 480)
+    ref_h, ref_c = M.cat_visualize(f, fov_warp=False)
+    _check(*NoWarp().visualize(f), ref_h, ref_c, "nowarp 270x480")

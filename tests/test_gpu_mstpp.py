@@ -93,3 +93,16 @@ def test_bad_state_dict_is_rejected():
     sd.pop("conv_out.weight")
     with pytest.raises(KeyError):
         MSTPlusPlus(sd)
+
+
+def test_safe_norm_maps():
+    """uv_helpers.py:47-53 on interleaved maps, including a constant map (range < 1e-9 -> zeros)."""
+    from animal_vision_b200.mstpp import safe_norm_maps
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((37, 53, 4)).astype(np.float32)
+    a[..., 2] = 0.25                                           # constant map
+    a[..., 3] = np.abs(a[..., 3]) * 1e3
+    got = safe_norm_maps(torch.from_numpy(a).cuda()).cpu().numpy()
+    for k in range(4):
+        ref = uv.safe_norm(a[..., k])
+        assert np.array_equal(got[..., k], ref), k

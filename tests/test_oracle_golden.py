@@ -42,6 +42,15 @@ def test_cat_bit_exact(golden, golden_meta):
         human, cat = M.cat_visualize(f)
         assert np.array_equal(human, g[f"human/{name}"]), name
         assert np.array_equal(cat, g[f"cat/{name}"]), name
+    # class switch ENABLE_FOV_WARP = False (cat.py:21)
+    n = 0
+    for key in g:
+        if key.startswith("nowarp_cat/"):
+            name = key.split("/")[1]
+            human, cat = M.cat_visualize(fr[name], fov_warp=False)
+            assert np.array_equal(human, g[f"nowarp_human/{name}"]) and np.array_equal(cat, g[key]), key
+            n += 1
+    assert n >= 3
 
 
 def test_honeybee_bit_exact(golden, golden_meta):

@@ -68,6 +68,12 @@ def main():
         human, cat = Cat().visualize(f.copy())
         store[f"human/{name}"] = human
         store[f"cat/{name}"] = cat
+    CatNoWarp = type("CatNoWarp", (Cat,), {"ENABLE_FOV_WARP": False})        # class switch, cat.py:21
+    for name in ("noise0", "natural", "le1", "bars"):
+        f = dict(frames.parity_set(h, w))[name]
+        human, cat = CatNoWarp().visualize(f.copy())
+        store[f"nowarp_human/{name}"] = human
+        store[f"nowarp_cat/{name}"] = cat
     np.savez_compressed(os.path.join(OUT, "cat.npz"), **store)
 
     # ---- honeybee: default on the full set; other mappers / adaptation on noise + natural
