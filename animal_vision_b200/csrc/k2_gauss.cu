@@ -15,16 +15,25 @@
 // The fp32 intermediate never leaves shared memory: HBM sees the uint8 frame once in and once out
 // (6 B/px).
 //
+// Two-plane mode: every dichromat matrix of the reference (collapse_LMS_matrix, animal_utils.py:
+// 88-119, and the cat's L/M merge) has rank 2 -- L and M are merged before the way back to RGB --
+// so T = P(3x2) Q(2x3) and blur(T x) = P blur(Q x): only TWO planes are produced and blurred (a
+// third fewer FMAs), the 3x2 expansion happens in the encode phase.  Full-rank matrices take the
+// three-plane instantiation.
+//
 // The producer is a policy: DogProducer (LUT decode + 3x3; animals/dog.py:35-48) or CatProducer
 // (binocular wide-FOV gather + blend + pow decode + 3x3; animals/cat_widevision_utils.py:46-99,
 // animals/cat.py:95-101).
+#include <algorithm>
+#include <cmath>
+
 #include "avb_common.cuh"
 
 namespace avb {
 
 constexpr int G_TW = 128;       // strip width in pixels
 constexpr int G_RB = 8;         // rows per block
-constexpr int G_THREADS = 384;  // 12 warps: H pass (channel, row, 8-px group); V pass (channel, column)
+constexpr int G_THREADS_PER_PLANE = 128;  // H pass (plane, row, 8-px group); V pass (plane, column)
 constexpr int G_MAX_TAPS = 33;
 constexpr int G_ENC_SMEM = AVB_ENC_TABLE_MAX;  // uint32 words reserved for the encode table
 constexpr int G_RAW_PITCH = 528;               // bytes per row of the raw tile (>= 16 * 33)
@@ -41,14 +50,14 @@ struct GaussCfg {
     static constexpr int SP_MIN = SP_WIN > 4 * GROUPS ? SP_WIN : 4 * GROUPS;
     static constexpr int S_PITCH = g_round_pitch(SP_MIN);             // % 8 == 4: odd multiple of 16 B, conflict-free LDS.128
     static constexpr int X_PITCH = G_TW + 4;
-    static constexpr int S_FLOATS = 3 * G_RB * S_PITCH;
-    static constexpr int X_FLOATS = 3 * G_RB * X_PITCH;
-    static constexpr int STAGE_BYTES = G_RB * G_TW * 3;
+    static constexpr int S_PLANE = G_RB * S_PITCH;                    // floats per plane
+    static constexpr int X_PLANE = G_RB * X_PITCH;
     static constexpr int RAW_BYTES = G_RB * G_RAW_PITCH;
 };
 
 struct GaussCommon {
     FrameIO io;
+    float P[6];            // two-plane mode: rgb[c] = P[2c] * plane0 + P[2c+1] * plane1 (rank-2 colour matrix)
     float taps[G_MAX_TAPS];
     const uint32_t *enc;   // encode table (device)
     uint32_t *flags;       // per-frame "some byte >= 2" (AVB_NORM_AUTO) or nullptr
@@ -234,16 +243,17 @@ struct CatProducer {
 template <int R>
 struct GaussOcc { static constexpr int MIN_BLOCKS = (R <= G_MINB3_R) ? 3 : G_MINB; };
 
-template <int R, class Prod>
-__global__ void __launch_bounds__(G_THREADS, GaussOcc<R>::MIN_BLOCKS)
+template <int R, class Prod, int NCH>
+__global__ void __launch_bounds__(G_THREADS_PER_PLANE * NCH, GaussOcc<R>::MIN_BLOCKS)
 gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant__ typename Prod::Params pp) {
     using C = GaussCfg<R>;
+    constexpr int THREADS = G_THREADS_PER_PLANE * NCH;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float *S = reinterpret_cast<float *>(smem_raw);            // [3][RB][S_PITCH] produced rows (+x halo)
-    float *X = S + C::S_FLOATS;                                // [3][RB][X_PITCH] horizontally blurred rows
-    float *prod_smem = X + C::X_FLOATS;
-    uint8_t *stage = reinterpret_cast<uint8_t *>(prod_smem + Prod::SMEM_FLOATS);   // [RB][TW*3] encoded bytes
-    uint32_t *enc_s = reinterpret_cast<uint32_t *>(stage + C::STAGE_BYTES);
+    float *S = reinterpret_cast<float *>(smem_raw);            // [NCH][RB][S_PITCH] produced rows (+x halo)
+    float *X = S + NCH * C::S_PLANE;                           // [NCH][RB][X_PITCH] horizontally blurred rows
+    float *Y = X + NCH * C::X_PLANE;                           // [NCH][RB][X_PITCH] fully blurred rows
+    float *prod_smem = Y + NCH * C::X_PLANE;
+    uint32_t *enc_s = reinterpret_cast<uint32_t *>(prod_smem + Prod::SMEM_FLOATS);
     uint8_t *rawt = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);               // [RB][RAW_PITCH] packed input rows
 
     const int frame = blockIdx.z;
@@ -265,11 +275,12 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     uint8_t *dst_frame = p.io.out + (int64_t)frame * p.io.out_fs;
     const bool vec_ok = (x0 + G_TW <= W) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
+    const bool out4 = ((p.io.out_rs & 3) == 0) && ((p.io.out_fs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.io.out) & 3) == 0);
 
     // a strip whose producer is identically zero (the cat's blind middle third) encodes to byte 0
     if (prod.all_black(x0 - R, x0 + G_TW + R)) {
         const int nbytes = min(G_TW, W - x0) * 3;
-        for (int y = y_start + warp; y < y_end; y += G_THREADS / 32) {
+        for (int y = y_start + warp; y < y_end; y += THREADS / 32) {
             uint8_t *row = dst_frame + (int64_t)y * p.io.out_rs + (int64_t)x0 * 3;
             if (vec_ok) {
                 if (lane < G_TW * 3 / 16) reinterpret_cast<uint4 *>(row)[lane] = make_uint4(0u, 0u, 0u, 0u);
@@ -285,21 +296,21 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     const int a_byte = 3 * (x0 - R);                 // first byte of the produced span
     const int a0 = a_byte & ~15;
     const int n_chunks = (a_byte - a0 + 12 * C::GROUPS + 15) >> 4;
-    const bool vec_in = Prod::VEC && x0 - R >= 0 && a0 + 16 * n_chunks <= 3 * W && G_RB * n_chunks <= G_THREADS && ((p.io.in_rs & 15) == 0) &&
+    const bool vec_in = Prod::VEC && x0 - R >= 0 && a0 + 16 * n_chunks <= 3 * W && G_RB * n_chunks <= THREADS && ((p.io.in_rs & 15) == 0) &&
                         ((p.io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
 
     const int n_in_rows = (y_end - y_start) + 2 * R;
     const int n_in_blocks = (n_in_rows + G_RB - 1) / G_RB;
 
-    // task coordinates.  H pass: thread -> (channel, row, 8-px group); V pass: thread -> (channel, column)
-    const int ch = tid >> 7;                         // 128 threads per channel
+    // task coordinates.  H pass: thread -> (plane, row, 8-px group); V pass: thread -> (plane, column)
+    const int ch = tid >> 7;                         // 128 threads per plane
     const int h_r = tid & 7, h_xg = (tid & 127) >> 3;
     const int v_x = tid & 127;
     float A[2 * R];                                  // partial sums of the 2R output rows in flight
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) A[i] = 0.f;
 
-    // vector path: one 16-byte chunk of the raw tile per thread (8 rows x <= 33 chunks <= 384 threads)
+    // vector path: one 16-byte chunk of the raw tile per thread (8 rows x <= 32 chunks <= 256 threads)
     const int pf_r = tid / max(n_chunks, 1), pf_q = tid - pf_r * max(n_chunks, 1);
     uint4 pf = make_uint4(0u, 0u, 0u, 0u);
     if (vec_in && tid < G_RB * n_chunks)
@@ -316,7 +327,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
             if (ib + 1 < n_in_blocks && tid < G_RB * n_chunks)
                 pf = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(yb + G_RB + pf_r, H) * p.io.in_rs + a0) + pf_q);
             const int sh = (a_byte - a0) & 3, w_off = (a_byte - a0) >> 2;
-            for (int idx = tid; idx < G_RB * C::GROUPS; idx += G_THREADS) {
+            for (int idx = tid; idx < G_RB * C::GROUPS; idx += THREADS) {
                 const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
                 const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * G_RAW_PITCH) + w_off + 3 * g;
                 uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
@@ -328,14 +339,14 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
                 }
                 float4 c0, c1, c2;
                 prod.decode4(w0, w1, w2, c0, c1, c2);
-                *reinterpret_cast<float4 *>(&S[(0 * G_RB + r) * C::S_PITCH + 4 * g]) = c0;
-                *reinterpret_cast<float4 *>(&S[(1 * G_RB + r) * C::S_PITCH + 4 * g]) = c1;
-                *reinterpret_cast<float4 *>(&S[(2 * G_RB + r) * C::S_PITCH + 4 * g]) = c2;
+                *reinterpret_cast<float4 *>(&S[0 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c0;
+                *reinterpret_cast<float4 *>(&S[1 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c1;
+                if (NCH == 3) *reinterpret_cast<float4 *>(&S[2 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c2;
             }
         } else {
             // pixel-by-pixel producer (image borders, unaligned frames, the cat warp): a task is one
             // column x 4 rows, so per-column state (table loads, tap geometry) is set up once per 4 px
-            for (int idx = tid; idx < 2 * C::IN_W; idx += G_THREADS) {
+            for (int idx = tid; idx < 2 * C::IN_W; idx += THREADS) {
                 const int half = idx / C::IN_W, i = idx - half * C::IN_W;
                 const typename Prod::Column col = prod.column(reflect101(x0 - R + i, W));
 #pragma unroll
@@ -343,9 +354,9 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
                     const int r = half * (G_RB / 2) + rr;
                     float o0, o1, o2;
                     prod.at(col, reflect101(yb + r, H), o0, o1, o2);
-                    S[(0 * G_RB + r) * C::S_PITCH + i] = o0;
-                    S[(1 * G_RB + r) * C::S_PITCH + i] = o1;
-                    S[(2 * G_RB + r) * C::S_PITCH + i] = o2;
+                    S[0 * C::S_PLANE + r * C::S_PITCH + i] = o0;
+                    S[1 * C::S_PLANE + r * C::S_PITCH + i] = o1;
+                    if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + i] = o2;
                 }
             }
         }
@@ -353,7 +364,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 
         // ---- horizontal pass: 8 outputs per thread from a WIN-wide register window
         {
-            const float4 *w4 = reinterpret_cast<const float4 *>(&S[(ch * G_RB + h_r) * C::S_PITCH + h_xg * 8]);
+            const float4 *w4 = reinterpret_cast<const float4 *>(&S[ch * C::S_PLANE + h_r * C::S_PITCH + h_xg * 8]);
             float v[4 * C::NW4];
 #pragma unroll
             for (int q = 0; q < C::NW4; ++q) {
@@ -369,7 +380,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(tk, v[j + k], acc[j]);
             }
-            float4 *d4 = reinterpret_cast<float4 *>(&X[(ch * G_RB + h_r) * C::X_PITCH + h_xg * 8]);
+            float4 *d4 = reinterpret_cast<float4 *>(&X[ch * C::X_PLANE + h_r * C::X_PITCH + h_xg * 8]);
             d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
@@ -378,44 +389,64 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         // ---- vertical pass, one input row at a time: finish the oldest output row, advance the rest.
         // Input row i (0-based in the segment) completes output row y_start + i - 2R.
         {
-            const float *col = X + ch * G_RB * C::X_PITCH + v_x;
+            const float *col = X + ch * C::X_PLANE + v_x;
+            float *ycol = Y + ch * C::X_PLANE + v_x;
 #pragma unroll
             for (int r = 0; r < G_RB; ++r) {
                 const float h = col[r * C::X_PITCH];
-                const float out = fmaf(p.taps[2 * R], h, A[0]);
+                ycol[r * C::X_PITCH] = fmaf(p.taps[2 * R], h, A[0]);
 #pragma unroll
                 for (int m = 0; m < 2 * R - 1; ++m) A[m] = fmaf(p.taps[2 * R - 1 - m], h, A[m + 1]);
                 A[2 * R - 1] = p.taps[0] * h;
-                if (ib * G_RB + r >= 2 * R) stage[r * (G_TW * 3) + v_x * 3 + ch] = (uint8_t)encode_u8(enc, out);
             }
         }
         __syncthreads();
 
-        // ---- store the finished rows of this block: input row i = 8*ib + r -> output row y_start + i - 2R
+        // ---- expand (two-plane mode) + encode + store: a task is 4 consecutive pixels of one row
+        // (12 bytes = three 32-bit stores); input row i = 8*ib + r -> output row y_start + i - 2R
         {
             const int oy0 = y_start + ib * G_RB - 2 * R;
-            if (vec_ok) {
-                constexpr int V_PER_ROW = G_TW * 3 / 16;       // 24 x 16 B per row
-                for (int idx = tid; idx < G_RB * V_PER_ROW; idx += G_THREADS) {
-                    const int r = idx / V_PER_ROW, q = idx - r * V_PER_ROW;
-                    const int oy = oy0 + r;
-                    if (oy >= y_start && oy < y_end) {
-                        const uint4 val = reinterpret_cast<const uint4 *>(stage + r * (G_TW * 3))[q];
-                        *reinterpret_cast<uint4 *>(dst_frame + (int64_t)oy * p.io.out_rs + (int64_t)x0 * 3 + q * 16) = val;
+            for (int t = tid; t < G_RB * (G_TW / 4); t += THREADS) {
+                const int r = t >> 5, g4 = t & 31;
+                const int oy = oy0 + r;
+                if (oy < y_start || oy >= y_end) continue;
+                const int xo = x0 + 4 * g4;
+                if (xo >= W) continue;
+                const float4 a4 = *reinterpret_cast<const float4 *>(&Y[0 * C::X_PLANE + r * C::X_PITCH + 4 * g4]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&Y[1 * C::X_PLANE + r * C::X_PITCH + 4 * g4]);
+                float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NCH == 3) c4 = *reinterpret_cast<const float4 *>(&Y[2 * C::X_PLANE + r * C::X_PITCH + 4 * g4]);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+                uint32_t by[12];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float r0, r1, r2;
+                    if (NCH == 2) {
+                        r0 = fmaf(p.P[1], bv[j], p.P[0] * av[j]);
+                        r1 = fmaf(p.P[3], bv[j], p.P[2] * av[j]);
+                        r2 = fmaf(p.P[5], bv[j], p.P[4] * av[j]);
+                    } else {
+                        r0 = av[j]; r1 = bv[j]; r2 = cv[j];
                     }
+                    by[3 * j] = encode_u8(enc, r0);
+                    by[3 * j + 1] = encode_u8(enc, r1);
+                    by[3 * j + 2] = encode_u8(enc, r2);
                 }
-            } else {
-                const int nbytes = min(G_TW, W - x0) * 3;
-                for (int idx = tid; idx < G_RB * G_TW * 3; idx += G_THREADS) {
-                    const int r = idx / (G_TW * 3), b = idx - r * (G_TW * 3);
-                    const int oy = oy0 + r;
-                    if (oy >= y_start && oy < y_end && b < nbytes)
-                        dst_frame[(int64_t)oy * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[idx];
+                uint8_t *o = dst_frame + (int64_t)oy * p.io.out_rs + (int64_t)xo * 3;
+                if (out4 && xo + 3 < W) {
+                    uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
+                } else {
+                    const int nb = 3 * min(4, W - xo);
+#pragma unroll
+                    for (int q = 0; q < 12; ++q)
+                        if (q < nb) o[q] = (uint8_t)by[q];
                 }
             }
         }
         // hazards: the next produce writes rawt / S (H pass done); X is rewritten after the next
-        // produce barrier (V pass done); stage is rewritten two barriers from here.
+        // produce barrier (V pass done); Y is rewritten after the next H-pass barrier (encode done).
     }
 
     if (p.flags != nullptr && !p.fixup) {
@@ -424,15 +455,15 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     }
 }
 
-template <int R, class Prod>
+template <int R, class Prod, int NCH>
 static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
     using C = GaussCfg<R>;
-    const size_t smem = (size_t)(C::S_FLOATS + C::X_FLOATS + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::STAGE_BYTES + C::RAW_BYTES;
-    auto kern = gauss_stream_kernel<R, Prod>;
+    const size_t smem = (size_t)(NCH * C::S_PLANE + 2 * NCH * C::X_PLANE + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::RAW_BYTES;
+    auto kern = gauss_stream_kernel<R, Prod, NCH>;
     AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
     AVB_TIMED(gc.fixup ? Prod::fixup_name() : Prod::name(), st);
-    kern<<<grid, G_THREADS, smem, st>>>(gc, pp);
+    kern<<<grid, G_THREADS_PER_PLANE * NCH, smem, st>>>(gc, pp);
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }
@@ -441,7 +472,7 @@ static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, 
 // 2*RP halo rows re-produced per segment stay a small fraction
 static int pick_seg_h(int n, int H, int W, int radius) {
     const int strips = (W + G_TW - 1) / G_TW;
-    const long target = 4L * 2 * sm_count();                 // ~4 waves at 2 CTAs/SM
+    const long target = 4L * 3 * sm_count();                 // ~4 waves at 3 CTAs/SM
     long segs = (target + (long)strips * n - 1) / ((long)strips * n);
     const int min_h = 16 * radius;                             // halo rows re-produced per segment <= 12.5 %
     long max_segs = (H + min_h - 1) / min_h;
@@ -452,11 +483,55 @@ static int pick_seg_h(int n, int H, int W, int radius) {
     return seg_h;
 }
 
+// T (3x3, applied as out = T lin) = P (3x2) Q (2x3) if it has rank <= 2: Q = the two most independent
+// rows of T (exact copies), P = the coefficients of every row in that basis (least squares, double).
+// Returns false for a full-rank matrix (residual above float32 rounding of T itself).
+static bool rank2_factor(const float *T, float *Q /*6*/, float *P /*6*/) {
+    double r[3][3];
+    for (int i = 0; i < 9; ++i) r[i / 3][i % 3] = T[i];
+    int bi = 0, bj = 1;
+    double best = -1.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j) {
+            const double cx = r[i][1] * r[j][2] - r[i][2] * r[j][1], cy = r[i][2] * r[j][0] - r[i][0] * r[j][2],
+                         cz = r[i][0] * r[j][1] - r[i][1] * r[j][0];
+            const double n2 = cx * cx + cy * cy + cz * cz;
+            if (n2 > best) { best = n2; bi = i; bj = j; }
+        }
+    const double aa = r[bi][0] * r[bi][0] + r[bi][1] * r[bi][1] + r[bi][2] * r[bi][2];
+    const double bb = r[bj][0] * r[bj][0] + r[bj][1] * r[bj][1] + r[bj][2] * r[bj][2];
+    const double ab = r[bi][0] * r[bj][0] + r[bi][1] * r[bj][1] + r[bi][2] * r[bj][2];
+    const double det = aa * bb - ab * ab;
+    double scale = 0.0;
+    for (int i = 0; i < 9; ++i) scale = std::max(scale, std::fabs((double)T[i]));
+    if (!(det > 1e-12 * scale * scale * scale * scale)) return false;      // rank <= 1: not worth a special case
+    double resid = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double ka = r[k][0] * r[bi][0] + r[k][1] * r[bi][1] + r[k][2] * r[bi][2];
+        const double kb = r[k][0] * r[bj][0] + r[k][1] * r[bj][1] + r[k][2] * r[bj][2];
+        double c0 = (ka * bb - kb * ab) / det, c1 = (kb * aa - ka * ab) / det;
+        if (k == bi) { c0 = 1.0; c1 = 0.0; }
+        if (k == bj) { c0 = 0.0; c1 = 1.0; }
+        P[2 * k] = (float)c0; P[2 * k + 1] = (float)c1;
+        for (int c = 0; c < 3; ++c) resid = std::max(resid, std::fabs(r[k][c] - ((double)P[2 * k] * r[bi][c] + (double)P[2 * k + 1] * r[bj][c])));
+    }
+    for (int c = 0; c < 3; ++c) { Q[c] = T[3 * bi + c]; Q[3 + c] = T[3 * bj + c]; }
+    return resid <= 4e-7 * scale;       // a few float32 ulps of the largest entry: T itself was rounded to float32
+}
+
 template <class Prod>
-static int dispatch_gauss(int radius, GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
+static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp, cudaStream_t st) {
     gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius);
+    float Q[6];
+    const float T[9] = {pp.M.m[0], pp.M.m[1], pp.M.m[2], pp.M.m[3], pp.M.m[4], pp.M.m[5], pp.M.m[6], pp.M.m[7], pp.M.m[8]};
+    const bool two = rank2_factor(T, Q, gc.P);
+    typename Prod::Params q = pp;
+    if (two) {
+        for (int i = 0; i < 6; ++i) q.M.m[i] = Q[i];
+        q.M.m[6] = q.M.m[7] = q.M.m[8] = 0.f;
+    }
     switch (radius) {
-#define AVB_CASE(RR) case RR: return launch_gauss<RR, Prod>(gc, pp, st);
+#define AVB_CASE(RR) case RR: return two ? launch_gauss<RR, Prod, 2>(gc, q, st) : launch_gauss<RR, Prod, 3>(gc, q, st);
         AVB_CASE(1) AVB_CASE(2) AVB_CASE(3) AVB_CASE(4) AVB_CASE(5) AVB_CASE(6) AVB_CASE(7) AVB_CASE(8)
         AVB_CASE(9) AVB_CASE(10) AVB_CASE(11) AVB_CASE(12) AVB_CASE(13) AVB_CASE(14) AVB_CASE(15) AVB_CASE(16)
 #undef AVB_CASE

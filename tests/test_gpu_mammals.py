@@ -105,3 +105,25 @@ def test_host_batch_pipeline_matches_device_path():
         ref = ref if name == "Cat" else (ref[1],)
         for a, b in zip(o, ref):
             assert torch.equal(a, b.cpu()), name
+
+
+def test_full_rank_matrix_takes_three_plane_path():
+    """avb_dichromat_blur_u8 accepts any 3x3; species matrices are rank 2 (two-plane kernel), a
+    generic full-rank matrix must give the same answer through the three-plane instantiation."""
+    import torch
+    from animal_vision_b200 import tables
+    from animal_vision_b200.engine import get_engine
+    from oracle import colorimetry as C
+    from oracle import cvops as V
+    eng = get_engine()
+    T = np.array([[0.8, 0.15, 0.05], [0.1, 0.7, 0.2], [-0.05, 0.25, 0.8]], np.float32)
+    assert abs(np.linalg.det(T.astype(np.float64))) > 0.1
+    for sigma in (0.7, 2.0, 3.5):
+        taps = tables.gaussian_taps(tables.gaussian_ksize(sigma), sigma)
+        for f in (frames.noise(200, 300, 2), frames.natural(200, 300), frames.bars(131, 517)):
+            lin = C.apply_matrix(C.decode_srgb(C.normalize_frame(f)), T)
+            ref = C.encode_tail(V.gaussian_blur(lin, sigma), np.uint8)
+            d_in = torch.from_numpy(f[None]).cuda()
+            d_out = torch.empty_like(d_in)
+            eng.dichromat_blur(d_in, d_out, T, taps)
+            _cmp(d_out[0].cpu().numpy(), ref, f"full-rank sigma={sigma}", max_frac=0.03)
