@@ -36,7 +36,6 @@ constexpr int G_RB = 8;         // rows per block
 constexpr int G_THREADS_PER_PLANE = 128;  // H pass (plane, row, 8-px group); V pass (plane, column)
 constexpr int G_MAX_TAPS = 33;
 constexpr int G_ENC_SMEM = AVB_ENC_TABLE_MAX;  // uint32 words reserved for the encode table
-constexpr int G_RAW_PITCH = 528;               // bytes per row of the raw tile (>= 16 * 33)
 
 constexpr int g_round_pitch(int v) { return (v % 8 == 4) ? v : (v + ((12 - v % 8) % 8)); }
 
@@ -52,7 +51,6 @@ struct GaussCfg {
     static constexpr int X_PITCH = G_TW + 4;
     static constexpr int S_PLANE = G_RB * S_PITCH;                    // floats per plane
     static constexpr int X_PLANE = G_RB * X_PITCH;
-    static constexpr int RAW_BYTES = G_RB * G_RAW_PITCH;
 };
 
 struct GaussCommon {
@@ -75,6 +73,9 @@ struct DogProducer {
     };
     static constexpr int SMEM_FLOATS = 256;
     static constexpr bool VEC = true;      // has a 4-pixel vector path (three packed 32-bit words -> 4 px)
+    static constexpr bool GATHER = false;
+    static constexpr int RAW_PITCH = 528;  // bytes per row of the raw tile: 33 chunks of 16 B
+    static constexpr int PF_N = 1;         // prefetched 16-byte chunks per thread
     const float *lut_s;
     const uint8_t *src;
     int64_t rs;
@@ -114,6 +115,8 @@ struct DogProducer {
         seen |= b0 | b1 | b2;
         px(b0, b1, b2, o0, o1, o2);
     }
+    __device__ __forceinline__ void at_row(const Column &, const uint8_t *, float &, float &, float &) {}
+    __device__ __forceinline__ void span(const Column &, int &, int &, int &) const {}
 };
 
 struct CatProducer {
@@ -128,6 +131,9 @@ struct CatProducer {
     };
     static constexpr int SMEM_FLOATS = 256;
     static constexpr bool VEC = false;
+    static constexpr bool GATHER = true;   // source columns of a strip are staged in shared memory, taps gather from there
+    static constexpr int RAW_PITCH = 928;  // 58 chunks of 16 B: (128 + 2*16) columns x 2.1 source px x 3 B + alignment slack
+    static constexpr int PF_N = 2;
     const float *norm_s;
     const uint8_t *src;
     int64_t rs;
@@ -207,12 +213,21 @@ struct CatProducer {
         // ~5e-7 relative: far inside the 1-LSB budget of the uint8 result)
         return v <= 0.04045f ? v * (1.0f / 12.92f) : exp2f(2.4f * __log2f((v + 0.055f) * (1.0f / 1.055f)));
     }
+    // source-column span this output column touches, and which eye views are live
+    __device__ __forceinline__ void span(const Column &c, int &lo, int &hi, int &mode) const {
+        if (c.wL != 0.0f) { lo = min(lo, c.L.ix); hi = max(hi, c.L.ix + 1); mode |= 1; }
+        if (c.wR != 0.0f) { lo = min(lo, c.R.ix); hi = max(hi, c.R.ix + 1); mode |= 2; }
+        if (c.wL != 0.0f && c.wR != 0.0f) mode |= 4;
+    }
     __device__ __forceinline__ void at(const Column &c, int y, float &o0, float &o1, float &o2) {
+        at_row(c, src + (int64_t)y * rs, o0, o1, o2);
+    }
+    // `row` addresses source column ix at row[3*ix] (a global row, or the shared raw tile rebased)
+    __device__ __forceinline__ void at_row(const Column &c, const uint8_t *row, float &o0, float &o1, float &o2) {
         if (c.wL == 0.0f && c.wR == 0.0f) {     // outside both eye views: (0*wL + 0*wR)/ws = 0 -> decode(0) = 0
             o0 = o1 = o2 = 0.f;
             return;
         }
-        const uint8_t *row = src + (int64_t)y * rs;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         // a zero weight multiplies a finite sample: skipping the gather leaves the sum unchanged
         if (c.wL != 0.0f) gather(row, c.L, l0, l1, l2);
@@ -255,6 +270,8 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     float *prod_smem = Y + NCH * C::X_PLANE;
     uint32_t *enc_s = reinterpret_cast<uint32_t *>(prod_smem + Prod::SMEM_FLOATS);
     uint8_t *rawt = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);               // [RB][RAW_PITCH] packed input rows
+    constexpr int RAW_PITCH = Prod::RAW_PITCH, PF_N = Prod::PF_N;
+    __shared__ int gat[3];                                                          // gather producer: span lo, hi, eye mode
 
     const int frame = blockIdx.z;
     if (p.fixup && p.flags[frame] != 0) return;
@@ -291,13 +308,28 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         return;
     }
 
-    // vector produce: the strip plus its halo (and the over-read of the last 4-pixel group) lies
-    // inside the row, rows are 16-byte aligned
-    const int a_byte = 3 * (x0 - R);                 // first byte of the produced span
-    const int a0 = a_byte & ~15;
-    const int n_chunks = (a_byte - a0 + 12 * C::GROUPS + 15) >> 4;
-    const bool vec_in = Prod::VEC && x0 - R >= 0 && a0 + 16 * n_chunks <= 3 * W && G_RB * n_chunks <= THREADS && ((p.io.in_rs & 15) == 0) &&
-                        ((p.io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
+    // Raw tile: the packed bytes [a0, a0 + 16*n_chunks) of 8 input rows, fetched with 16-byte loads
+    // one block ahead.  LUT producer: the strip plus its halo (and the over-read of the last 4-pixel
+    // group); gather producer: the source columns the strip's taps touch (single live eye view).
+    const bool in16 = ((p.io.in_rs & 15) == 0) && ((p.io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
+    int a_byte = 3 * (x0 - R);                       // first byte of the produced span (LUT producer)
+    int a0 = a_byte & ~15;
+    int n_chunks = (a_byte - a0 + 12 * C::GROUPS + 15) >> 4;
+    bool vec_in = Prod::VEC && x0 - R >= 0 && a0 + 16 * n_chunks <= 3 * W && in16;
+    if (Prod::GATHER) {
+        if (tid == 0) { gat[0] = 0x7fffffff; gat[1] = -1; gat[2] = 0; }
+        __syncthreads();
+        int lo = 0x7fffffff, hi = -1, mode = 0;
+        for (int i = tid; i < C::IN_W; i += THREADS) prod.span(prod.column(reflect101(x0 - R + i, W)), lo, hi, mode);
+        if (mode) { atomicMin(&gat[0], lo); atomicMax(&gat[1], hi); atomicOr(&gat[2], mode); }
+        __syncthreads();
+        const int ixlo = max(gat[0], 0), ixhi = min(gat[1], W - 1);
+        a0 = (3 * ixlo) & ~15;
+        n_chunks = (3 * (ixhi + 1) - a0 + 15) >> 4;
+        vec_in = (gat[2] == 1 || gat[2] == 2) && in16 && n_chunks > 0 && 16 * n_chunks <= RAW_PITCH &&
+                 a0 + 16 * n_chunks <= (int)p.io.in_rs;
+    }
+    vec_in = vec_in && G_RB * n_chunks <= PF_N * THREADS;
 
     const int n_in_rows = (y_end - y_start) + 2 * R;
     const int n_in_blocks = (n_in_rows + G_RB - 1) / G_RB;
@@ -310,11 +342,29 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) A[i] = 0.f;
 
-    // vector path: one 16-byte chunk of the raw tile per thread (8 rows x <= 32 chunks <= 256 threads)
-    const int pf_r = tid / max(n_chunks, 1), pf_q = tid - pf_r * max(n_chunks, 1);
-    uint4 pf = make_uint4(0u, 0u, 0u, 0u);
-    if (vec_in && tid < G_RB * n_chunks)
-        pf = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(y_start - R + pf_r, H) * p.io.in_rs + a0) + pf_q);
+    // raw-tile prefetch registers: chunk c = tid + k*THREADS -> (row c / n_chunks, chunk c % n_chunks)
+    uint4 pf[PF_N];
+    auto raw_fetch = [&](int yb_) {
+#pragma unroll
+        for (int k = 0; k < PF_N; ++k) {
+            const int c = tid + k * THREADS;
+            if (c < G_RB * n_chunks) {
+                const int r = c / n_chunks, q = c - r * n_chunks;
+                pf[k] = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(yb_ + r, H) * p.io.in_rs + a0) + q);
+            }
+        }
+    };
+    auto raw_publish = [&]() {
+#pragma unroll
+        for (int k = 0; k < PF_N; ++k) {
+            const int c = tid + k * THREADS;
+            if (c < G_RB * n_chunks) {
+                const int r = c / n_chunks, q = c - r * n_chunks;
+                reinterpret_cast<uint4 *>(rawt + r * RAW_PITCH)[q] = pf[k];
+            }
+        }
+    };
+    if (vec_in) raw_fetch(y_start - R);
 
     for (int ib = 0; ib < n_in_blocks; ++ib) {
         const int yb = y_start - R + ib * G_RB;      // first input row of this block
@@ -322,26 +372,42 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         if (vec_in) {
             // the packed rows of this block were fetched one block ahead (registers); publish them,
             // then put the next block's loads in flight before any arithmetic
-            if (tid < G_RB * n_chunks) reinterpret_cast<uint4 *>(rawt + pf_r * G_RAW_PITCH)[pf_q] = pf;
+            raw_publish();
             __syncthreads();
-            if (ib + 1 < n_in_blocks && tid < G_RB * n_chunks)
-                pf = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(yb + G_RB + pf_r, H) * p.io.in_rs + a0) + pf_q);
-            const int sh = (a_byte - a0) & 3, w_off = (a_byte - a0) >> 2;
-            for (int idx = tid; idx < G_RB * C::GROUPS; idx += THREADS) {
-                const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * G_RAW_PITCH) + w_off + 3 * g;
-                uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
-                if (sh) {
-                    const uint32_t w3 = q[3];
-                    w0 = __funnelshift_r(w0, w1, 8 * sh);
-                    w1 = __funnelshift_r(w1, w2, 8 * sh);
-                    w2 = __funnelshift_r(w2, w3, 8 * sh);
+            if (ib + 1 < n_in_blocks) raw_fetch(yb + G_RB);
+            if (Prod::GATHER) {
+                // taps gather from the shared raw tile: a task is one column x 4 rows
+                for (int idx = tid; idx < 2 * C::IN_W; idx += THREADS) {
+                    const int half = idx / C::IN_W, i = idx - half * C::IN_W;
+                    const typename Prod::Column col = prod.column(reflect101(x0 - R + i, W));
+#pragma unroll
+                    for (int rr = 0; rr < G_RB / 2; ++rr) {
+                        const int r = half * (G_RB / 2) + rr;
+                        float o0, o1, o2;
+                        prod.at_row(col, rawt + r * RAW_PITCH - a0, o0, o1, o2);
+                        S[0 * C::S_PLANE + r * C::S_PITCH + i] = o0;
+                        S[1 * C::S_PLANE + r * C::S_PITCH + i] = o1;
+                        if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + i] = o2;
+                    }
                 }
-                float4 c0, c1, c2;
-                prod.decode4(w0, w1, w2, c0, c1, c2);
-                *reinterpret_cast<float4 *>(&S[0 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c0;
-                *reinterpret_cast<float4 *>(&S[1 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c1;
-                if (NCH == 3) *reinterpret_cast<float4 *>(&S[2 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c2;
+            } else {
+                const int sh = (a_byte - a0) & 3, w_off = (a_byte - a0) >> 2;
+                for (int idx = tid; idx < G_RB * C::GROUPS; idx += THREADS) {
+                    const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * RAW_PITCH) + w_off + 3 * g;
+                    uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                    if (sh) {
+                        const uint32_t w3 = q[3];
+                        w0 = __funnelshift_r(w0, w1, 8 * sh);
+                        w1 = __funnelshift_r(w1, w2, 8 * sh);
+                        w2 = __funnelshift_r(w2, w3, 8 * sh);
+                    }
+                    float4 c0, c1, c2;
+                    prod.decode4(w0, w1, w2, c0, c1, c2);
+                    *reinterpret_cast<float4 *>(&S[0 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c0;
+                    *reinterpret_cast<float4 *>(&S[1 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c1;
+                    if (NCH == 3) *reinterpret_cast<float4 *>(&S[2 * C::S_PLANE + r * C::S_PITCH + 4 * g]) = c2;
+                }
             }
         } else {
             // pixel-by-pixel producer (image borders, unaligned frames, the cat warp): a task is one
@@ -458,7 +524,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 template <int R, class Prod, int NCH>
 static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
     using C = GaussCfg<R>;
-    const size_t smem = (size_t)(NCH * C::S_PLANE + 2 * NCH * C::X_PLANE + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + C::RAW_BYTES;
+    const size_t smem = (size_t)(NCH * C::S_PLANE + 2 * NCH * C::X_PLANE + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + (size_t)G_RB * Prod::RAW_PITCH;
     auto kern = gauss_stream_kernel<R, Prod, NCH>;
     AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
