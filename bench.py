@@ -44,6 +44,13 @@ FRAMES_PER_GPU = 60
 SPECIES = ("Dog", "Cat", "HoneyBee")
 # algorithmic bytes per pixel (uint8 in + uint8 out(s)); SURVEY.md 8(d)
 ALGO_BYTES_PER_PX = {"Dog": 6, "Cat": 9, "HoneyBee": 6}
+# per KERNEL: bytes it must read + write per output pixel (cat warp: u8 frame in, cat view out; the
+# centre zoom's output belongs to cat_center_zoom), and DRAM bytes per pixel measured once with
+# `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_all_r1e.txt)
+KERNEL_ALGO_BYTES_PER_PX = {"k2_gauss_dichromat": 6.0, "k2_gauss_cat_warp": 6.0, "cat_center_zoom": 3.0 + 3.0 / 2.25,
+                            "k3_uv_map": 6.0, "k3_uv_hist": 3.0, "k3_uv_stats": 3.0, "k3_uv_compact": 8.0, "k2_streak": 6.0}
+KERNEL_NCU_DRAM_BYTES_PER_PX = {"k2_gauss_dichromat": 4.51, "k2_gauss_cat_warp": 4.49, "cat_center_zoom": 2.29,
+                                "k3_uv_map": 4.49, "k3_uv_hist": 9.12, "k3_uv_stats": 3.07, "k3_uv_compact": 8.21}
 KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
                   "k3_uv_stats": "HoneyBee", "k3_uv_hist1": "HoneyBee", "k3_uv_hist2": "HoneyBee",
                   "k3_uv_hist3": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_collect": "HoneyBee", "k3_uv_compact": "HoneyBee",
@@ -352,13 +359,16 @@ def run_b200(args):
     dom = next(iter(shares))
     dom_sp = KERNEL_SPECIES.get(dom, "Dog")
     frames_per_launch = dev_in[dom_sp].shape[0]
-    algo_bytes = ALGO_BYTES_PER_PX[dom_sp] * frames_per_launch * H * W
+    bpp = KERNEL_ALGO_BYTES_PER_PX.get(dom, ALGO_BYTES_PER_PX[dom_sp])
+    algo_bytes = bpp * frames_per_launch * H * W
+    ncu_bpp = KERNEL_NCU_DRAM_BYTES_PER_PX.get(dom)
     peak, peak_src = peak_numbers()
     achieved = algo_bytes / (shares[dom]["ms_per_launch"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": None if ncu_bpp is None else ncu_bpp * frames_per_launch * H * W, "peak_source": peak_src,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per pixel (profiles/r1_ncu_all_r1e.txt), scaled to this launch",
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": f"{ALGO_BYTES_PER_PX[dom_sp]} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
+                "note": f"{bpp:g} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
                 "kernel_shares": shares}
 
     # ---- end to end through the host API: pinned host in -> pinned host out
@@ -432,7 +442,7 @@ def main():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step (multiple of 3)")
-    ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline chunk in the e2e leg")
+    ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the 3840-wide CPU-baseline sample frames")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--mstpp-batch", type=int, default=4, help="482x512 patches per GPU in the MST++ leg (0: skip)")
