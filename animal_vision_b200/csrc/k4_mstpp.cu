@@ -355,33 +355,46 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {   // torch 'reflect' 
     if (i >= n) i = 2 * n - 2 - i;
     return i;
 }
-__global__ void __launch_bounds__(256) conv_in_kernel(const __grid_constant__ ConvInP p) {
-    __shared__ float ws[27 * 32];
+// One thread per output pixel: its 27 inputs (reflect padding of the frame, zero padding of the
+// conv) are gathered once into registers, then all 32 output channels are accumulated from
+// broadcast float4 weight reads; eight 16-byte stores write the pixel's channel vector.
+__global__ void __launch_bounds__(128) conv_in_kernel(const __grid_constant__ ConvInP p) {
+    __shared__ __align__(16) float ws[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = __ldg(p.w + i);
     __syncthreads();
-    const int co = threadIdx.x & 31;
     const long long npx = (long long)p.B * p.Hp * p.Wp;
-    for (long long px = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); px < npx; px += (long long)gridDim.x * 8) {
-        const int x = (int)(px % p.Wp);
-        const long long t = px / p.Wp;
-        const int y = (int)(t % p.Hp), b = (int)(t / p.Hp);
-        float acc = 0.f;
+    const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const int x = (int)(px % p.Wp);
+    const long long t = px / p.Wp;
+    const int y = (int)(t % p.Hp), b = (int)(t / p.Hp);
+    float in[27];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yp = y + ky - 1, xp = x + kx - 1;          // coordinates in the PADDED image
-                if ((unsigned)yp < (unsigned)p.Hp && (unsigned)xp < (unsigned)p.Wp) {   // conv zero padding
-                    const int ys = reflect_idx(yp - p.top, p.H), xs = reflect_idx(xp - p.left, p.W);
-                    const long long o = (((long long)b * p.H + ys) * p.W + xs) * 3;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yp = y + ky - 1, xp = x + kx - 1;          // coordinates in the PADDED image
+            const bool inside = (unsigned)yp < (unsigned)p.Hp && (unsigned)xp < (unsigned)p.Wp;   // conv zero padding
+            const int ys = reflect_idx(yp - p.top, p.H), xs = reflect_idx(xp - p.left, p.W);
+            const long long o = (((long long)b * p.H + min(max(ys, 0), p.H - 1)) * p.W + min(max(xs, 0), p.W - 1)) * 3;
 #pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) {
-                        const float v = p.in_u8 ? __fdiv_rn((float)((const uint8_t *)p.in)[o + ci], 255.0f) : ((const float *)p.in)[o + ci];
-                        acc = fmaf(v, ws[((ky * 3 + kx) * 3 + ci) * 32 + co], acc);
-                    }
-                }
+            for (int ci = 0; ci < 3; ++ci) {
+                float v = 0.f;
+                if (inside) v = p.in_u8 ? __fdiv_rn((float)((const uint8_t *)p.in)[o + ci], 255.0f) : ((const float *)p.in)[o + ci];
+                in[(ky * 3 + kx) * 3 + ci] = v;
             }
-        p.out[px * 32 + co] = acc;      // co == 31 has zero weights -> padded channel stays 0
+        }
+    float *dst = p.out + px * 32;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const float4 w = *reinterpret_cast<const float4 *>(&ws[k * 32 + 4 * c4]);
+            acc.x = fmaf(in[k], w.x, acc.x); acc.y = fmaf(in[k], w.y, acc.y);
+            acc.z = fmaf(in[k], w.z, acc.z); acc.w = fmaf(in[k], w.w, acc.w);
+        }
+        reinterpret_cast<float4 *>(dst)[c4] = acc;      // channel 31 has zero weights -> padded channel stays 0
     }
 }
 
@@ -1109,9 +1122,8 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
     {
         ConvInP p{in, in_is_u8, ws.x0, M->conv_in, n, H, W, Hp, Wp, top, left};
         const long long npx = (long long)n * Hp * Wp;
-        const int blocks = (int)std::min<long long>((npx + 7) / 8, (long long)sm_count() * 16);
         AVB_TIMED("k4_conv_in", cx.st);
-        conv_in_kernel<<<blocks, 256, 0, cx.st>>>(p);
+        conv_in_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, cx.st>>>(p);
     }
     const float *hin = ws.x0;
     float *pp[2] = {ws.hA, ws.hB};
