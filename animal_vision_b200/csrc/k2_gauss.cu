@@ -682,8 +682,18 @@ __global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *
 // Centre zoom (cat_widevision_utils.py:11-29): crop + cv2.resize(INTER_LINEAR) on uint8, restated
 // in OpenCV's 11-bit fixed point so the result is bit-exact.  tab = W x int4 {xi0, xi1, xw0, xw1}
 // then H x int4 {yi0, yi1, yw0, yw1} (source indices already include the crop origin).
-// One thread = 4 consecutive output pixels of a row (12 bytes = three 32-bit stores).
-__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab, int aligned_out) {
+// One thread = 4 consecutive output pixels of a row (12 bytes = three 32-bit stores).  The two
+// horizontal taps of a pixel are adjacent source pixels (xi1 = xi0 + 1, or xi1 = xi0 with weight 0
+// at the right edge), i.e. 6 contiguous bytes: the aligned path fetches them as three 32-bit words
+// per source row and realigns with funnel shifts instead of issuing six byte loads.
+__device__ __forceinline__ void zoom_taps(const uint32_t *row32, int xi0, int last_word, uint32_t (&a)[3], uint32_t (&b)[3]) {
+    const int ob = 3 * xi0, wi = ob >> 2, sh = (ob & 3) * 8;
+    const uint32_t w0 = __ldg(row32 + wi), w1 = __ldg(row32 + min(wi + 1, last_word)), w2 = __ldg(row32 + min(wi + 2, last_word));
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    a[0] = lo & 0xffu; a[1] = (lo >> 8) & 0xffu; a[2] = (lo >> 16) & 0xffu;       // pixel xi0
+    b[0] = lo >> 24; b[1] = hi & 0xffu; b[2] = (hi >> 8) & 0xffu;                  // pixel xi0 + 1
+}
+__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab, int aligned_out, int aligned_in) {
     const int W = io.W;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
@@ -691,17 +701,29 @@ __global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int3
     const int4 ty = __ldg(reinterpret_cast<const int4 *>(tab) + W + y);
     const uint8_t *src = io.in + (int64_t)blockIdx.z * io.in_fs;
     const uint8_t *r0 = src + (int64_t)ty.x * io.in_rs, *r1 = src + (int64_t)ty.y * io.in_rs;
+    const int last_word = (3 * W - 1) >> 2;
     uint32_t by[12];
     const int npx = min(4, W - x4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (j < npx) {
             const int4 tx = __ldg(reinterpret_cast<const int4 *>(tab) + x4 + j);
-            const uint8_t *a0 = r0 + 3 * tx.x, *a1 = r0 + 3 * tx.y, *b0 = r1 + 3 * tx.x, *b1 = r1 + 3 * tx.y;
+            uint32_t a0[3], a1[3], b0[3], b1[3];
+            if (aligned_in) {
+                zoom_taps(reinterpret_cast<const uint32_t *>(r0), tx.x, last_word, a0, a1);
+                zoom_taps(reinterpret_cast<const uint32_t *>(r1), tx.x, last_word, b0, b1);
+                // (xi1 == xi0 only where its weight is 0: the neighbour's bytes then multiply 0)
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a0[c] = r0[3 * tx.x + c]; a1[c] = r0[3 * tx.y + c];
+                    b0[c] = r1[3 * tx.x + c]; b1[c] = r1[3 * tx.y + c];
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const int s0 = a0[c] * tx.z + a1[c] * tx.w;
-                const int s1 = b0[c] * tx.z + b1[c] * tx.w;
+                const int s0 = (int)a0[c] * tx.z + (int)a1[c] * tx.w;
+                const int s1 = (int)b0[c] * tx.z + (int)b1[c] * tx.w;
                 const int v = ((((ty.z * (s0 >> 4)) >> 16) + ((ty.w * (s1 >> 4)) >> 16) + 2) >> 2);
                 by[3 * j + c] = (uint32_t)min(255, max(0, v));
             }
@@ -753,7 +775,8 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
         dim3 grid((W + 1023) / 1024, H, n);
         const int aligned_out = ((reinterpret_cast<uintptr_t>(out_human) | (uintptr_t)human_frame_stride | (uintptr_t)human_row_stride) & 3) == 0;
         AVB_TIMED("cat_center_zoom", st);
-        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev, aligned_out);
+        const int aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_frame_stride | (uintptr_t)in_row_stride) & 3) == 0;
+        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev, aligned_out, aligned_in);
         AVB_CUDA_OK(cudaGetLastError());
     }
     for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];
