@@ -115,6 +115,7 @@ struct DogProducer {
         seen |= b0 | b1 | b2;
         px(b0, b1, b2, o0, o1, o2);
     }
+    template <bool WORDS>
     __device__ __forceinline__ void at_row(const Column &, const uint8_t *, float &, float &, float &) {}
     __device__ __forceinline__ void span(const Column &, int &, int &, int &) const {}
 };
@@ -132,7 +133,7 @@ struct CatProducer {
     static constexpr int SMEM_FLOATS = 256;
     static constexpr bool VEC = false;
     static constexpr bool GATHER = true;   // source columns of a strip are staged in shared memory, taps gather from there
-    static constexpr int RAW_PITCH = 928;  // 58 chunks of 16 B: (128 + 2*16) columns x 2.1 source px x 3 B + alignment slack
+    static constexpr int RAW_PITCH = 960;  // 16 B slack + 58 chunks of 16 B + slack: (128 + 2*16) columns x 2.1 source px x 3 B + alignment slack
     static constexpr int PF_N = 2;
     const float *norm_s;
     const uint8_t *src;
@@ -208,6 +209,23 @@ struct CatProducer {
         c1 = __fadd_rn(__fmul_rn(a1, t.w0), __fmul_rn(b1, t.f));
         c2 = __fadd_rn(__fmul_rn(a2, t.w0), __fmul_rn(b2, t.f));
     }
+    // same taps from a 4-byte aligned row (the shared raw tile): the two source pixels are 6
+    // contiguous bytes = three 32-bit loads + two funnel shifts instead of six byte loads.  Out of
+    // image taps (border constant 0) are masked after the fact; the tile has slack on both sides.
+    __device__ __forceinline__ void gather_words(const uint8_t *row, const Tap &t, float &c0, float &c1, float &c2) {
+        const int ob = 3 * t.ix;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (ob & ~3));
+        const int sh = (ob & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        float a0 = norm_s[lo & 0xffu], a1 = norm_s[(lo >> 8) & 0xffu], a2 = norm_s[(lo >> 16) & 0xffu];
+        float b0 = norm_s[lo >> 24], b1 = norm_s[hi & 0xffu], b2 = norm_s[(hi >> 8) & 0xffu];
+        if (!t.ok0) { a0 = a1 = a2 = 0.f; }
+        if (!t.ok1) { b0 = b1 = b2 = 0.f; }
+        c0 = __fadd_rn(__fmul_rn(a0, t.w0), __fmul_rn(b0, t.f));
+        c1 = __fadd_rn(__fmul_rn(a1, t.w0), __fmul_rn(b1, t.f));
+        c2 = __fadd_rn(__fmul_rn(a2, t.w0), __fmul_rn(b2, t.f));
+    }
     static __device__ __forceinline__ float decode(float v) {
         // animals/animal_utils.py:5-11 on float32; the power goes through the SFU (ex2(2.4 lg2 x),
         // ~5e-7 relative: far inside the 1-LSB budget of the uint8 result)
@@ -220,9 +238,11 @@ struct CatProducer {
         if (c.wL != 0.0f && c.wR != 0.0f) mode |= 4;
     }
     __device__ __forceinline__ void at(const Column &c, int y, float &o0, float &o1, float &o2) {
-        at_row(c, src + (int64_t)y * rs, o0, o1, o2);
+        at_row<false>(c, src + (int64_t)y * rs, o0, o1, o2);
     }
-    // `row` addresses source column ix at row[3*ix] (a global row, or the shared raw tile rebased)
+    // `row` addresses source column ix at row[3*ix] (a global row, or the shared raw tile rebased;
+    // WORDS: the row is 4-byte aligned and readable a few bytes past either end of the span)
+    template <bool WORDS>
     __device__ __forceinline__ void at_row(const Column &c, const uint8_t *row, float &o0, float &o1, float &o2) {
         if (c.wL == 0.0f && c.wR == 0.0f) {     // outside both eye views: (0*wL + 0*wR)/ws = 0 -> decode(0) = 0
             o0 = o1 = o2 = 0.f;
@@ -230,8 +250,13 @@ struct CatProducer {
         }
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         // a zero weight multiplies a finite sample: skipping the gather leaves the sum unchanged
-        if (c.wL != 0.0f) gather(row, c.L, l0, l1, l2);
-        if (c.wR != 0.0f) gather(row, c.R, r0, r1, r2);
+        if (WORDS) {
+            if (c.wL != 0.0f) gather_words(row, c.L, l0, l1, l2);
+            if (c.wR != 0.0f) gather_words(row, c.R, r0, r1, r2);
+        } else {
+            if (c.wL != 0.0f) gather(row, c.L, l0, l1, l2);
+            if (c.wR != 0.0f) gather(row, c.R, r0, r1, r2);
+        }
         // (left*wL + right*wR) / (wL + wR + 1e-8), the quotient correctly rounded from the
         // per-column reciprocal (one Newton step on the quotient)
         const float n0 = __fadd_rn(__fmul_rn(l0, c.wL), __fmul_rn(r0, c.wR));
@@ -326,7 +351,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         const int ixlo = max(gat[0], 0), ixhi = min(gat[1], W - 1);
         a0 = (3 * ixlo) & ~15;
         n_chunks = (3 * (ixhi + 1) - a0 + 15) >> 4;
-        vec_in = (gat[2] == 1 || gat[2] == 2) && in16 && n_chunks > 0 && 16 * n_chunks <= RAW_PITCH &&
+        vec_in = (gat[2] == 1 || gat[2] == 2) && in16 && n_chunks > 0 && 16 * n_chunks + 32 <= RAW_PITCH &&
                  a0 + 16 * n_chunks <= (int)p.io.in_rs;
     }
     vec_in = vec_in && G_RB * n_chunks <= PF_N * THREADS;
@@ -360,7 +385,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
             const int c = tid + k * THREADS;
             if (c < G_RB * n_chunks) {
                 const int r = c / n_chunks, q = c - r * n_chunks;
-                reinterpret_cast<uint4 *>(rawt + r * RAW_PITCH)[q] = pf[k];
+                reinterpret_cast<uint4 *>(rawt + (Prod::GATHER ? 16 : 0) + r * RAW_PITCH)[q] = pf[k];
             }
         }
     };
@@ -384,7 +409,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
                     for (int rr = 0; rr < G_RB / 2; ++rr) {
                         const int r = half * (G_RB / 2) + rr;
                         float o0, o1, o2;
-                        prod.at_row(col, rawt + r * RAW_PITCH - a0, o0, o1, o2);
+                        prod.template at_row<true>(col, rawt + 16 + r * RAW_PITCH - a0, o0, o1, o2);
                         S[0 * C::S_PLANE + r * C::S_PITCH + i] = o0;
                         S[1 * C::S_PLANE + r * C::S_PITCH + i] = o1;
                         if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + i] = o2;
