@@ -229,7 +229,12 @@ struct CatProducer {
     static __device__ __forceinline__ float decode(float v) {
         // animals/animal_utils.py:5-11 on float32; the power goes through the SFU (ex2(2.4 lg2 x),
         // ~5e-7 relative: far inside the 1-LSB budget of the uint8 result)
-        return v <= 0.04045f ? v * (1.0f / 12.92f) : exp2f(2.4f * __log2f((v + 0.055f) * (1.0f / 1.055f)));
+        // (arguments stay in [0.09, 1] and exponents in [-8.4, 0]: the .ftz SFU forms are exact enough
+        // and need no denormal scaling code around them)
+        float l, e;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((v + 0.055f) * (1.0f / 1.055f)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(2.4f * l));
+        return v <= 0.04045f ? v * (1.0f / 12.92f) : e;
     }
     // source-column span this output column touches, and which eye views are live
     __device__ __forceinline__ void span(const Column &c, int &lo, int &hi, int &mode) const {
