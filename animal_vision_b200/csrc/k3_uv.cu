@@ -285,13 +285,25 @@ __device__ __forceinline__ void strip_of(const UvParams &p, int task, int &xs, i
     rows = min(UV_RH, p.io.H - ys);
 }
 
+// sqrt on the SFU (rsq + multiply, ~1 ulp): the opponent radius only feeds a percentile that is
+// computed from the very same values and a saturation ratio, both insensitive at the 1e-7 level.
+__device__ __forceinline__ float sqrt_sfu(float x) {
+#ifdef UV_SQRT_RN
+    return __fsqrt_rn(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
 // ------------------------------------------------------------------ mapper quantities
 template <int QS>
 __device__ __forceinline__ void quantities(const float (&c)[3], float (&q)[UV_NH]) {
     if (QS == QS_OPP) {
         // uv_mappers.py:55-60
         const float O1 = c[2] - c[1], O2 = c[1] - c[0];
-        q[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        q[0] = sqrt_sfu(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
         q[1] = div_by(__fadd_rn(__fadd_rn(c[0], c[1]), c[2]), 3.0f, 0.333333343267440796f);
         q[2] = 0.f;
     } else {
@@ -743,7 +755,7 @@ __device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &
         const float U = c[0], B = c[1], G = c[2];
         const float O1 = G - B, O2 = B - U;
         const float L = div_by(__fadd_rn(__fadd_rn(U, B), G), 3.0f, 0.333333343267440796f);
-        const float radius = __fsqrt_rn(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        const float radius = sqrt_sfu(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
         const float PI_F = 3.14159274101257324f;          // float32(np.pi)
                 const float hue = div_by(__fadd_rn(atan2_fast(O2, O1), PI_F), 6.28318548202514648f, 0.159154936671257019f);
         const float sat = __saturatef(div_by(radius, k.pr, k.rpr));
@@ -751,8 +763,8 @@ __device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &
         const float h6 = __fmul_rn(hue, 6.0f);
         const float fl = floorf(h6);
         const float f = h6 - fl;                           // exact
-        int sext = (int)fl % 6;
-        if (sext < 0) sext += 6;
+        int sext = (int)fl;                                // hue in [0,1] -> fl in {0..6}; 6 wraps to 0 (i % 6)
+        sext = sext >= 6 ? sext - 6 : (sext < 0 ? 0 : sext);
         // NumPy evaluates q and t in float64 (f = h*6 - int32 promotes) and rounds once; one fused
         // multiply-add keeps the float32 evaluation within an ulp of that
         const float pp = __fmul_rn(val, __fsub_rn(1.0f, sat));

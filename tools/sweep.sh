@@ -1,4 +1,3 @@
 #!/bin/bash
-for v in "" "-DPW_CTAS=3" "-DPW_CTAS=10"; do
-  echo "variant: $v"; AVB_NVCC_EXTRA="$v" timeout 200 python tools/mstpp_bench.py 1 482 512 --check 2>&1 | grep -E "MST|gemm|parity"
-done
+python -m pytest tests/test_gpu_honeybee.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -2
+for v in "" "-DUV_SQRT_RN"; do AVB_NVCC_EXTRA="$v" python tools/bee_kernels.py HoneyBee 2>&1 | tail -1; done
