@@ -1,0 +1,96 @@
+"""Spatial tiling of one frame over ranks (animal_vision_b200/tiling.py): halo exchange over a
+world_size-2 gloo group on CPU, and -- on the GPU -- that band + halo through the ordinary kernel
+reproduces the whole-frame result bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from animal_vision_b200 import tiling
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _frame(H, W):
+    return torch.from_numpy(np.random.default_rng(5).integers(0, 256, (1, H, W, 3), dtype=np.uint8))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W, radius = 37, 11, 4
+        frame = _frame(H, W)
+        y0, y1 = tiling.band_rows(H, rank, world)
+        ext, top, bot = tiling.exchange_halos(frame[:, y0:y1].contiguous(), radius, rank, world)
+        lo, hi = max(0, y0 - radius), min(H, y1 + radius)
+        ok = bool(torch.equal(ext, frame[:, lo:hi])) and top == y0 - lo and bot == hi - y1
+        dark = torch.zeros(1, y1 - y0, W, 3, dtype=torch.uint8)
+        if rank == 1:
+            dark[0, 0, 0, 0] = 7                       # only one rank sees a value > 1
+        q.put((rank, ok, tiling.frame_divides_by_255(dark), tiling.frame_divides_by_255(dark * 0 + 1)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_world_size_2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), "extended band != frame rows [y0-r, y1+r)"
+    assert all(r[2] is True for r in res), "the max > 1 branch must be agreed on by all ranks"
+    assert all(r[3] is False for r in res)
+
+
+def test_band_rows_and_radius():
+    import animal_vision_b200.animals as A
+    assert [tiling.band_rows(4320, r, 8) for r in (0, 7)] == [(0, 540), (3780, 4320)]
+    assert tiling.halo_radius(A.Dog()) == 14 and tiling.halo_radius(A.Squirrel()) == 3
+    assert tiling.halo_radius(A.Cow()) == 0 and tiling.halo_radius(A.HoneyBee()) == 0
+    with pytest.raises(tiling.AvbError):
+        tiling.exchange_halos(torch.zeros(1, 3, 8, 3, dtype=torch.uint8), 4, 0, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Dog", "Bear", "Squirrel"])
+def test_band_plus_halo_equals_whole_frame(name):
+    """What visualize_band computes on each rank, emulated in one process: attach the neighbour rows,
+    run the kernel, keep the band.  Must equal the whole-frame output exactly."""
+    import animal_vision_b200.animals as A
+    from animal_vision_b200 import tables
+    from animal_vision_b200._abi import AVB_NORM_DIV255
+    from animal_vision_b200.engine import get_engine
+    sp = getattr(A, name)()
+    H, W, world = 203, 160, 3
+    frame = _frame(H, W).cuda()
+    _, whole = sp.visualize_batch(frame)
+    eng = get_engine(frame.device)
+    radius = tiling.halo_radius(sp)
+    taps = tables.gaussian_taps(tables.gaussian_ksize(sp.SIGMA), sp.SIGMA)
+    for rank in range(world):
+        y0, y1 = tiling.band_rows(H, rank, world)
+        lo, hi = max(0, y0 - radius), min(H, y1 + radius)
+        ext = frame[:, lo:hi].contiguous()
+        out = torch.empty_like(ext)
+        eng.dichromat_blur(ext, out, sp._matrix(), taps, norm=AVB_NORM_DIV255)
+        assert torch.equal(out[:, y0 - lo:y0 - lo + (y1 - y0)], whole[:, y0:y1]), (name, rank)
+    # world == 1 goes through the public entry point
+    assert torch.equal(tiling.visualize_band(sp, frame, H, 0, 1), whole)
