@@ -52,6 +52,26 @@ __device__ __forceinline__ float gelu(float x) {
     return 0.5f * x * (1.0f + er);
 }
 
+// ------------------------------------------------------------------------------------ programmatic dependent launch
+// The forward is a chain of ~160 short dependent kernels.  Every kernel starts with pdl_wait() --
+// griddepcontrol.wait: the preceding kernel has completed and its writes are visible -- and is
+// launched with programmatic stream serialization, so its launch latency and CTA ramp-up overlap
+// the tail of its predecessor instead of adding to it.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename P>
+static void launch_pdl(void (*kern)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P &p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 // ------------------------------------------------------------------------------------ implicit GEMM
 constexpr int BM = 128, BK = 32;
 constexpr int GEMM_THREADS = 256;
@@ -74,6 +94,8 @@ struct GemmP {
     void *out; int ldo; int out_bf16;
     int out_mode;
     int Hreal, Wreal, Cpo, crop_top, crop_left;   // OUT_CONVT: Cpo; OUT_CROP: real size + crop origin
+    float *zero_ptr; int zero_n;                  // pointwise pipeline only: block (0,0,0) clears this buffer (attention statistics)
+    const float *ln_g, *ln_b; int ln_c;           // pointwise pipeline only: LayerNorm over the ln_c real channels of the fp32 A rows
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -137,8 +159,96 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Epilogue of one 128 x BN accumulator tile: warp w owns TMEM lanes 32*(w%4).. (rows) and column half
+// w/4; bias, GELU, fp32 / bf16 residuals and the three store modes are fused here.
+enum { EPI_BIAS = 1, EPI_GELU = 2, EPI_RES1 = 4, EPI_RES2 = 8, EPI_OUTBF16 = 16, EPI_CONVT = 32, EPI_RUNTIME = -1 };
+// flag word of a parameter block (what a compile-time EPI must equal for the specialised kernels)
+static inline int epi_of(const GemmP &p) {
+    return (p.bias ? EPI_BIAS : 0) | (p.gelu ? EPI_GELU : 0) | (p.res1 ? EPI_RES1 : 0) | (p.res2 ? EPI_RES2 : 0) |
+           (p.out_bf16 ? EPI_OUTBF16 : 0) | (p.out_mode == OUT_CONVT ? EPI_CONVT : 0);
+}
+
+// PRE: the residual rows were prefetched into registers by the caller (pre1: fp32, BN/8 vectors per
+// thread; pre2: bf16, BN/16 vectors) instead of being loaded -- and waited for -- inside the epilogue.
+template <int BN, int EPI, bool PRE = false>
+__device__ __forceinline__ void epilogue_tile(const GemmP &p, uint32_t tmem_d, int b, int m_base, int n_base, int warp, int lane,
+                                              const uint4 *pre1 = nullptr, const uint4 *pre2 = nullptr) {
+    constexpr bool RT = EPI == EPI_RUNTIME;
+    const bool has_bias = RT ? p.bias != nullptr : (EPI & EPI_BIAS) != 0, has_gelu = RT ? p.gelu != 0 : (EPI & EPI_GELU) != 0;
+    const bool has_res1 = RT ? p.res1 != nullptr : (EPI & EPI_RES1) != 0, has_res2 = RT ? p.res2 != nullptr : (EPI & EPI_RES2) != 0;
+    const bool out_bf16 = RT ? p.out_bf16 != 0 : (EPI & EPI_OUTBF16) != 0;
+    const int out_mode = RT ? p.out_mode : ((EPI & EPI_CONVT) ? OUT_CONVT : OUT_ROWS);
+    constexpr int HALF = BN / 2;
+    const int m = m_base + 32 * (warp & 3) + lane;
+    const int col0 = (warp >> 2) * HALF;
+    const long long row = (long long)b * p.rows + m;
+    long long obase = 0;
+    int cy = 0, cx = 0;
+    bool crop_ok = true;
+    if (out_mode == OUT_ROWS) obase = row * p.ldo;
+    else { cy = m / p.Wo; cx = m - cy * p.Wo; }
+    if (out_mode == OUT_CROP) {
+        cy -= p.crop_top; cx -= p.crop_left;
+        crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
+        obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
+    }
+#pragma unroll (PRE ? 4 : 1)
+    for (int c = 0; c < HALF; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col0 + c), v);     // all lanes: .sync.aligned
+        if (m < p.rows) {
+            const int n0 = n_base + col0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (has_bias) v[i] += __ldg(p.bias + n0 + i);
+                if (has_gelu) v[i] = gelu(v[i]);
+            }
+            if (has_res1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 r = PRE ? *reinterpret_cast<const float4 *>(&pre1[(c + i) / 4])
+                                         : *reinterpret_cast<const float4 *>(p.res1 + row * p.ldr1 + n0 + i);
+                    v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                }
+            }
+            if (has_res2) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    const uint4 raw = PRE ? pre2[(c + i) / 8] : *reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0 + i);
+                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { v[i + 2 * q] += __low2float(h2[q]); v[i + 2 * q + 1] += __high2float(h2[q]); }
+                }
+            }
+            if (out_mode == OUT_ROWS) {
+                if (out_bf16) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8)
+                        *reinterpret_cast<uint4 *>((bf16 *)p.out + obase + n0 + i) =
+                            make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4 *>((float *)p.out + obase + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            } else if (out_mode == OUT_CONVT) {
+                const int q = n0 / p.Cpo, co = n0 - q * p.Cpo;       // 16-column groups never straddle a (dy,dx) block
+                const long long o = ((((long long)b * 2 * p.Ho) + 2 * cy + (q >> 1)) * (2 * p.Wo) + 2 * cx + (q & 1)) * p.ldo + co;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4 *>((float *)p.out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else if (crop_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + i < NF) ((float *)p.out)[obase + n0 + i] = v[i];
+            }
+        }
+    }
+}
+
 template <int BN, bool A_BF16, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmP p) {
+    pdl_wait();
     constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;        // bytes between k-chunks of 8
     constexpr int A_STAGE = (BK / 8) * A_LBO, B_STAGE = (BK / 8) * B_LBO;
     constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));     // power of two >= BN
@@ -266,71 +376,193 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     mbar_wait(&mbar[(nk - 1) & 1], (uint32_t)(((nk - 1) >> 1) & 1));
     tc_fence_after();
 
-    // ---- epilogue: warp w owns TMEM lanes 32*(w%4).. (rows) and column half w/4
-    constexpr int HALF = BN / 2;
-    const int m = m_base + 32 * (warp & 3) + lane;
-    const int col0 = (warp >> 2) * HALF;
-    const long long row = (long long)b * p.rows + m;
-    long long obase = 0;
-    int cy = 0, cx = 0;
-    bool crop_ok = true;
-    if (p.out_mode == OUT_ROWS) obase = row * p.ldo;
-    else { cy = m / p.Wo; cx = m - cy * p.Wo; }
-    if (p.out_mode == OUT_CROP) {
-        cy -= p.crop_top; cx -= p.crop_left;
-        crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
-        obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
+    epilogue_tile<BN, EPI_RUNTIME>(p, tmem_d, b, m_base, n_base, warp, lane);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
-#pragma unroll 1
-    for (int c = 0; c < HALF; c += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col0 + c), v);     // all lanes: .sync.aligned
-        if (m < p.rows) {
-            const int n0 = n_base + col0 + c;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (p.bias) v[i] += __ldg(p.bias + n0 + i);
-                if (p.gelu) v[i] = gelu(v[i]);
-            }
-            if (p.res1) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 r = *reinterpret_cast<const float4 *>(p.res1 + row * p.ldr1 + n0 + i);
-                    v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-                }
-            }
-            if (p.res2) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                    const uint4 raw = *reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0 + i);
-                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { v[i + 2 * q] += __low2float(h2[q]); v[i + 2 * q + 1] += __high2float(h2[q]); }
-                }
-            }
-            if (p.out_mode == OUT_ROWS) {
-                if (p.out_bf16) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 8)
-                        *reinterpret_cast<uint4 *>((bf16 *)p.out + obase + n0 + i) =
-                            make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4 *>((float *)p.out + obase + n0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
-            } else if (p.out_mode == OUT_CONVT) {
-                const int q = n0 / p.Cpo, co = n0 - q * p.Cpo;       // 16-column groups never straddle a (dy,dx) block
-                const long long o = ((((long long)b * 2 * p.Ho) + 2 * cy + (q >> 1)) * (2 * p.Wo) + 2 * cx + (q & 1)) * p.ldo + co;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4 *>((float *)p.out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else if (crop_ok) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (n0 + i < NF) ((float *)p.out)[obase + n0 + i] = v[i];
+}
+
+// ------------------------------------------------------------------------------------ pointwise pipeline
+// Pointwise GEMMs (q|k|v, attention projection, FFN in / out, transposed conv, skip fusion) with
+// K <= 128: the CTA keeps its weight tile resident in shared memory and walks over a strided
+// sequence of 128-row tiles as a software pipeline --
+//     global loads of tile i+2 (registers)  ||  tcgen05.mma of tile i+1 (TMEM buffer (i+1)&1)  ||  epilogue of tile i
+// -- so neither the HBM/L2 latency of the A rows nor the tensor-core latency is exposed, and one
+// __syncthreads per tile is all the CTA-wide synchronisation there is.  The whole K extent of a
+// tile sits in one shared-memory stage (two stages), the accumulator is double buffered in TMEM.
+// Optional fused LayerNorm (PreNorm in front of the FFN, MST_Plus_Plus.py:57-65): the two loader
+// threads of a row hold all its channels, so mean / variance are one shuffle away and the
+// normalised bf16 row goes straight into the operand tile -- no LayerNorm launch, no bf16 copy of x.
+template <int BN, int KP, bool A_BF16, bool LN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_pw_kernel(const __grid_constant__ GemmP p) {
+    pdl_wait();
+    static_assert(!(LN && A_BF16), "LayerNorm is fused on the fp32 residual stream");
+    constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;
+    constexpr int A_STAGE = (KP / 8) * A_LBO, B_BYTES = (KP / 8) * B_LBO;
+    constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    constexpr int BUF1 = TMEM_COLS / 2;                       // column offset of the second accumulator
+    constexpr int CPT = KP / 2;                               // channels per loader thread (two threads per row)
+    constexpr int NV = A_BF16 ? CPT / 8 : CPT / 4;            // 16-byte vectors per loader thread
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *As = dsm;                                        // [2][A_STAGE]
+    uint8_t *Bs = dsm + 2 * A_STAGE;                          // [B_BYTES]
+    float *ln_s = reinterpret_cast<float *>(dsm + 2 * A_STAGE + B_BYTES);      // gamma[KP] | beta[KP]
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, n_base = blockIdx.y * BN;
+    const int m_tiles = (p.rows + BM - 1) / BM;
+    const int n_my = ((int)blockIdx.x < m_tiles) ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.zero_ptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = tid; i < p.zero_n; i += GEMM_THREADS) p.zero_ptr[i] = 0.f;
+    {   // resident weight tile: BN rows x KP, canonical K-major
+        const bf16 *Wb = p.W + (long long)b * p.w_bstride;
+        for (int idx = tid; idx < BN * (KP / 8); idx += GEMM_THREADS) {
+            const int n = idx / (KP / 8), q = idx - n * (KP / 8);
+            *reinterpret_cast<uint4 *>(Bs + q * B_LBO + (n >> 3) * 128 + (n & 7) * 16) =
+                __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K) + q);
+        }
+        if (LN) {
+            for (int i = tid; i < KP; i += GEMM_THREADS) {
+                ln_s[i] = i < p.ln_c ? __ldg(p.ln_g + i) : 0.f;
+                ln_s[KP + i] = i < p.ln_c ? __ldg(p.ln_b + i) : 0.f;
             }
         }
+    }
+
+    // ---- A loader: thread -> (row, half of the K extent); a two-source GEMM (cat([up, skip])) takes
+    // half 0 from A1 and half 1 from A2
+    const int lr = tid >> 1, lh = tid & 1;
+    const bool two = p.K1 < p.K;
+    const uint8_t *abase = static_cast<const uint8_t *>((two && lh) ? p.A2 : p.A1);
+    const long long a_ld = (two && lh) ? p.lda2 : p.lda1;
+    const int a_c0 = two ? 0 : lh * CPT;
+    uint4 areg[NV];
+    auto a_fetch = [&](int tile) {
+        const int lm = tile * BM + lr;
+        if (lm < p.rows) {
+            const long long off = ((long long)b * p.rows + lm) * a_ld + a_c0;
+            const uint4 *q = reinterpret_cast<const uint4 *>(abase + off * (A_BF16 ? 2 : 4));
+#pragma unroll
+            for (int i = 0; i < NV; ++i) areg[i] = __ldg(q + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) areg[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    auto a_store = [&](int st) {
+        uint8_t *d = As + st * A_STAGE + (lh * (CPT / 8)) * A_LBO + (lr >> 3) * 128 + (lr & 7) * 16;
+        if (A_BF16) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) *reinterpret_cast<uint4 *>(d + i * A_LBO) = areg[i];
+        } else {
+            float mean = 0.f, rstd = 1.f;
+            if (LN) {
+                const int ch0 = lh * CPT;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
+                    s += (ch0 + 4 * i < p.ln_c ? f.x : 0.f) + (ch0 + 4 * i + 1 < p.ln_c ? f.y : 0.f) +
+                         (ch0 + 4 * i + 2 < p.ln_c ? f.z : 0.f) + (ch0 + 4 * i + 3 < p.ln_c ? f.w : 0.f);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                mean = s / (float)p.ln_c;
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
+                    const float d0 = ch0 + 4 * i < p.ln_c ? f.x - mean : 0.f, d1 = ch0 + 4 * i + 1 < p.ln_c ? f.y - mean : 0.f;
+                    const float d2 = ch0 + 4 * i + 2 < p.ln_c ? f.z - mean : 0.f, d3 = ch0 + 4 * i + 3 < p.ln_c ? f.w - mean : 0.f;
+                    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                }
+                q += __shfl_xor_sync(0xffffffffu, q, 1);
+                rstd = rsqrtf(q / (float)p.ln_c + 1e-5f);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i += 2) {
+                float4 f0 = *reinterpret_cast<const float4 *>(&areg[i]), f1 = *reinterpret_cast<const float4 *>(&areg[i + 1]);
+                if (LN) {       // gamma / beta are zero on the padded channels: they stay exactly zero
+                    const float *g = ln_s + lh * CPT + 4 * i, *be = ln_s + KP + lh * CPT + 4 * i;
+                    f0.x = (f0.x - mean) * rstd * g[0] + be[0]; f0.y = (f0.y - mean) * rstd * g[1] + be[1];
+                    f0.z = (f0.z - mean) * rstd * g[2] + be[2]; f0.w = (f0.w - mean) * rstd * g[3] + be[3];
+                    f1.x = (f1.x - mean) * rstd * g[4] + be[4]; f1.y = (f1.y - mean) * rstd * g[5] + be[5];
+                    f1.z = (f1.z - mean) * rstd * g[6] + be[6]; f1.w = (f1.w - mean) * rstd * g[7] + be[7];
+                }
+                *reinterpret_cast<uint4 *>(d + (i / 2) * A_LBO) =
+                    make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            }
+        }
+    };
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    auto issue = [&](int i, uint32_t tmem_d) {       // one thread: the KP/16 MMAs of tile i
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(As + (i & 1) * A_STAGE), b0 = smem_u32(Bs);
+#pragma unroll
+        for (int j = 0; j < KP / 16; ++j)
+            mma_f16(tmem_d + (uint32_t)((i & 1) * BUF1), make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128),
+                    IDESC, j > 0 ? 1u : 0u);
+        mma_commit(&mbar[i & 1]);
+    };
+
+    // residual rows of the tile about to be finished, fetched before the CTA turns to the next tile's
+    // operands so that their latency hides behind a_store / the barrier / the MMA wait
+    constexpr bool PRE = ((EPI & (EPI_RES1 | EPI_RES2)) != 0) && BN <= 64;
+    constexpr int NR1 = (PRE && (EPI & EPI_RES1)) ? BN / 8 : 1, NR2 = (PRE && (EPI & EPI_RES2)) ? BN / 16 : 1;
+    uint4 rreg1[NR1], rreg2[NR2];
+    auto r_fetch = [&](int tile) {
+        if (!PRE) return;
+        const int m = tile * BM + 32 * (warp & 3) + lane;
+        if (m >= p.rows) return;
+        const long long row = (long long)b * p.rows + m;
+        const int n0 = n_base + (warp >> 2) * (BN / 2);
+        if (EPI & EPI_RES1) {
+#pragma unroll
+            for (int i = 0; i < NR1; ++i) rreg1[i] = *(reinterpret_cast<const uint4 *>(p.res1 + row * p.ldr1 + n0) + i);
+        }
+        if (EPI & EPI_RES2) {
+#pragma unroll
+            for (int i = 0; i < NR2; ++i) rreg2[i] = *(reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0) + i);
+        }
+    };
+
+    if (n_my > 0) a_fetch(blockIdx.x);
+    if (LN) __syncthreads();                 // gamma / beta are read from shared memory by a_store
+    if (n_my > 0) a_store(0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    if (n_my > 0 && tid == 0) issue(0, tmem_d);
+    if (n_my > 1) a_fetch(blockIdx.x + gridDim.x);
+    for (int i = 0; i < n_my; ++i) {
+        r_fetch(blockIdx.x + i * gridDim.x);
+        if (i + 1 < n_my) {
+            // stage (i+1)&1 was last read by the MMAs of tile i-1 and TMEM buffer (i+1)&1 drained by the
+            // epilogue of tile i-1: both finished before this point in every thread's program order
+            a_store((i + 1) & 1);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) issue(i + 1, tmem_d);
+            if (i + 2 < n_my) a_fetch(blockIdx.x + (i + 2) * gridDim.x);
+        }
+        mbar_wait(&mbar[i & 1], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        epilogue_tile<BN, EPI, PRE>(p, tmem_d + (uint32_t)((i & 1) * BUF1), b, (blockIdx.x + i * gridDim.x) * BM, n_base, warp, lane, rreg1, rreg2);
     }
     tc_fence_before();
     __syncthreads();
@@ -359,6 +591,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {   // torch 'reflect' 
 // conv) are gathered once into registers, then all 32 output channels are accumulated from
 // broadcast float4 weight reads; eight 16-byte stores write the pixel's channel vector.
 __global__ void __launch_bounds__(128) conv_in_kernel(const __grid_constant__ ConvInP p) {
+    pdl_wait();
     __shared__ __align__(16) float ws[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = __ldg(p.w + i);
     __syncthreads();
@@ -425,6 +658,7 @@ __device__ __forceinline__ void dw_unpack(const typename DwVec<CPT>::T &raw, flo
 }
 template <int CPT>
 __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP p) {
+    pdl_wait();
     typedef typename DwVec<CPT>::T V;
     const int groups = p.Cp / CPT;
     const int segs = (p.H + p.seg - 1) / p.seg;
@@ -498,47 +732,6 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
     }
 }
 
-// ------------------------------------------------------------------------------------ LayerNorm
-// nn.LayerNorm(c) over the REAL c channels (eps 1e-5, biased variance; MST_Plus_Plus.py:57-65),
-// fp32 in -> bf16 out (padded channels written as 0).  One warp per pixel.
-struct LnP {
-    const float *in; bf16 *out; const float *gamma, *beta;
-    long long rows; int c, Cp;
-};
-template <int PER>   // channels per lane = Cp / 32
-__global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ LnP p) {
-    const int lane = threadIdx.x & 31;
-    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += (long long)gridDim.x * 8) {
-        float v[PER];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int ch = lane + 32 * i;
-            v[i] = ch < p.c ? p.in[row * p.Cp + ch] : 0.f;
-            s += v[i];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / (float)p.c;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int ch = lane + 32 * i;
-            const float d = ch < p.c ? v[i] - mean : 0.f;
-            q += d * d;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        const float rstd = rsqrtf(q / (float)p.c + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int ch = lane + 32 * i;
-            const float y = ch < p.c ? (v[i] - mean) * rstd * __ldg(p.gamma + ch) + __ldg(p.beta + ch) : 0.f;
-            p.out[row * p.Cp + ch] = __float2bfloat16_rn(y);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------ attention statistics
 // Per image and head: G[i][j] = sum_px k[px][i] q[px][j], nk[i] = sum k^2, nq[j] = sum q^2
 // (MST_Plus_Plus.py:127-129: the L2 normalisation runs over ALL pixels, so the reduction is global).
@@ -552,6 +745,7 @@ struct AttnStatP {
 // 256 threads = 4 pixel groups x (8 x 8) threads, each thread a 4 x 4 register tile of G: per pixel
 // two LDS.128 feed 16 FMAs, so the kernel is bound by the FP32 pipe / HBM, not by shared memory.
 __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__ AttnStatP p) {
+    pdl_wait();
     constexpr int TP = 128;
     __shared__ __align__(16) float qs[TP][32];
     __shared__ __align__(16) float ks[TP][32];
@@ -630,6 +824,7 @@ struct AttnFinP {
     int c, Cp, heads;
 };
 __global__ void __launch_bounds__(1024) attn_finalize_kernel(const __grid_constant__ AttnFinP p) {
+    pdl_wait();
     __shared__ float attn[4][31][32];
     const int b = blockIdx.x, tid = threadIdx.x;
     // softmax rows: one thread per (head, i)
@@ -905,6 +1100,7 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 struct Ctx {
     cudaStream_t st;
     int B;
+    int unsupported = 0;      // a layer shape none of the kernels covers (cannot happen for MST++'s own shapes)
 };
 
 template <int BN, bool A_BF16, int MODE>
@@ -917,10 +1113,58 @@ static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
         attr_set = true;
     }
     AVB_TIMED(name, cx.st);
-    tc::gemm_tc_kernel<BN, A_BF16, MODE><<<grid, GEMM_THREADS, smem, cx.st>>>(p);
+    launch_pdl(tc::gemm_tc_kernel<BN, A_BF16, MODE>, grid, dim3(GEMM_THREADS), smem, cx.st, p);
 }
+template <int BN, int KP, bool A_BF16, bool LN, int EPI>
+static void launch_pw_t(Ctx &cx, const GemmP &p, const char *name) {
+    constexpr int smem = 2 * (KP / 8) * (BM / 8) * 128 + (KP / 8) * (BN / 8) * 128 + (LN ? 2 * KP * 4 : 0);
+    constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::gemm_pw_kernel<BN, KP, A_BF16, LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    // resident CTAs per SM: TMEM columns, shared memory, and no more than the pipeline needs
+    const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
+    const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
+    int gx = std::max(1, std::min(m_tiles, sm_count() * per_sm / std::max(1, ny * cx.B)));
+    const int per_cta = (m_tiles + gx - 1) / gx;
+    gx = (m_tiles + per_cta - 1) / per_cta;              // same depth, no idle CTAs
+    AVB_TIMED(name, cx.st);
+    launch_pdl(tc::gemm_pw_kernel<BN, KP, A_BF16, LN, EPI>, dim3(gx, ny, cx.B), dim3(GEMM_THREADS), smem, cx.st, p);
+}
+
+// Shapes of the MST++ pointwise layers that take the pipelined kernel (anything else falls through
+// to the generic K-chunked kernel): K = the padded channel count of the level, N a multiple of it.
+template <bool A_BF16>
+static bool launch_pw(Ctx &cx, const GemmP &p, const char *name) {
+    if (p.K1 < p.K && 2 * p.K1 != p.K) return false;
+    const bool ln = p.ln_g != nullptr;
+    const int epi = tc::epi_of(p);
+#define PW_CASE(BN_, KP_, LN_, EPI_) \
+    if (p.K == KP_ && p.Np % BN_ == 0 && ln == LN_ && epi == (EPI_)) { launch_pw_t<BN_, KP_, A_BF16, LN_, (EPI_)>(cx, p, name); return true; }
+    using namespace tc;
+    if constexpr (A_BF16) {
+        constexpr int PROJ = EPI_BIAS | EPI_RES1 | EPI_RES2;                     // x = v M^T + b + pos_emb + x
+        PW_CASE(32, 32, false, PROJ) PW_CASE(64, 64, false, PROJ) PW_CASE(128, 128, false, PROJ)
+        PW_CASE(32, 128, false, EPI_RES1)                                        // FFN out, full-resolution level
+    } else {
+        constexpr int FFN0 = EPI_GELU | EPI_OUTBF16, UP = EPI_BIAS | EPI_CONVT;
+        PW_CASE(128, 32, true, FFN0) PW_CASE(256, 64, true, FFN0) PW_CASE(256, 128, true, FFN0)
+        PW_CASE(96, 32, false, EPI_OUTBF16) PW_CASE(192, 64, false, EPI_OUTBF16) PW_CASE(192, 128, false, EPI_OUTBF16)   // q | k | v
+        PW_CASE(256, 128, false, UP) PW_CASE(128, 64, false, UP)                 // ConvTranspose2d(2, 2)
+        PW_CASE(64, 128, false, 0) PW_CASE(32, 64, false, 0)                     // 1x1 fusion of cat([up, skip])
+    }
+#undef PW_CASE
+    return false;
+}
+
 template <bool A_BF16, int MODE>
 static void launch_gemm(Ctx &cx, const GemmP &p, const char *name) {
+    if constexpr (MODE == MODE_PW) {
+        if (launch_pw<A_BF16>(cx, p, name)) return;
+    }
+    if (p.ln_g || p.zero_ptr) { cx.unsupported = 1; return; }      // the generic kernel has no fused LayerNorm / clear
     // one CTA covers as many output channels as one tcgen05.mma can (N <= 256): the A tile is read once
     if (p.Np % 256 == 0) launch_gemm_t<256, A_BF16, MODE>(cx, p, name);
     else if (p.Np % 192 == 0) launch_gemm_t<192, A_BF16, MODE>(cx, p, name);
@@ -951,7 +1195,7 @@ static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const f
     DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out, seg};
     const long long total = (long long)cx.B * ((H + seg - 1) / seg) * W * (Cp / DW_CPT);
     AVB_TIMED(name, cx.st);
-    dwconv_kernel<DW_CPT><<<(unsigned)((total + 127) / 128), 128, 0, cx.st>>>(p);
+    launch_pdl(dwconv_kernel<DW_CPT>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, cx.st, p);
 }
 
 // MSAB with num_blocks = 1 (MST_Plus_Plus.py:160-186), in place on x (fp32 [B*rows, Cp]).
@@ -962,22 +1206,22 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         GemmP p = gemm_defaults();
         p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.Np = 3 * Cp; p.rows = rows;
         p.out = ws.qkv; p.ldo = 3 * Cp; p.out_bf16 = 1;
+        p.zero_ptr = ws.stats; p.zero_n = cx.B * m.heads * 1024;       // the statistics pass accumulates with atomics
         launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_qkv");
     }
     // Gram + norms over all pixels
-    cudaMemsetAsync(ws.stats, 0, sizeof(float) * (size_t)cx.B * m.heads * 1024, cx.st);
     {
         AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
         int ctas = std::max(1, std::min((rows + 511) / 512, sm_count() * 4 / std::max(1, cx.B * m.heads)));
         p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
         AVB_TIMED("k4_attn_stats", cx.st);
-        attn_stats_kernel<<<dim3(ctas, m.heads, cx.B), 256, 0, cx.st>>>(p);
+        launch_pdl(attn_stats_kernel, dim3(ctas, m.heads, cx.B), dim3(256), 0, cx.st, p);
     }
     {
         AttnFinP p{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
         AVB_TIMED("k4_attn_finalize", cx.st);
-        attn_finalize_kernel<<<cx.B, 1024, 0, cx.st>>>(p);
+        launch_pdl(attn_finalize_kernel, dim3(cx.B), dim3(1024), 0, cx.st, p);
     }
     // pos_emb(v): dw3x3 -> GELU -> dw3x3
     dwconv(cx, ws.qkv + 2 * Cp, 3 * Cp, ws.p1, Cp, m.pos0, H, W, Cp, 1, "k4_dw_pos");
@@ -989,20 +1233,13 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         p.bias = m.bproj; p.res1 = x; p.ldr1 = Cp; p.res2 = ws.p2; p.ldr2 = Cp; p.out = x; p.ldo = Cp;
         launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_attn_proj");
     }
-    // FFN: x = W4 GELU(dw(GELU(W0 LN(x)))) + x
-    {
-        LnP p{x, ws.ln, m.ln_g, m.ln_b, (long long)cx.B * rows, m.c, Cp};
-        const int blocks = (int)std::min<long long>((p.rows + 7) / 8, (long long)sm_count() * 16);
-        AVB_TIMED("k4_layernorm", cx.st);
-        if (Cp == 32) layernorm_kernel<1><<<blocks, 256, 0, cx.st>>>(p);
-        else if (Cp == 64) layernorm_kernel<2><<<blocks, 256, 0, cx.st>>>(p);
-        else layernorm_kernel<4><<<blocks, 256, 0, cx.st>>>(p);
-    }
+    // FFN: x = W4 GELU(dw(GELU(W0 LN(x)))) + x; the LayerNorm runs inside the FFN-in GEMM's loader
     {
         GemmP p = gemm_defaults();
-        p.A1 = ws.ln; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.ffn0; p.Np = Hp; p.rows = rows;
+        p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.ffn0; p.Np = Hp; p.rows = rows;
+        p.ln_g = m.ln_g; p.ln_b = m.ln_b; p.ln_c = m.c;
         p.gelu = 1; p.out = ws.hid1; p.ldo = Hp; p.out_bf16 = 1;
-        launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_ffn0");
+        launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_ln_ffn0");
     }
     dwconv(cx, ws.hid1, Hp, ws.hid2, Hp, m.ffn_dw, H, W, Hp, 1, "k4_dw_ffn");
     {
@@ -1123,7 +1360,7 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
         ConvInP p{in, in_is_u8, ws.x0, M->conv_in, n, H, W, Hp, Wp, top, left};
         const long long npx = (long long)n * Hp * Wp;
         AVB_TIMED("k4_conv_in", cx.st);
-        conv_in_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, cx.st>>>(p);
+        launch_pdl(conv_in_kernel, dim3((unsigned)((npx + 127) / 128)), dim3(128), 0, cx.st, p);
     }
     const float *hin = ws.x0;
     float *pp[2] = {ws.hA, ws.hB};
@@ -1138,6 +1375,7 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
         p.res1 = ws.x0; p.ldr1 = 32; p.out = out; p.out_mode = OUT_CROP; p.Hreal = H; p.Wreal = W; p.crop_top = top; p.crop_left = left;
         launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
     }
+    AVB_REQUIRE(!cx.unsupported, "layer shape without a kernel");
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }

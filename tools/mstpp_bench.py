@@ -32,6 +32,13 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    import time
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        y = net.forward_nhwc(x)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"host enqueue time {1e3 * (t1 - t0) / iters:.3f} ms/forward (asynchronous part of the call)")
     scale = (h * w) / (482 * 512)
     print(f"MST++ {n} x {h}x{w}: {ms:.3f} ms/forward, {n / ms * 1e3:.1f} patch/s, {FLOP_PER_PATCH * scale * n / ms / 1e9:.1f} TFLOP/s algorithmic")
     lib = _abi.load()
@@ -50,6 +57,10 @@ def main():
     for nm, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         print(f"  {nm:22s} {t:8.3f} ms  {c:4d} launches  {100 * t / tot:5.1f}%")
     print(f"  sum of kernels {tot:.3f} ms, {nrec} launches")
+    if "--seq" in sys.argv:
+        for i in range(min(nrec, 40)):
+            nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
+            print(f"    {i:3d} {nm:22s} {msbuf[i] * 1e3:8.1f} us")
     if check:
         xs = x[:1].cpu().permute(0, 3, 1, 2)
         ref = O.forward(xs, sd).permute(0, 2, 3, 1).numpy()
