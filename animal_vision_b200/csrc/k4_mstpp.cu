@@ -246,7 +246,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmP &p, uint32_t tmem_d, i
     }
 }
 
-template <int BN, bool A_BF16, int MODE>
+template <int BN, bool A_BF16, int MODE, bool DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmP p) {
     pdl_wait();
     constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;        // bytes between k-chunks of 8
@@ -296,55 +296,61 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         const long long off = (((long long)b * p.Hi + yy) * p.Wi + xx) * p.lda1 + c0 + 16 * lh;
         return A_BF16 ? (const void *)((const bf16 *)p.A1 + off) : (const void *)((const float *)p.A1 + off);
     };
-    uint4 areg[2];
-    auto a_fetch = [&](int kbase) {
-        bool ok;
-        const void *src = a_src(kbase, ok);
-        if (!ok) { areg[0] = areg[1] = make_uint4(0u, 0u, 0u, 0u); return; }
-        if (A_BF16) {
-            const uint4 *q = (const uint4 *)src;
-            areg[0] = __ldg(q); areg[1] = __ldg(q + 1);
-        } else {
-            const float4 *q = (const float4 *)src;
-            const float4 f0 = __ldg(q), f1 = __ldg(q + 1), f2 = __ldg(q + 2), f3 = __ldg(q + 3);
-            areg[0] = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
-            areg[1] = make_uint4(pack_bf16(f2.x, f2.y), pack_bf16(f2.z, f2.w), pack_bf16(f3.x, f3.y), pack_bf16(f3.z, f3.w));
-        }
-    };
-    auto a_store = [&](int st) {      // k-chunks 2*lh and 2*lh+1 of row lr
-        uint8_t *d = &As[st][(2 * lh) * A_LBO + (lr >> 3) * 128 + (lr & 7) * 16];
-        *reinterpret_cast<uint4 *>(d) = areg[0];
-        *reinterpret_cast<uint4 *>(d + A_LBO) = areg[1];
-    };
+    // Register ring: the global loads of chunk kc + D are issued while chunk kc feeds the tensor cores, so
+    // the K loop pays the L2 / HBM latency once per D chunks instead of once per chunk (the conv layers
+    // have 9 .. 32 chunks and, at the coarse levels, fewer CTAs than SMs to hide it otherwise; DEEP is chosen
+    // for those -- grids of several waves hide the latency with resident CTAs and prefer the registers).  Rows are
+    // kept RAW in the ring (fp32 rows are converted when they are stored to shared memory) so that
+    // nothing waits on a load before its turn.
     constexpr int B_PER_THREAD = (BN * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
+    constexpr int A_VEC = A_BF16 ? 2 : 4;
+    constexpr int D = !DEEP ? 1 : ((A_VEC + B_PER_THREAD) <= 5 ? 4 : ((A_VEC + B_PER_THREAD) <= 6 ? 3 : 2));
+    uint4 araw[D][A_VEC];
+    uint4 breg[D][B_PER_THREAD];
     const bf16 *Wb = p.W + (long long)b * p.w_bstride;
-    uint4 breg[B_PER_THREAD];
-    auto b_fetch = [&](int kbase) {
+    auto fetch = [&](int kc, uint4 (&ar)[A_VEC], uint4 (&br)[B_PER_THREAD]) {
+        const int kbase = kc * BK;
+        bool ok;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a_src(kbase, ok));
+#pragma unroll
+        for (int i = 0; i < A_VEC; ++i) ar[i] = ok ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int i = 0; i < B_PER_THREAD; ++i) {
             const int idx = tid + i * GEMM_THREADS;
             if (idx < BN * 4) {
                 const int n = idx >> 2, q = idx & 3;
-                breg[i] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K + kbase) + q);
+                br[i] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K + kbase) + q);
             }
         }
     };
-    auto b_store = [&](int st) {
+    auto store = [&](int st, const uint4 (&ar)[A_VEC], const uint4 (&br)[B_PER_THREAD]) {
+        uint8_t *d = &As[st][(2 * lh) * A_LBO + (lr >> 3) * 128 + (lr & 7) * 16];      // k-chunks 2*lh and 2*lh+1 of row lr
+        if (A_BF16) {
+            *reinterpret_cast<uint4 *>(d) = ar[0];
+            *reinterpret_cast<uint4 *>(d + A_LBO) = ar[1];
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 f0 = *reinterpret_cast<const float4 *>(&ar[2 * h]), f1 = *reinterpret_cast<const float4 *>(&ar[2 * h + 1]);
+                *reinterpret_cast<uint4 *>(d + h * A_LBO) =
+                    make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            }
+        }
 #pragma unroll
         for (int i = 0; i < B_PER_THREAD; ++i) {
             const int idx = tid + i * GEMM_THREADS;
             if (idx < BN * 4) {
                 const int n = idx >> 2, q = idx & 3;
-                *reinterpret_cast<uint4 *>(&Bs[st][q * B_LBO + (n >> 3) * 128 + (n & 7) * 16]) = breg[i];
+                *reinterpret_cast<uint4 *>(&Bs[st][q * B_LBO + (n >> 3) * 128 + (n & 7) * 16]) = br[i];
             }
         }
     };
 
     const int nk = p.K / BK;
-    a_fetch(0);
-    b_fetch(0);
-    a_store(0);
-    b_store(0);
+#pragma unroll
+    for (int u = 0; u < D; ++u)
+        if (u < nk) fetch(u, araw[u], breg[u]);
+    store(0, araw[0], breg[0]);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -353,25 +359,31 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc & 1;
-        if (kc + 1 < nk) { a_fetch((kc + 1) * BK); b_fetch((kc + 1) * BK); }
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(&As[st][0]), b0 = smem_u32(&Bs[st][0]);
+    for (int kc0 = 0; kc0 < nk; kc0 += D) {
 #pragma unroll
-            for (int j = 0; j < BK / 16; ++j)
-                mma_f16(tmem_d, make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128), IDESC,
-                        (kc > 0 || j > 0) ? 1u : 0u);
-            mma_commit(&mbar[st]);          // arrives when every MMA issued so far has finished reading smem
+        for (int u = 0; u < D; ++u) {           // ring slot of chunk kc is kc % D = u (static)
+            const int kc = kc0 + u;
+            if (kc < nk) {
+                const int st = kc & 1;
+                if (D == 1 && kc + 1 < nk) fetch(kc + 1, araw[0], breg[0]);      // single slot: it was stored last iteration
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(&As[st][0]), b0 = smem_u32(&Bs[st][0]);
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)
+                        mma_f16(tmem_d, make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128), IDESC,
+                                (kc > 0 || j > 0) ? 1u : 0u);
+                    mma_commit(&mbar[st]);          // arrives when every MMA issued so far has finished reading smem
+                }
+                if (kc + 1 < nk) {
+                    if (kc >= 1) mbar_wait(&mbar[st ^ 1], (uint32_t)(((kc - 1) >> 1) & 1));    // chunk kc-1 done with stage st^1
+                    store(st ^ 1, araw[(u + 1) % D], breg[(u + 1) % D]);
+                    fence_async_smem();
+                }
+                if (D > 1 && kc + D < nk) fetch(kc + D, araw[u], breg[u]);       // slot u was drained by the store of the previous iteration
+                __syncthreads();
+            }
         }
-        if (kc + 1 < nk) {
-            if (kc >= 1) mbar_wait(&mbar[st ^ 1], (uint32_t)(((kc - 1) >> 1) & 1));    // chunk kc-1 done with stage st^1
-            a_store(st ^ 1);
-            b_store(st ^ 1);
-            fence_async_smem();
-        }
-        __syncthreads();
     }
     mbar_wait(&mbar[(nk - 1) & 1], (uint32_t)(((nk - 1) >> 1) & 1));
     tc_fence_after();
@@ -429,10 +441,25 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_pw_kernel(const __grid_cons
         for (int i = tid; i < p.zero_n; i += GEMM_THREADS) p.zero_ptr[i] = 0.f;
     {   // resident weight tile: BN rows x KP, canonical K-major
         const bf16 *Wb = p.W + (long long)b * p.w_bstride;
-        for (int idx = tid; idx < BN * (KP / 8); idx += GEMM_THREADS) {
-            const int n = idx / (KP / 8), q = idx - n * (KP / 8);
-            *reinterpret_cast<uint4 *>(Bs + q * B_LBO + (n >> 3) * 128 + (n & 7) * 16) =
-                __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K) + q);
+        constexpr int NVEC = BN * (KP / 8), BATCH = 8;                 // eight 16-byte loads in flight per thread
+        for (int i0 = 0; i0 < NVEC; i0 += BATCH * GEMM_THREADS) {
+            uint4 wv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 8), q = idx - n * (KP / 8);
+                    wv[u] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K) + q);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 8), q = idx - n * (KP / 8);
+                    *reinterpret_cast<uint4 *>(Bs + q * B_LBO + (n >> 3) * 128 + (n & 7) * 16) = wv[u];
+                }
+            }
         }
         if (LN) {
             for (int i = tid; i < KP; i += GEMM_THREADS) {
@@ -680,26 +707,32 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
             const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + CPT * g + c));
             w[k][c] = w0.x; w[k][c + 1] = w0.y; w[k][c + 2] = w0.z; w[k][c + 3] = w0.w;
         }
-    const bf16 *base = p.in + (long long)b * p.H * p.W * p.ldi + CPT * g;
+    // running pointers: rin -> (row being loaded, column x), advanced by one row pitch per load_row
+    const long long in_pitch = (long long)p.W * p.ldi, out_pitch = (long long)p.W * p.ldo;
+    const bf16 *rin = p.in + (((long long)b * p.H + (y0 - 1)) * p.W + x) * p.ldi + CPT * g;
+    bf16 *rout = p.out + (((long long)b * p.H + y0) * p.W + x) * p.ldo + CPT * g;
+    const int ldi = p.ldi;
     const bool has_l = x > 0, has_r = x + 1 < p.W;
-    auto load_row = [&](int y, V (&raw)[3]) {
+    int y_next = y0 - 1;                                              // row rin points at
+    auto load_row = [&](V (&raw)[3]) {
         raw[0] = raw[1] = raw[2] = V{};                               // conv zero padding
-        if ((unsigned)y < (unsigned)p.H) {
-            const bf16 *r = base + ((long long)y * p.W + x) * p.ldi;
-            if (has_l) raw[0] = __ldg(reinterpret_cast<const V *>(r - p.ldi));
-            raw[1] = __ldg(reinterpret_cast<const V *>(r));
-            if (has_r) raw[2] = __ldg(reinterpret_cast<const V *>(r + p.ldi));
+        if ((unsigned)y_next < (unsigned)p.H) {
+            if (has_l) raw[0] = __ldg(reinterpret_cast<const V *>(rin - ldi));
+            raw[1] = __ldg(reinterpret_cast<const V *>(rin));
+            if (has_r) raw[2] = __ldg(reinterpret_cast<const V *>(rin + ldi));
         }
+        rin += in_pitch;
+        ++y_next;
     };
     float win[3][3][CPT];             // [row slot][dx][channel]
     V raw[3];
-    load_row(y0 - 1, raw);
+    load_row(raw);
 #pragma unroll
     for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[0][d]);
-    load_row(y0, raw);
+    load_row(raw);
 #pragma unroll
     for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[1][d]);
-    load_row(y0 + 1, raw);
+    load_row(raw);
     for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
         for (int ph = 0; ph < 3; ++ph) {           // static rotation of the three row slots
@@ -707,7 +740,7 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
             if (y < y1) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[(ph + 2) % 3][d]);      // row y + 1
-                if (y + 1 < y1) load_row(y + 2, raw);
+                if (y + 1 < y1) load_row(raw);
                 float acc[CPT];
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
@@ -724,9 +757,9 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
                 uint32_t o[CPT / 2];
 #pragma unroll
                 for (int q = 0; q < CPT / 2; ++q) o[q] = pack_bf16(acc[2 * q], acc[2 * q + 1]);
-                bf16 *dst = p.out + (((long long)b * p.H + y) * p.W + x) * p.ldo + CPT * g;
-                if (CPT == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[CPT / 2 - 2], o[CPT / 2 - 1]);
-                else *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
+                if (CPT == 8) *reinterpret_cast<uint4 *>(rout) = make_uint4(o[0], o[1], o[CPT / 2 - 2], o[CPT / 2 - 1]);
+                else *reinterpret_cast<uint2 *>(rout) = make_uint2(o[0], o[1]);
+                rout += out_pitch;
             }
         }
     }
@@ -754,7 +787,6 @@ __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__
     const int head = blockIdx.y, b = blockIdx.z;
     const int p0 = blockIdx.x * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
     const int ld = 3 * p.Cp;
-    const bf16 *base = p.qkv + (long long)b * p.rows * ld + head * NF;
     float acc[4][4], nk[4], nq[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -762,17 +794,24 @@ __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     }
+    // A head's 31 channels start at column 31*head of the q (and k) block: fetch the <= 5 aligned
+    // 8-channel chunks that cover them with 16-byte loads and scatter the members into the fp32 tile
+    const int lo8 = (head * NF) & ~7;
+    for (int e = tid; e < TP; e += 256) qs[e][31] = ks[e][31] = 0.f;
     for (int t0 = p0; t0 < p1; t0 += TP) {
-        for (int e = tid; e < TP * 32; e += 256) {
-            const int px = e >> 5, ch = e & 31;
-            float qv = 0.f, kv = 0.f;
-            if (t0 + px < p1 && ch < NF) {
-                const bf16 *r = base + (long long)(t0 + px) * ld + ch;
-                qv = __bfloat162float(r[0]);
-                kv = __bfloat162float(r[p.Cp]);
+        for (int e = tid; e < TP * 10; e += 256) {
+            const int px = e / 10, c = e - px * 10;
+            const int isk = c >= 5, col0 = lo8 + 8 * (c - 5 * isk);
+            if (col0 >= p.Cp) continue;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            if (t0 + px < p1) raw = __ldg(reinterpret_cast<const uint4 *>(p.qkv + ((long long)b * p.rows + t0 + px) * ld + isk * p.Cp + col0));
+            float *dst = isk ? ks[px] : qs[px];
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ch = col0 + i - head * NF;
+                if ((unsigned)ch < (unsigned)NF) dst[ch] = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
             }
-            qs[px][ch] = qv;
-            ks[px][ch] = kv;
         }
         __syncthreads();
 #pragma unroll 4
@@ -823,40 +862,52 @@ struct AttnFinP {
     bf16 *M;             // [B][Cp][Cp]
     int c, Cp, heads;
 };
+// grid (B, Cp / 32): every CTA redoes the (tiny) softmax and produces 32 rows of M from a Wproj slab
+// staged in shared memory with coalesced loads.
 __global__ void __launch_bounds__(1024) attn_finalize_kernel(const __grid_constant__ AttnFinP p) {
     pdl_wait();
     __shared__ float attn[4][31][32];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ float rq[4][32];              // 1 / max(|q_j|, 1e-12)
+    __shared__ float wslab[32][128];         // Wproj rows co0 .. co0+31 (c <= 124 columns)
+    const int b = blockIdx.x, co0 = blockIdx.y * 32, tid = threadIdx.x;
+    for (int e = tid; e < 32 * p.c; e += 1024) {
+        const int r = e / p.c, k = e - r * p.c;
+        wslab[r][k] = (co0 + r < p.c) ? __ldg(p.wproj + (long long)(co0 + r) * p.c + k) : 0.f;
+    }
+    if (tid < p.heads * 32) {
+        const int h = tid >> 5, j = tid & 31;
+        const float *S = p.stats + ((long long)b * p.heads + h) * 1024;
+        rq[h][j] = j < NF ? 1.0f / fmaxf(sqrtf(S[31 * 32 + j]), 1e-12f) : 0.f;
+    }
+    __syncthreads();
     // softmax rows: one thread per (head, i)
     if (tid < p.heads * NF) {
         const int h = tid / NF, i = tid - h * NF;
         const float *S = p.stats + ((long long)b * p.heads + h) * 1024;
-        const float nk = fmaxf(sqrtf(S[i * 32 + 31]), 1e-12f);
-        const float rs = __ldg(p.rescale + h);
+        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf(S[i * 32 + 31]), 1e-12f);
         float row[NF], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-            const float nq = fmaxf(sqrtf(S[31 * 32 + j]), 1e-12f);
-            row[j] = S[i * 32 + j] / (nk * nq) * rs;
+            row[j] = S[i * 32 + j] * (sc * rq[h][j]);
             mx = fmaxf(mx, row[j]);
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < NF; ++j) { row[j] = expf(row[j] - mx); sum += row[j]; }
+        for (int j = 0; j < NF; ++j) { row[j] = __expf(row[j] - mx); sum += row[j]; }
         const float inv = 1.0f / sum;
 #pragma unroll
         for (int j = 0; j < NF; ++j) attn[h][i][j] = row[j] * inv;
     }
     __syncthreads();
-    bf16 *M = p.M + (long long)b * p.Cp * p.Cp;
-    for (int e = tid; e < p.Cp * p.Cp; e += 1024) {
-        const int co = e / p.Cp, k = e - co * p.Cp;
+    bf16 *M = p.M + ((long long)b * p.Cp + co0) * p.Cp;
+    for (int e = tid; e < 32 * p.Cp; e += 1024) {
+        const int r = e / p.Cp, k = e - r * p.Cp;
         float v = 0.f;
-        if (co < p.c && k < p.c) {
+        if (co0 + r < p.c && k < p.c) {
             const int h = k / NF, j = k - h * NF;
-            const float *wrow = p.wproj + (long long)co * p.c + h * NF;
+            const float *wrow = &wslab[r][h * NF];
 #pragma unroll
-            for (int i = 0; i < NF; ++i) v = fmaf(__ldg(wrow + i), attn[h][i][j], v);
+            for (int i = 0; i < NF; ++i) v = fmaf(wrow[i], attn[h][i][j], v);
         }
         M[e] = __float2bfloat16_rn(v);
     }
@@ -1103,17 +1154,23 @@ struct Ctx {
     int unsupported = 0;      // a layer shape none of the kernels covers (cannot happen for MST++'s own shapes)
 };
 
-template <int BN, bool A_BF16, int MODE>
-static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
-    dim3 grid((p.rows + BM - 1) / BM, p.Np / BN, cx.B);
+template <int BN, bool A_BF16, int MODE, bool DEEP>
+static void launch_gemm_td(Ctx &cx, const GemmP &p, dim3 grid, const char *name) {
     constexpr int smem = 2 * (BK / 8) * (BM / 8) * 128 + 2 * (BK / 8) * (BN / 8) * 128;
     static bool attr_set = false;       // per instantiation; the attribute is idempotent, a race only repeats it
     if (!attr_set) {
-        cudaFuncSetAttribute(tc::gemm_tc_kernel<BN, A_BF16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(tc::gemm_tc_kernel<BN, A_BF16, MODE, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
     AVB_TIMED(name, cx.st);
-    launch_pdl(tc::gemm_tc_kernel<BN, A_BF16, MODE>, grid, dim3(GEMM_THREADS), smem, cx.st, p);
+    launch_pdl(tc::gemm_tc_kernel<BN, A_BF16, MODE, DEEP>, grid, dim3(GEMM_THREADS), smem, cx.st, p);
+}
+template <int BN, bool A_BF16, int MODE>
+static void launch_gemm_t(Ctx &cx, const GemmP &p, const char *name) {
+    dim3 grid((p.rows + BM - 1) / BM, p.Np / BN, cx.B);
+    // fewer than ~3 CTAs per SM: nothing else hides the load latency of the K loop
+    if ((long long)grid.x * grid.y * grid.z < 3LL * sm_count()) launch_gemm_td<BN, A_BF16, MODE, true>(cx, p, grid, name);
+    else launch_gemm_td<BN, A_BF16, MODE, false>(cx, p, grid, name);
 }
 template <int BN, int KP, bool A_BF16, bool LN, int EPI>
 static void launch_pw_t(Ctx &cx, const GemmP &p, const char *name) {
@@ -1212,7 +1269,7 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
     // Gram + norms over all pixels
     {
         AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
-        int ctas = std::max(1, std::min((rows + 511) / 512, sm_count() * 4 / std::max(1, cx.B * m.heads)));
+        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 4 / std::max(1, cx.B * m.heads)));
         p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
         AVB_TIMED("k4_attn_stats", cx.st);
@@ -1221,7 +1278,7 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
     {
         AttnFinP p{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
         AVB_TIMED("k4_attn_finalize", cx.st);
-        launch_pdl(attn_finalize_kernel, dim3(cx.B), dim3(1024), 0, cx.st, p);
+        launch_pdl(attn_finalize_kernel, dim3(cx.B, Cp / 32), dim3(1024), 0, cx.st, p);
     }
     // pos_emb(v): dw3x3 -> GELU -> dw3x3
     dwconv(cx, ws.qkv + 2 * Cp, 3 * Cp, ws.p1, Cp, m.pos0, H, W, Cp, 1, "k4_dw_pos");
