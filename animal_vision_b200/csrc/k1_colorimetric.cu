@@ -9,7 +9,13 @@
 
 namespace avb {
 
-constexpr int K1_THREADS = 256;
+#ifndef K1_THREADS_N
+#define K1_THREADS_N 256
+#endif
+#ifndef K1_CTAS_PER_SM
+#define K1_CTAS_PER_SM 2
+#endif
+constexpr int K1_THREADS = K1_THREADS_N;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_UNIT = 1536;          // bytes per warp iteration
 constexpr int K1_ENC_SMEM = AVB_ENC_TABLE_MAX;
@@ -58,65 +64,160 @@ __device__ __forceinline__ void transform16(uint32_t (&w)[12], const float *lut,
     for (int i = 0; i < 12; ++i) w[i] = o[i];
 }
 
-// Fast path: frames are contiguous (row stride == 3*W) and 16-byte aligned.
+// ---------------------------------------------------------------- bulk-copy (TMA) helpers
+__device__ __forceinline__ uint32_t k1_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k1_mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k1_smem(bar)));
+}
+__device__ __forceinline__ void k1_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k1_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(k1_smem(dst)), "l"(src), "r"(bytes), "r"(k1_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void k1_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = k1_smem(bar);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void k1_bulk_store(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(k1_smem(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// Fast path: frames are contiguous (row stride == 3*W) and 16-byte aligned.  Every warp runs its own
+// double-buffered pipeline over 1536-byte units: the TMA engine (cp.async.bulk, completion on an
+// mbarrier) fills slab i+1 while the lanes transform slab i, and finished slabs leave through bulk
+// stores -- no thread ever waits on an HBM load it issued itself.  The 256-entry decode LUT is
+// replicated once per shared-memory bank (index v*32 + lane), so the three decode lookups of a pixel
+// are conflict-free whatever the image content (noise frames made the single copy 3-4-way conflicted).
+constexpr int K1_LUT_REP = 32;
+struct K1Smem {
+    uint4 in[K1_WARPS][2][96];
+    uint4 out[K1_WARPS][2][96];
+    float lut[256 * K1_LUT_REP];
+    uint32_t enc[K1_ENC_SMEM];
+    uint64_t bar[K1_WARPS][2];
+};
+
 template <bool GAIN>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_contig_kernel(const __grid_constant__ K1Params p) {
-    __shared__ __align__(16) uint4 slab[K1_WARPS][96];
-    __shared__ float lut_s[256];
-    __shared__ uint32_t enc_s[K1_ENC_SMEM];
+__device__ __forceinline__ void transform16r(uint32_t (&w)[12], const float *lut_lane, const EncTable &enc, const float (&m)[9],
+                                             const float *row_gain, int64_t first_px, int W) {
+    uint32_t o[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = 0;
+    int y = 0, xr = 0;
+    if (GAIN) {
+        y = (int)(first_px / W);
+        xr = (int)(first_px - (int64_t)y * W);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float l0 = lut_lane[byte_of(w, 3 * j) * K1_LUT_REP], l1 = lut_lane[byte_of(w, 3 * j + 1) * K1_LUT_REP],
+                    l2 = lut_lane[byte_of(w, 3 * j + 2) * K1_LUT_REP];
+        const float r0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
+        const float r1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
+        float r2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
+        if (GAIN) {
+            const int yy = y + ((xr + j >= W) ? 1 : 0);   // contiguous path requires W >= 16: one wrap at most
+            r2 = __fmul_rn(r2, __ldg(row_gain + yy));
+        }
+        const uint32_t e0 = encode_u8(enc, r0), e1 = encode_u8(enc, r1), e2 = encode_u8(enc, r2);
+        o[(3 * j) >> 2] |= e0 << (8 * ((3 * j) & 3));
+        o[(3 * j + 1) >> 2] |= e1 << (8 * ((3 * j + 1) & 3));
+        o[(3 * j + 2) >> 2] |= e2 << (8 * ((3 * j + 2) & 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = o[i];
+}
+
+template <bool GAIN>
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_contig_kernel(const __grid_constant__ K1Params p) {
+    extern __shared__ __align__(128) uint8_t k1_dsm[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_dsm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += K1_THREADS) lut_s[i] = __ldg(p.lut + i);
-    copy_to_smem(enc_s, p.enc, min(K1_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    if (p.fixup) {          // second pass of AVB_NORM_AUTO: almost always nothing to redo -- leave before the tables are built
+        bool todo = false;
+        for (int i = lane; i < p.io.n; i += 32) todo |= p.flags[i] == 0;
+        if (!__any_sync(0xffffffffu, todo)) return;
+    }
+    for (int i = tid; i < 256 * K1_LUT_REP; i += K1_THREADS) sm.lut[i] = __ldg(p.lut + (i >> 5));
+    copy_to_smem(sm.enc, p.enc, min(K1_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    if (lane == 0) {
+        k1_mbar_init(&sm.bar[warp][0]);
+        k1_mbar_init(&sm.bar[warp][1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const EncTable enc = enc_view(enc_s);
+    const EncTable enc = enc_view(sm.enc);
+    const float *lut_lane = sm.lut + lane;
     float m[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) m[i] = p.M.m[i];
 
     const int64_t frame_bytes = 3LL * p.io.W * p.io.H;
     const int64_t total_units = (int64_t)p.units_per_frame * p.io.n;
-    uint32_t seen = 0;
-    int flagged_frame = -1;
-    for (int64_t u = (int64_t)blockIdx.x * K1_WARPS + warp; u < total_units; u += (int64_t)gridDim.x * K1_WARPS) {
-        const int frame = (int)(u / p.units_per_frame);
-        if (p.fixup && p.flags[frame] != 0) continue;
+    const int64_t stride = (int64_t)gridDim.x * K1_WARPS;
+    // unit -> (frame, byte offset); `full` units go through the slab pipeline, frame tails are done in place
+    auto locate = [&](int64_t u, int &frame, int64_t &off, bool &full, bool &skip) {
+        frame = (int)(u / p.units_per_frame);
+        off = (u - (int64_t)frame * p.units_per_frame) * K1_UNIT;
+        full = frame_bytes - off >= K1_UNIT;
+        skip = p.fixup && p.flags[frame] != 0;
+    };
+    auto prefetch = [&](int64_t u, int slot) {       // lane 0 only
+        if (u >= total_units) return;
+        int frame; int64_t off; bool full, skip;
+        locate(u, frame, off, full, skip);
+        if (full && !skip) k1_bulk_load(sm.in[warp][slot], p.io.in + (int64_t)frame * p.io.in_fs + off, K1_UNIT, &sm.bar[warp][slot]);
+    };
+    uint32_t seen = 0, phases = 0;                     // bit s: parity the next wait on slot s expects
+    int flagged_frame = -1, slot = 0;
+    int64_t u = (int64_t)blockIdx.x * K1_WARPS + warp;
+    if (lane == 0) prefetch(u, 0);
+    for (; u < total_units; u += stride) {
+        int frame; int64_t off; bool full, skip;
+        locate(u, frame, off, full, skip);
+        if (lane == 0) prefetch(u + stride, slot ^ (full && !skip ? 1 : 0));     // a unit that uses no slab leaves the slot to its successor
+        if (skip) continue;
         if (frame != flagged_frame) {   // flush the per-frame "byte >= 2" accumulator
             if (p.flags && !p.fixup && flagged_frame >= 0 && __any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0)
                 p.flags[flagged_frame] = 1u;
             seen = 0;
             flagged_frame = frame;
         }
-        const int64_t off = (u - (int64_t)frame * p.units_per_frame) * K1_UNIT;
         const uint8_t *src = p.io.in + (int64_t)frame * p.io.in_fs + off;
         uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs + off;
-        const int64_t remain = frame_bytes - off;              // > 0
-        if (remain >= K1_UNIT) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) slab[warp][k * 32 + lane] = __ldcs(reinterpret_cast<const uint4 *>(src) + k * 32 + lane);
-            __syncwarp();
+        if (full) {
+            k1_mbar_wait(&sm.bar[warp][slot], (phases >> slot) & 1u);
+            phases ^= 1u << slot;
             uint32_t w[12];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const uint4 t = slab[warp][lane * 3 + k];
+                const uint4 t = sm.in[warp][slot][lane * 3 + k];
                 w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
             }
 #pragma unroll
             for (int i = 0; i < 12; ++i) seen |= w[i];
-            transform16<GAIN>(w, lut_s, enc, m, p.row_gain, (off + lane * 48) / 3, p.io.W);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) slab[warp][lane * 3 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            transform16r<GAIN>(w, lut_lane, enc, m, p.row_gain, (off + lane * 48) / 3, p.io.W);
+            // the bulk store that last read out[slot] (two units ago) must have drained it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 3; ++k) __stcs(reinterpret_cast<uint4 *>(dst) + k * 32 + lane, slab[warp][k * 32 + lane]);
+            for (int k = 0; k < 3; ++k) sm.out[warp][slot][lane * 3 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
+            if (lane == 0) k1_bulk_store(dst, sm.out[warp][slot], K1_UNIT);
+            slot ^= 1;
         } else {
             // frame tail (< 1536 B): whole pixels, one per lane-iteration
-            const int npx = (int)(remain / 3);
+            const int npx = (int)((frame_bytes - off) / 3);
             const int64_t px0 = off / 3;
             for (int j = lane; j < npx; j += 32) {
                 const uint32_t b0 = src[3 * j], b1 = src[3 * j + 1], b2 = src[3 * j + 2];
                 seen |= b0 | b1 | b2;
-                const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
+                const float l0 = lut_lane[b0 * K1_LUT_REP], l1 = lut_lane[b1 * K1_LUT_REP], l2 = lut_lane[b2 * K1_LUT_REP];
                 const float r0 = m[0] * l0 + m[1] * l1 + m[2] * l2;
                 const float r1 = m[3] * l0 + m[4] * l1 + m[5] * l2;
                 float r2 = m[6] * l0 + m[7] * l1 + m[8] * l2;
@@ -127,6 +228,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_contig_kernel(const __grid_c
             }
         }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // slabs stay valid until read out
     if (p.flags && !p.fixup && flagged_frame >= 0 && __any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0)
         p.flags[flagged_frame] = 1u;
 }
@@ -174,10 +276,16 @@ static int launch_k1(const K1Params &p, cudaStream_t st) {
     if (contig) {
         const int64_t total_units = (int64_t)p.units_per_frame * io.n;
         int64_t blocks = (total_units + K1_WARPS - 1) / K1_WARPS;
-        const int64_t cap = (int64_t)sm_count() * 4 * 4;   // 4 resident CTAs per SM, a few waves each
+        const int64_t cap = (int64_t)sm_count() * K1_CTAS_PER_SM;   // persistent: every resident CTA walks its share of the units
         if (blocks > cap) blocks = cap;
-        if (p.row_gain) k1_contig_kernel<true><<<(unsigned)blocks, K1_THREADS, 0, st>>>(p);
-        else k1_contig_kernel<false><<<(unsigned)blocks, K1_THREADS, 0, st>>>(p);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k1_contig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+            cudaFuncSetAttribute(k1_contig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+            attr_set = true;
+        }
+        if (p.row_gain) k1_contig_kernel<true><<<(unsigned)blocks, K1_THREADS, sizeof(K1Smem), st>>>(p);
+        else k1_contig_kernel<false><<<(unsigned)blocks, K1_THREADS, sizeof(K1Smem), st>>>(p);
     } else {
         dim3 grid((io.W + K1_THREADS - 1) / K1_THREADS, io.H < 1024 ? io.H : 1024, io.n);
         if (p.row_gain) k1_strided_kernel<true><<<grid, K1_THREADS, 0, st>>>(p);
