@@ -266,7 +266,7 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
             "patches_per_s": nb * world / (ms * 1e-3), "ms_per_forward": ms, "batch_per_gpu": nb,
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,
                          "peak_source": src, "algorithmic_flop_per_patch": MSTPP_FLOP_PER_PATCH,
-                         "note": "whole forward (176 launches), not one kernel; the network is launch/HBM bound at C=31 (SURVEY.md section 7)"}}
+                         "note": "whole forward (161 dependent launches chained with programmatic dependent launch), not one kernel; at C=31 the network is bound by per-kernel latency and HBM, not by the tensor pipe (SURVEY.md section 7)"}}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -386,6 +386,26 @@ def run_b200(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     barrier()
 
+    # ---- K1 leg (north_star kernel 1, BASELINE configs[0]'s species family): the pure colorimetric kernel
+    # (Rat: LUT decode, 3x3, row gain, encode) on the Dog shard, device resident, CUDA events
+    rat = A.Rat()
+    rat_out = torch.empty_like(dev_in["Dog"])
+    for _ in range(3):
+        rat.visualize_batch(dev_in["Dog"], out=rat_out)
+    barrier()
+    k0, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(10):
+        rat.visualize_batch(dev_in["Dog"], out=rat_out)
+    k1e.record()
+    barrier()
+    k1_ms = max_over_ranks(k0.elapsed_time(k1e) / 10)
+    k1_bytes = 6.0 * dev_in["Dog"].shape[0] * H * W
+    colorimetric = {"kernel": "k1_colorimetric (+ its AVB_NORM_AUTO fixup launch)", "species": "Rat", "frames": int(dev_in["Dog"].shape[0]),
+                    "ms": k1_ms, "mpix_per_s": dev_in["Dog"].shape[0] * H * W / (k1_ms * 1e-3) / 1e6,
+                    "roofline": {"bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": k1_bytes}}
+
     # ---- K4 leg (BASELINE configs[3]): MST++ forward on 482x512 patches, tensor-pipe roofline
     mstpp = run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier)
 
@@ -417,6 +437,7 @@ def run_b200(args):
         "roofline": roofline,
     }
     line["mstpp"] = mstpp
+    line["colorimetric"] = colorimetric
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         rows = args.cpu_rows
