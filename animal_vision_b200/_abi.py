@@ -18,6 +18,7 @@ _lib = None
 AVB_NORM_DIV255 = 0
 AVB_NORM_AUTO = 1
 AVB_ENC_TABLE_MAX = 2048
+AVB_F32_POINT, AVB_F32_GAUSS, AVB_F32_STREAK = 0, 1, 2
 
 _p = C.c_void_p
 _i = C.c_int
@@ -41,6 +42,7 @@ SIGNATURES = {
     "avb_mstpp_forward": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "avb_band_project_f32": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
     "avb_safe_norm_f32": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    "avb_dichromat_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p]),
     "avb_uv_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "avb_uv_map_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i, _f, _i, _p, _i, _i, _p, _f, _p, _p, _p]),
 }

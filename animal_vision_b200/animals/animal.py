@@ -26,6 +26,24 @@ def is_frame(image) -> bool:
             and np.issubdtype(image.dtype, np.number))
 
 
+def run_single_float(engine, image: np.ndarray, fn):
+    """Float (or non-uint8 integer) frame through the float32 device path: the reference's own first step
+    is `image.astype(np.float32)` (animals/animal_utils.py:45), done here on the way into pinned memory;
+    `fn(dev_in, dev_out, dev_tmp, quantize)` runs on the current stream.  Returns one HxWx3 array of the
+    caller's dtype (dog.py:56-59: integer dtypes get x*255+0.5 truncated, floats a plain cast)."""
+    torch = engine.torch
+    integer = np.issubdtype(image.dtype, np.integer)
+    with torch.cuda.device(engine.device):
+        pin = torch.empty((1,) + image.shape, dtype=torch.float32).pin_memory()
+        pin[0].numpy()[...] = image                      # float32 conversion, as astype(np.float32)
+        dev_in = pin.to(engine.device, non_blocking=True)
+        dev_out, dev_tmp = torch.empty_like(dev_in), torch.empty_like(dev_in)
+        fn(dev_in, dev_out, dev_tmp, integer)
+        pin.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream(engine.device).synchronize()
+        return pin[0].numpy().astype(image.dtype)
+
+
 def run_single(engine, image: np.ndarray, fn, n_out: int = 1):
     """NumPy-in / NumPy-out shim: pinned H2D copy, `fn(dev_in, dev_outs)` on the current stream,
     pinned D2H copy, one synchronise.  Returns a list of fresh HxWx3 uint8 arrays."""

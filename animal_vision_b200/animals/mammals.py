@@ -12,7 +12,8 @@ import numpy as np
 
 from .. import tables
 from ..engine import get_engine
-from .animal import Animal, is_frame, run_single
+from .._abi import AVB_F32_GAUSS, AVB_F32_POINT, AVB_F32_STREAK
+from .animal import Animal, is_frame, run_single, run_single_float
 
 
 class _Mammal(Animal):
@@ -25,6 +26,9 @@ class _Mammal(Animal):
     def _run(self, eng, frames, out):
         raise NotImplementedError
 
+    def _run_f32(self, eng, frames, out, tmp, quantize):
+        raise NotImplementedError
+
     def visualize_batch(self, frames, out=None):
         eng = get_engine(frames.device)
         if out is None:
@@ -35,6 +39,9 @@ class _Mammal(Animal):
     def visualize(self, image: np.ndarray) -> Optional[Tuple[np.ndarray, np.ndarray]]:
         assert is_frame(image)                       # dog.py:33
         eng = get_engine()
+        if image.dtype != np.uint8:                  # float in => float out (dog.py:56-59): the float32 device path
+            out = run_single_float(eng, image, lambda d_in, d_out, d_tmp, q: self._run_f32(eng, d_in, d_out, d_tmp, q))
+            return image, out
         (out,) = run_single(eng, image, lambda d_in, d_out: self._run(eng, d_in, d_out[0]))
         return image, out                            # baseline is the input object itself (dog.py:61)
 
@@ -46,6 +53,10 @@ class _GaussMammal(_Mammal):
         taps = tables.gaussian_taps(tables.gaussian_ksize(self.SIGMA), self.SIGMA)
         eng.dichromat_blur(frames, out, self._matrix(), taps)
 
+    def _run_f32(self, eng, frames, out, tmp, quantize):
+        taps = tables.gaussian_taps(tables.gaussian_ksize(self.SIGMA), self.SIGMA)
+        eng.dichromat_f32(frames, out, tmp, self._matrix(), AVB_F32_GAUSS, taps=taps, quantize=quantize)
+
 
 class _StreakMammal(_Mammal):
     STREAK = (0.5, 0.8, 2.2, 6.0)    # y_center, sigma_streak, sigma_far, falloff
@@ -53,6 +64,9 @@ class _StreakMammal(_Mammal):
 
     def _run(self, eng, frames, out):
         eng.streak_blur(frames, out, self._matrix(), self.STREAK, self.CHROMA)
+
+    def _run_f32(self, eng, frames, out, tmp, quantize):
+        eng.dichromat_f32(frames, out, tmp, self._matrix(), AVB_F32_STREAK, streak=self.STREAK, chroma=self.CHROMA, quantize=quantize)
 
 
 def _gauss(name, alpha, s_scale, sigma, cite):
@@ -99,6 +113,12 @@ class Rat(_Mammal):
         gain = eng.cached(("scone", H, tuple(sorted(self.SCONE.items()))),
                           lambda: eng._dev(tables.scone_row_gain(H, **self.SCONE)))
         eng.colorimetric(frames, out, self._matrix(), row_gain=gain)
+
+    def _run_f32(self, eng, frames, out, tmp, quantize):
+        H = frames.shape[1]
+        gain = eng.cached(("scone", H, tuple(sorted(self.SCONE.items()))),
+                          lambda: eng._dev(tables.scone_row_gain(H, **self.SCONE)))
+        eng.dichromat_f32(frames, out, tmp, self._matrix(), AVB_F32_POINT, row_gain=gain, quantize=quantize)
 
 
 MAMMALS = {c.__name__.lower(): c for c in (Dog, Bear, Lion, Tiger, Elephant, Fox, Wolf, Raccoon, Squirrel, Rat,

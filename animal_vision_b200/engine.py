@@ -124,6 +124,28 @@ class Engine:
         check(rc, "avb_streak_blur_u8")
         self.launches += 2 if norm == AVB_NORM_AUTO else 1
 
+    def dichromat_f32(self, frames, out, tmp, M: np.ndarray, kind: int, taps=None, streak=None, row_gain=None,
+                      chroma: float = 0.0, quantize: bool = False):
+        """Float-frame path (include/avb200.h avb_dichromat_f32): packed float32 CUDA tensors [N,H,W,3]."""
+        t = self.torch
+        for name, x in (("frames", frames), ("out", out), ("tmp", tmp)):
+            if not (x.is_cuda and x.dtype == t.float32 and x.dim() == 4 and x.shape[3] == 3 and x.is_contiguous()):
+                raise AvbError(f"{name} must be a contiguous float32 CUDA tensor [N,H,W,3]")
+        n, h, w, _ = frames.shape
+        M = np.ascontiguousarray(M, np.float32)
+        tab = None
+        if streak is not None:
+            key = ("streak", h, M.tobytes(), tuple(float(v) for v in streak))
+            tab = self.cached(key, lambda: self._dev(tables.streak_row_table(h, M, *streak)))
+        tp = None if taps is None else np.ascontiguousarray(taps, np.float32)
+        rc = self.lib.avb_dichromat_f32(
+            frames.data_ptr(), out.data_ptr(), tmp.data_ptr(), n, h, w, _fptr(M), kind,
+            None if tp is None else _fptr(tp), 0 if tp is None else int(tp.size),
+            None if tab is None else tab.data_ptr(), None if row_gain is None else row_gain.data_ptr(),
+            float(chroma), int(bool(quantize)), self.flags(n).data_ptr(), self.stream_ptr())
+        check(rc, "avb_dichromat_f32")
+        self.launches += 3 + (kind != 0) + (kind == 1)
+
     def cat(self, frames, out_human, out_cat, M: np.ndarray, taps: np.ndarray, warp_dev, zoom_dev, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, hfs, hrs = self.check_frames(out_human, "out_human")

@@ -205,6 +205,28 @@ AVB_API int avb_band_project_f32(const float *cube_dev, const float *weights_dev
 AVB_API int avb_safe_norm_f32(const float *in_dev, float *out_dev, int64_t npx, int stride, int n_maps,
                               void *scratch_dev, avb_stream_t stream);
 
+/* Float-frame path of the 19 dichromat mammals: "float in => float [0,1] out, no quantisation"
+ * (animals/dog.py:56-59).  get_normalized_image's branch (animals/animal_utils.py:41-50: divide by
+ * 255 only if the frame maximum exceeds 1) is decided per frame on the device; decode / encode are
+ * the IEC 61966-2-1 functions of animal_utils.py:5-19 in float32.  All frame pointers: packed device
+ * float32 [n,H,W,3]; `tmp_dev` is scratch of the same size; `out_dev` must not alias `in_dev`.
+ *   kind          AVB_F32_POINT   no spatial filter (Rat: row_gain_dev = S-cone gain per row, or NULL)
+ *                 AVB_F32_GAUSS   cv2.GaussianBlur taps (host, odd ksize <= 33), REFLECT_101
+ *                                 (animal_utils.py:121-145)
+ *                 AVB_F32_STREAK  per-row filter, row_tab_dev as for avb_streak_blur_u8
+ *                                 (animal_utils.py:147-172)
+ *   chroma        apply_chroma_compression strength after the filter (animal_utils.py:174-181), 0 = off
+ *   quantize      1: finish with trunc(x*255 + 0.5) for callers whose frames had an integer dtype
+ *                 other than uint8 (dog.py:56-57); the values stay float32
+ *   maxbits_dev   n uint32 of scratch */
+#define AVB_F32_POINT 0
+#define AVB_F32_GAUSS 1
+#define AVB_F32_STREAK 2
+AVB_API int avb_dichromat_f32(const float *in_dev, float *out_dev, float *tmp_dev, int n, int H, int W,
+                              const float *m_host, int kind, const float *taps_host, int ksize,
+                              const float *row_tab_dev, const float *row_gain_dev, float chroma, int quantize,
+                              uint32_t *maxbits_dev, avb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,3 +86,15 @@ def parity_set(h: int, w: int):
     yield "noise0", noise(h, w, 0)
     for name, fn in STRUCTURED.items():
         yield name, fn(h, w)
+
+
+def float_set(h: int, w: int):
+    """Non-uint8 frames for the "float in => float out" contract (dog.py:56-59) and the data-dependent
+    normalisation branch (animal_utils.py:41-50): unit-range float32 (not divided), 0..255 float32
+    (divided), unit-range float64, and an integer dtype other than uint8."""
+    return [
+        ("f32_unit", (natural(h, w).astype(np.float32) / np.float32(255.0))),
+        ("f32_255", noise(h, w, 7).astype(np.float32)),
+        ("f64_unit", np.random.default_rng(11).random((h, w, 3))),
+        ("u16_255", noise(h, w, 9).astype(np.uint16)),
+    ]
