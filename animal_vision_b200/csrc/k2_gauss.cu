@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *
 // Centre zoom (cat_widevision_utils.py:11-29): crop + cv2.resize(INTER_LINEAR) on uint8, restated
 // in OpenCV's 11-bit fixed point so the result is bit-exact.  tab = W x int4 {xi0, xi1, xw0, xw1}
 // then H x int4 {yi0, yi1, yw0, yw1} (source indices already include the crop origin).
-// One thread = 4 consecutive output pixels of a row (12 bytes = three 32-bit stores).  The two
+// One thread = 4 consecutive output pixels per row (12 bytes = three 32-bit stores).  The two
 // horizontal taps of a pixel are adjacent source pixels (xi1 = xi0 + 1, or xi1 = xi0 with weight 0
 // at the right edge), i.e. 6 contiguous bytes: the aligned path fetches them as three 32-bit words
 // per source row and realigns with funnel shifts instead of issuing six byte loads.
@@ -723,51 +723,81 @@ __device__ __forceinline__ void zoom_taps(const uint32_t *row32, int xi0, int la
     a[0] = lo & 0xffu; a[1] = (lo >> 8) & 0xffu; a[2] = (lo >> 16) & 0xffu;       // pixel xi0
     b[0] = lo >> 24; b[1] = hi & 0xffu; b[2] = (hi >> 8) & 0xffu;                  // pixel xi0 + 1
 }
-__global__ void __launch_bounds__(256) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab, int aligned_out, int aligned_in) {
-    const int W = io.W;
+// cv2.resize is separable: a thread owns 4 output pixels of a column strip and walks down ZOOM_ROWS output
+// rows, keeping the horizontally interpolated values (a0*xw0 + a1*xw1, three channels x four pixels) of
+// the two source rows in flight in registers.  Going down, the source row pair advances by 0 or 1 per
+// output row (scale 1/1.5), so most rows recompute one horizontal row or none instead of two.
+#ifndef ZOOM_ROWS_N
+#define ZOOM_ROWS_N 32
+#endif
+constexpr int ZOOM_ROWS = ZOOM_ROWS_N;
+__global__ void __launch_bounds__(128) center_zoom_kernel(FrameIO io, const int32_t *__restrict__ tab, int aligned_out, int aligned_in) {
+    const int W = io.W, H = io.H;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
     if (x4 >= W) return;
-    const int4 ty = __ldg(reinterpret_cast<const int4 *>(tab) + W + y);
+    const int y_begin = blockIdx.y * ZOOM_ROWS, y_end = min(H, y_begin + ZOOM_ROWS);
     const uint8_t *src = io.in + (int64_t)blockIdx.z * io.in_fs;
-    const uint8_t *r0 = src + (int64_t)ty.x * io.in_rs, *r1 = src + (int64_t)ty.y * io.in_rs;
     const int last_word = (3 * W - 1) >> 2;
-    uint32_t by[12];
     const int npx = min(4, W - x4);
+    int4 tx[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j < npx) {
-            const int4 tx = __ldg(reinterpret_cast<const int4 *>(tab) + x4 + j);
-            uint32_t a0[3], a1[3], b0[3], b1[3];
+    for (int j = 0; j < 4; ++j) tx[j] = __ldg(reinterpret_cast<const int4 *>(tab) + min(x4 + j, W - 1));
+    int sa[12], sb[12];                       // (a0*xw0 + a1*xw1) >> 4 of source rows ia, ib
+    int ia = -1, ib = -1;
+    auto hrow = [&](int r, int (&s)[12]) {
+        const uint8_t *row = src + (int64_t)r * io.in_rs;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t a0[3], a1[3];
             if (aligned_in) {
-                zoom_taps(reinterpret_cast<const uint32_t *>(r0), tx.x, last_word, a0, a1);
-                zoom_taps(reinterpret_cast<const uint32_t *>(r1), tx.x, last_word, b0, b1);
+                zoom_taps(reinterpret_cast<const uint32_t *>(row), tx[j].x, last_word, a0, a1);
                 // (xi1 == xi0 only where its weight is 0: the neighbour's bytes then multiply 0)
             } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    a0[c] = r0[3 * tx.x + c]; a1[c] = r0[3 * tx.y + c];
-                    b0[c] = r1[3 * tx.x + c]; b1[c] = r1[3 * tx.y + c];
-                }
+                for (int c = 0; c < 3; ++c) { a0[c] = row[3 * tx[j].x + c]; a1[c] = row[3 * tx[j].y + c]; }
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int s0 = (int)a0[c] * tx.z + (int)a1[c] * tx.w;
-                const int s1 = (int)b0[c] * tx.z + (int)b1[c] * tx.w;
-                const int v = ((((ty.z * (s0 >> 4)) >> 16) + ((ty.w * (s1 >> 4)) >> 16) + 2) >> 2);
-                by[3 * j + c] = (uint32_t)min(255, max(0, v));
-            }
-        } else {
-            by[3 * j] = by[3 * j + 1] = by[3 * j + 2] = 0u;
+            for (int c = 0; c < 3; ++c) s[3 * j + c] = ((int)a0[c] * tx[j].z + (int)a1[c] * tx[j].w) >> 4;
         }
-    }
-    uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y * io.out_rs + 3 * x4;
-    if (aligned_out && npx == 4) {
-        uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+    };
+    uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y_begin * io.out_rs + 3 * x4;
+    for (int y = y_begin; y < y_end; ++y, o += io.out_rs) {
+        const int4 ty = __ldg(reinterpret_cast<const int4 *>(tab) + W + y);      // uniform over the block
+        // block-uniform conditions: the empty asm statements keep the compiler from if-converting these
+        // bodies into dozens of predicated instructions that would issue on every row
+        if (ty.x != ia) {
+            asm volatile("");
+            if (ty.x == ib) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
-    } else {
-        for (int q = 0; q < 3 * npx; ++q) o[q] = (uint8_t)by[q];
+                for (int i = 0; i < 12; ++i) sa[i] = sb[i];
+            } else {
+                hrow(ty.x, sa);
+            }
+            ia = ty.x;
+        }
+        if (ty.y != ib) {
+            asm volatile("");
+            if (ty.y == ia) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) sb[i] = sa[i];
+            } else {
+                hrow(ty.y, sb);
+            }
+            ib = ty.y;
+        }
+        uint32_t by[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int v = ((((ty.z * sa[i]) >> 16) + ((ty.w * sb[i]) >> 16) + 2) >> 2);
+            by[i] = (uint32_t)min(255, max(0, v));
+        }
+        if (aligned_out && npx == 4) {
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
+        } else {
+            for (int q = 0; q < 3 * npx; ++q) o[q] = (uint8_t)by[q];
+        }
     }
 }
 
@@ -802,11 +832,11 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
         FrameIO zio{in, out_human, in_frame_stride, in_row_stride, human_frame_stride, human_row_stride, n, H, W};
         AVB_REQUIRE(H <= 65535 && n <= 65535, "frame height / batch too large for one launch");
         AVB_REQUIRE((reinterpret_cast<uintptr_t>(zoom_dev) & 15) == 0, "zoom_dev must be 16-byte aligned");
-        dim3 grid((W + 1023) / 1024, H, n);
+        dim3 grid((W + 511) / 512, (H + ZOOM_ROWS - 1) / ZOOM_ROWS, n);
         const int aligned_out = ((reinterpret_cast<uintptr_t>(out_human) | (uintptr_t)human_frame_stride | (uintptr_t)human_row_stride) & 3) == 0;
         AVB_TIMED("cat_center_zoom", st);
         const int aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_frame_stride | (uintptr_t)in_row_stride) & 3) == 0;
-        center_zoom_kernel<<<grid, 256, 0, st>>>(zio, zoom_dev, aligned_out, aligned_in);
+        center_zoom_kernel<<<grid, 128, 0, st>>>(zio, zoom_dev, aligned_out, aligned_in);
         AVB_CUDA_OK(cudaGetLastError());
     }
     for (int i = 0; i < ksize; ++i) gc.taps[i] = taps_host[i];
