@@ -160,6 +160,7 @@ struct CatProducer {
         seen = 0;
     }
     __device__ __forceinline__ void decode4(uint32_t, uint32_t, uint32_t, float4 &, float4 &, float4 &) {}
+    __device__ __forceinline__ void px(uint32_t, uint32_t, uint32_t, float &, float &, float &) const {}
     // every column of [xa, xb) has zero weight in both eye views: the strip is black
     __device__ __forceinline__ bool all_black(int xa, int xb) const {
         bool any = false;
@@ -406,23 +407,50 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
             __syncthreads();
             if (ib + 1 < n_in_blocks) raw_fetch(yb + G_RB);
             if (Prod::GATHER) {
-                // taps gather from the shared raw tile: a task is one column x 4 rows
-                for (int idx = tid; idx < 2 * C::IN_W; idx += THREADS) {
-                    const int half = idx / C::IN_W, i = idx - half * C::IN_W;
+                // taps gather from the shared raw tile: a task is one column x 4 rows.  The 2 * IN_W tasks
+                // do not divide by the thread count: the tasks beyond the first THREADS are split into
+                // single pixels, so the second round costs one pixel per thread instead of four
+                constexpr int NT = 2 * C::IN_W, REM = NT > THREADS ? NT - THREADS : 0;
+                static_assert((G_RB / 2) * REM <= THREADS, "second producer round must fit one pass");
+                auto gather_px = [&](const typename Prod::Column &col, int i, int r) {
+                    float o0, o1, o2;
+                    prod.template at_row<true>(col, rawt + 16 + r * RAW_PITCH - a0, o0, o1, o2);
+                    S[0 * C::S_PLANE + r * C::S_PITCH + i] = o0;
+                    S[1 * C::S_PLANE + r * C::S_PITCH + i] = o1;
+                    if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + i] = o2;
+                };
+                if (tid < NT) {
+                    const int half = tid / C::IN_W, i = tid - half * C::IN_W;
                     const typename Prod::Column col = prod.column(reflect101(x0 - R + i, W));
 #pragma unroll
-                    for (int rr = 0; rr < G_RB / 2; ++rr) {
-                        const int r = half * (G_RB / 2) + rr;
-                        float o0, o1, o2;
-                        prod.template at_row<true>(col, rawt + 16 + r * RAW_PITCH - a0, o0, o1, o2);
-                        S[0 * C::S_PLANE + r * C::S_PITCH + i] = o0;
-                        S[1 * C::S_PLANE + r * C::S_PITCH + i] = o1;
-                        if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + i] = o2;
-                    }
+                    for (int rr = 0; rr < G_RB / 2; ++rr) gather_px(col, i, half * (G_RB / 2) + rr);
+                }
+                if (REM > 0 && tid < (G_RB / 2) * REM) {
+                    const int idx = THREADS + tid / (G_RB / 2), rr = tid % (G_RB / 2);
+                    const int half = idx / C::IN_W, i = idx - half * C::IN_W;
+                    gather_px(prod.column(reflect101(x0 - R + i, W)), i, half * (G_RB / 2) + rr);
                 }
             } else {
+                // a task is a group of 4 pixels; the tasks beyond the first THREADS are split into single
+                // pixels (second round: one pixel per thread instead of four)
+                constexpr int NTG = G_RB * C::GROUPS, REMG_ALL = NTG > THREADS ? NTG - THREADS : 0;
+                // (measured: splitting pays while the remainder is small; with 56 left-over groups -- 29 taps --
+                // the byte-granular second round costs as much as it saves)
+                constexpr int REMG = REMG_ALL <= 32 ? REMG_ALL : 0;
                 const int sh = (a_byte - a0) & 3, w_off = (a_byte - a0) >> 2;
-                for (int idx = tid; idx < G_RB * C::GROUPS; idx += THREADS) {
+                if (REMG > 0 && tid < 4 * REMG) {
+                    const int idx = NTG - REMG + (tid >> 2), j = tid & 3;
+                    const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
+                    const uint8_t *q = rawt + r * RAW_PITCH + (a_byte - a0) + 3 * (4 * g + j);
+                    const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
+                    prod.seen |= b0 | b1 | b2;
+                    float o0, o1, o2;
+                    prod.px(b0, b1, b2, o0, o1, o2);
+                    S[0 * C::S_PLANE + r * C::S_PITCH + 4 * g + j] = o0;
+                    S[1 * C::S_PLANE + r * C::S_PITCH + 4 * g + j] = o1;
+                    if (NCH == 3) S[2 * C::S_PLANE + r * C::S_PITCH + 4 * g + j] = o2;
+                }
+                for (int idx = tid; idx < NTG - REMG; idx += THREADS) {
                     const int r = idx / C::GROUPS, g = idx - r * C::GROUPS;
                     const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * RAW_PITCH) + w_off + 3 * g;
                     uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
