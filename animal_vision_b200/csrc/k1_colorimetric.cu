@@ -157,29 +157,39 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_contig_kernel(c
     for (int i = 0; i < 9; ++i) m[i] = p.M.m[i];
 
     const int64_t frame_bytes = 3LL * p.io.W * p.io.H;
-    const int64_t total_units = (int64_t)p.units_per_frame * p.io.n;
     const int64_t stride = (int64_t)gridDim.x * K1_WARPS;
-    // unit -> (frame, byte offset); `full` units go through the slab pipeline, frame tails are done in place
-    auto locate = [&](int64_t u, int &frame, int64_t &off, bool &full, bool &skip) {
-        frame = (int)(u / p.units_per_frame);
-        off = (u - (int64_t)frame * p.units_per_frame) * K1_UNIT;
-        full = frame_bytes - off >= K1_UNIT;
-        skip = p.fixup && p.flags[frame] != 0;
+    // A unit is (frame, index within the frame); positions advance incrementally (no 64-bit division per
+    // unit).  `full` units go through the slab pipeline, frame tails (< 1536 B) are done in place.
+    const int upf = p.units_per_frame;
+    struct Pos { int frame, uif; };
+    auto advance = [&](Pos &q) {
+        int64_t v = (int64_t)q.uif + stride;
+        while (v >= upf) { v -= upf; ++q.frame; }
+        q.uif = (int)v;
     };
-    auto prefetch = [&](int64_t u, int slot) {       // lane 0 only
-        if (u >= total_units) return;
-        int frame; int64_t off; bool full, skip;
-        locate(u, frame, off, full, skip);
-        if (full && !skip) k1_bulk_load(sm.in[warp][slot], p.io.in + (int64_t)frame * p.io.in_fs + off, K1_UNIT, &sm.bar[warp][slot]);
+    auto is_full = [&](const Pos &q) { return frame_bytes - (int64_t)q.uif * K1_UNIT >= K1_UNIT; };
+    auto is_skip = [&](const Pos &q) { return p.fixup && p.flags[q.frame] != 0; };
+    auto prefetch = [&](const Pos &q, int slot) {       // lane 0 only
+        if (q.frame >= p.io.n) return;
+        if (is_full(q) && !is_skip(q))
+            k1_bulk_load(sm.in[warp][slot], p.io.in + (int64_t)q.frame * p.io.in_fs + (int64_t)q.uif * K1_UNIT, K1_UNIT, &sm.bar[warp][slot]);
     };
     uint32_t seen = 0, phases = 0;                     // bit s: parity the next wait on slot s expects
     int flagged_frame = -1, slot = 0;
-    int64_t u = (int64_t)blockIdx.x * K1_WARPS + warp;
-    if (lane == 0) prefetch(u, 0);
-    for (; u < total_units; u += stride) {
-        int frame; int64_t off; bool full, skip;
-        locate(u, frame, off, full, skip);
-        if (lane == 0) prefetch(u + stride, slot ^ (full && !skip ? 1 : 0));     // a unit that uses no slab leaves the slot to its successor
+    Pos cur, nxt;
+    {
+        const int64_t u0 = (int64_t)blockIdx.x * K1_WARPS + warp;
+        cur.frame = (int)(u0 / upf);
+        cur.uif = (int)(u0 - (int64_t)cur.frame * upf);
+    }
+    if (lane == 0) prefetch(cur, 0);
+    nxt = cur;
+    for (; cur.frame < p.io.n; cur = nxt) {
+        advance(nxt);
+        const int frame = cur.frame;
+        const int64_t off = (int64_t)cur.uif * K1_UNIT;
+        const bool full = is_full(cur), skip = is_skip(cur);
+        if (lane == 0) prefetch(nxt, slot ^ (full && !skip ? 1 : 0));     // a unit that uses no slab leaves the slot to its successor
         if (skip) continue;
         if (frame != flagged_frame) {   // flush the per-frame "byte >= 2" accumulator
             if (p.flags && !p.fixup && flagged_frame >= 0 && __any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0)

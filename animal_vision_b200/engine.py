@@ -69,9 +69,15 @@ class Engine:
         return v
 
     def flags(self, n: int):
-        if self._flags is None or self._flags.numel() < n:
-            self._flags = self.torch.zeros(max(n, 64), dtype=self.torch.int32, device=self.device)
-        return self._flags
+        """Per-frame flag / scratch words.  One buffer PER STREAM: batches of different species may run
+        concurrently on different streams and must not share scratch."""
+        key = self.stream_ptr()
+        if self._flags is None:
+            self._flags = {}
+        buf = self._flags.get(key)
+        if buf is None or buf.numel() < n:
+            buf = self._flags[key] = self.torch.zeros(max(n, 64), dtype=self.torch.int32, device=self.device)
+        return buf
 
     def stream_ptr(self) -> int:
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -168,10 +174,11 @@ class Engine:
         need = int(self.lib.avb_uv_workspace_bytes(n, h, w, int(map_mode)))
         if need <= 0:
             raise AvbError("avb_uv_workspace_bytes: bad arguments")
-        ws = self._cache.get("uv_ws")
+        ws_key = ("uv_ws", self.stream_ptr())                 # per stream, like flags()
+        ws = self._cache.get(ws_key)
         if ws is None or ws.numel() < need:
-            self._cache["uv_ws"] = None
-            ws = self._cache["uv_ws"] = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+            self._cache[ws_key] = None
+            ws = self._cache[ws_key] = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
         M3 = np.ascontiguousarray(M3, np.float32)
         taps = np.ascontiguousarray(blur_taps, np.float32)
         mp = None if map_params is None else np.ascontiguousarray(map_params, np.float32)

@@ -316,9 +316,43 @@ def run_b200(args):
     torch.cuda.synchronize()
     px_step = nf * H * W                                   # per GPU
 
-    def step():
+    # The three species batches are independent: each runs on its own stream (fork / join with events on
+    # the timing stream), so the partially filled last wave of one kernel overlaps the next species' work.
+    nsplit = max(0, args.streams)
+    side = {(sp, k): torch.cuda.Stream(device=dev) for sp in SPECIES for k in range(nsplit)} if nsplit else None
+
+    def run_part(sp, k, parts):
+        n = dev_in[sp].shape[0]
+        a, b = n * k // parts, n * (k + 1) // parts
+        if a == b:
+            return
+        o = dev_out[sp]
+        species[sp].visualize_batch(dev_in[sp][a:b], out=(o[0][a:b], o[1][a:b]) if isinstance(o, tuple) else o[a:b])
+
+    def step(single: bool = False):
+        if side is None or single:
+            for sp in SPECIES:
+                run_part(sp, 0, 1)
+            return
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for k in range(nsplit):
+            for sp in SPECIES:
+                st = side[(sp, k)]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    run_part(sp, k, nsplit)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                main.wait_event(done)
+
+    def checksum():
+        outs = []
         for sp in SPECIES:
-            species[sp].visualize_batch(dev_in[sp], out=dev_out[sp])
+            o = dev_out[sp]
+            outs += list(o) if isinstance(o, tuple) else [o]
+        return [int(t.reshape(-1).view(torch.int32).sum(dtype=torch.int64).item()) for t in outs]
 
     # ---- device-resident throughput ("value")
     for _ in range(args.warmup):
@@ -339,9 +373,13 @@ def run_b200(args):
 
     # ---- per-kernel timing over the same steps (roofline leg): CUDA events around every launch
     prof_steps = max(1, min(args.steps, 3))
+    sum_streams = checksum()                        # outputs of the concurrent steps ...
+    step(single=True)                               # per-kernel times are taken on ONE stream: no overlap between kernels
+    torch.cuda.synchronize()
+    streams_ok = checksum() == sum_streams          # ... equal those of a single-stream step
     lib.avb_profile_begin()
     for _ in range(prof_steps):
-        step()
+        step(single=True)
     cap = 4096
     names = C.create_string_buffer(cap * 48)
     msbuf = (C.c_float * cap)()
@@ -425,6 +463,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
                    "resolution": f"{W}x{H}", "frames_per_gpu": nf, "species": list(SPECIES), "parallelism": f"frame-sharded x{world}, no collective",
+                   "streams": f"{3 * nsplit} CUDA streams: every species batch in {nsplit} part(s), fork/join on the timed stream; outputs equal the single-stream step: {streams_ok}" if nsplit else "single stream",
                    "l2": f"inputs {nf * H * W * 3 / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
                    "normalisation": "AVB_NORM_AUTO (reference semantics, decided per frame on device)"},
         "fps_4k": value * 1e6 / (H4K * W4K),
@@ -466,6 +505,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the 3840-wide CPU-baseline sample frames")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="streams per species batch in the device-resident step (the batch is cut into that many parts); 0: a single stream")
     ap.add_argument("--mstpp-batch", type=int, default=4, help="482x512 patches per GPU in the MST++ leg (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3:
