@@ -277,10 +277,15 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout must carry the ONE JSON line and nothing else, but native libraries (NCCL's "NCCL version ..."
+    # banner) print to file descriptor 1: park the real stdout, point fd 1 at stderr for the whole run and
+    # write the JSON line to the parked descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -488,7 +493,7 @@ def run_b200(args):
             "cores": threads.get("sched_affinity") or threads.get("os_cpu_count") or 1, "kind": "port",
             "sample": f"1 Dog + 1 Cat + 1 HoneyBee frame of {rows}x{W4K} (full-width band of a 4K frame), {dt:.1f} s of CPU work, oracle port with OpenCV/BLAS threads = all cores",
             "threads": threads}
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
