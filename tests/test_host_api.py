@@ -59,3 +59,34 @@ def test_batch_feed_gathers_frames_in_order():
         seen += [int(f[0, 0, 0]) for f in b]
         assert b.shape[1:] == (6, 8, 3) and b.dtype == np.uint8
     assert sizes == [3, 3, 1] and seen == list(range(7))
+
+
+@pytest.mark.gpu
+def test_species_batches_on_concurrent_streams_match_serial_results():
+    """Independent batches may be issued on different CUDA streams (bench.py does): every entry point is
+    stream ordered and the engine keeps its scratch (normalisation flags, K3 workspace) per stream."""
+    import torch
+    import animal_vision_b200.animals as A
+    rng = np.random.default_rng(21)
+    frames = {name: torch.from_numpy(rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)).cuda()
+              for name in ("Dog", "Cat", "HoneyBee", "Cow")}
+    frames["Dog"][1] = frames["Dog"][1] // 200          # a frame whose maximum is <= 1: the other normalisation branch
+    species = {name: getattr(A, name)() for name in frames}
+    serial = {}
+    for name, sp in species.items():
+        base, out = sp.visualize_batch(frames[name])
+        serial[name] = (base.clone() if name == "Cat" else None, out.clone())
+    torch.cuda.synchronize()
+    streams = {name: torch.cuda.Stream() for name in frames}
+    got = {}
+    for _ in range(3):                                   # a few rounds so that launches really interleave
+        for name, sp in species.items():
+            streams[name].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[name]):
+                got[name] = sp.visualize_batch(frames[name])
+    torch.cuda.synchronize()
+    for name in frames:
+        base, out = got[name]
+        assert torch.equal(out, serial[name][1]), name
+        if name == "Cat":
+            assert torch.equal(base, serial[name][0]), name
