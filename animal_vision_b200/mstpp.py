@@ -93,7 +93,8 @@ class MSTPlusPlus:
             rc = self.eng.lib.avb_mstpp_create(flat.ctypes.data_as(C.c_void_p), flat.size, C.byref(h))
         check(rc, "avb_mstpp_create")
         self._h = h
-        self._ws = None
+        self._ws = {}              # workspace per CUDA stream: forwards on different streams may overlap
+        self._streams = []
 
     def close(self):
         if getattr(self, "_h", None):
@@ -106,7 +107,7 @@ class MSTPlusPlus:
         except Exception:
             pass
 
-    def _run(self, frames, pad_multiple: int, centred: bool):
+    def _run(self, frames, pad_multiple: int, centred: bool, out=None):
         """frames: CUDA tensor [N,H,W,3] float32 (in [0,1]) or uint8 -> float32 [N,H,W,31]."""
         t = self.eng.torch
         if not (isinstance(frames, t.Tensor) and frames.is_cuda and frames.dim() == 4 and frames.shape[3] == 3
@@ -117,13 +118,45 @@ class MSTPlusPlus:
         need = int(self.eng.lib.avb_mstpp_workspace_bytes(n, h, w, pad_multiple, int(centred)))
         if need <= 0:
             raise AvbError("avb_mstpp_workspace_bytes: bad geometry")
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = t.empty(need, dtype=t.uint8, device=self.eng.device)
-        out = t.empty((n, h, w, N_FEAT), dtype=t.float32, device=self.eng.device)
+        key = self.eng.stream_ptr()
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            self._ws[key] = None
+            ws = self._ws[key] = t.empty(need, dtype=t.uint8, device=self.eng.device)
+        if out is None:
+            out = t.empty((n, h, w, N_FEAT), dtype=t.float32, device=self.eng.device)
+        assert out.is_contiguous() and tuple(out.shape) == (n, h, w, N_FEAT) and out.dtype == t.float32
         rc = self.eng.lib.avb_mstpp_forward(self._h, frames.data_ptr(), int(frames.dtype == t.uint8), out.data_ptr(),
-                                            n, h, w, pad_multiple, int(centred), self._ws.data_ptr(), self.eng.stream_ptr())
+                                            n, h, w, pad_multiple, int(centred), ws.data_ptr(), self.eng.stream_ptr())
         check(rc, "avb_mstpp_forward")
+        return out
+
+    def forward_nhwc_streams(self, frames, streams: int = 2):
+        """forward_nhwc with the batch cut into `streams` parts that run concurrently on their own CUDA
+        streams (fork / join on the current stream).  Patches are independent -- the attention statistics
+        are per patch -- and the coarse levels of the network are latency bound, so overlapping forwards
+        raises the throughput of a batch."""
+        t = self.eng.torch
+        n = frames.shape[0]
+        parts = max(1, min(int(streams), n))
+        if parts == 1:
+            return self._run(frames, 8, False)
+        frames = frames.contiguous()
+        while len(self._streams) < parts:
+            self._streams.append(t.cuda.Stream(device=self.eng.device))
+        out = t.empty((n,) + tuple(frames.shape[1:3]) + (N_FEAT,), dtype=t.float32, device=self.eng.device)
+        main = t.cuda.current_stream(self.eng.device)
+        fork = t.cuda.Event()
+        fork.record(main)
+        for k in range(parts):
+            a, b = n * k // parts, n * (k + 1) // parts
+            st = self._streams[k]
+            st.wait_event(fork)
+            with t.cuda.stream(st):
+                self._run(frames[a:b], 8, False, out=out[a:b])
+                done = t.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
         return out
 
     def forward_nhwc(self, frames):

@@ -106,3 +106,20 @@ def test_safe_norm_maps():
     for k in range(4):
         ref = uv.safe_norm(a[..., k])
         assert np.array_equal(got[..., k], ref), k
+
+
+def test_concurrent_forwards_match_single_stream():
+    """forward_nhwc_streams cuts the batch into parts that run on their own streams (own workspaces);
+    results agree with the single-stream forward up to the order of the float atomics in the attention
+    statistics."""
+    import torch
+    from animal_vision_b200.mstpp import MSTPlusPlus
+    from oracle import mstpp as O
+    net = MSTPlusPlus(O.make_weights(0))
+    x = torch.rand(5, 64, 72, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    ref = net.forward_nhwc(x)
+    for parts in (2, 3, 8):
+        got = net.forward_nhwc_streams(x, parts)
+        torch.cuda.synchronize()
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3, parts

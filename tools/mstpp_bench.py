@@ -61,6 +61,18 @@ def main():
         for i in range(min(nrec, 40)):
             nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
             print(f"    {i:3d} {nm:22s} {msbuf[i] * 1e3:8.1f} us")
+    for parts in (2, 4):
+        if n >= parts:
+            for _ in range(2):
+                y2 = net.forward_nhwc_streams(x, parts)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                y2 = net.forward_nhwc_streams(x, parts)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / iters
+            print(f"  {parts} streams: {ms2:.3f} ms/forward, {n / ms2 * 1e3:.1f} patch/s, max |diff| / max |y| vs single stream: {float((y2 - y).abs().max() / y.abs().max()):.2e} (float atomics in the attention statistics: not bitwise)")
     if check:
         xs = x[:1].cpu().permute(0, 3, 1, 2)
         ref = O.forward(xs, sd).permute(0, 2, 3, 1).numpy()
