@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmP &p, uint32_t tmem_d, i
         crop_ok = (unsigned)cy < (unsigned)p.Hreal && (unsigned)cx < (unsigned)p.Wreal;
         obase = (((long long)b * p.Hreal + cy) * p.Wreal + cx) * NF;
     }
-#pragma unroll (PRE ? 4 : 1)
+#pragma unroll (PRE ? 4 : 2)
     for (int c = 0; c < HALF; c += 16) {
         float v[16];
         tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col0 + c), v);     // all lanes: .sync.aligned
@@ -772,11 +772,15 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
 // ------------------------------------------------------------------------------------ attention statistics
 // Per image and head: G[i][j] = sum_px k[px][i] q[px][j], nk[i] = sum k^2, nq[j] = sum q^2
 // (MST_Plus_Plus.py:127-129: the L2 normalisation runs over ALL pixels, so the reduction is global).
-// stats layout per (image, head): 32 x 32 floats; row i < 31, col j < 31: G; [i][31] = nk[i];
+// Accumulation across CTAs is in 64-bit FIXED POINT (2^-24 units, integer atomics): integer addition is
+// associative, so the statistics -- and with them the whole forward -- are bit-reproducible from run to
+// run; float atomics made two runs differ by 2e-3 of the output range after 15 bf16 layers.
+// stats layout per (image, head): 32 x 32 entries; row i < 31, col j < 31: G; [i][31] = nk[i];
 // [31][j] = nq[j].
+constexpr double STAT_SCALE = 16777216.0;       // 2^24: |sums| < 2^39 fit an int64 with room to spare
 struct AttnStatP {
     const bf16 *qkv;     // [B*rows, 3*Cp]: q | k | v
-    float *stats;        // [B][heads][32][32], zeroed
+    long long *stats;    // [B][heads][32][32] fixed point (STAT_SCALE), zeroed
     int rows, Cp, heads, px_per_cta;
 };
 // 256 threads = 4 pixel groups x (8 x 8) threads, each thread a 4 x 4 register tile of G: per pixel
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; ++j) rn[(grp * 2 + 1) * 32 + 4 * tj + j] = nq[j];
     __syncthreads();
-    float *out = p.stats + ((long long)b * p.heads + head) * 1024;
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(p.stats) + ((long long)b * p.heads + head) * 1024;
     for (int e = tid; e < 1024; e += 256) {
         const int i = e >> 5, j = e & 31;
         float v;
@@ -855,14 +859,14 @@ __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__
         else if (i < NF) v = rn[i] + rn[64 + i] + rn[128 + i] + rn[192 + i];                  // [i][31] = |k_i|^2
         else if (j < NF) v = rn[32 + j] + rn[96 + j] + rn[160 + j] + rn[224 + j];             // [31][j] = |q_j|^2
         else v = 0.f;
-        atomicAdd(out + e, v);
+        atomicAdd(out + e, (unsigned long long)__double2ll_rn((double)v * STAT_SCALE));      // two's complement: negative sums wrap correctly
     }
 }
 
 // attn = softmax_j(rescale * G_ij / (max(|k_i|,1e-12) max(|q_j|,1e-12)))  (:127-131), then
 // M[co][h*31+j] = sum_i Wproj[co][h*31+i] attn_h[i][j]  -> bf16 [B][Cp][Cp] (zero padded).
 struct AttnFinP {
-    const float *stats; const float *rescale; const float *wproj;   // wproj fp32 [c][c]
+    const long long *stats; const float *rescale; const float *wproj;   // wproj fp32 [c][c]
     bf16 *M;             // [B][Cp][Cp]
     int c, Cp, heads;
 };
@@ -880,19 +884,19 @@ __global__ void __launch_bounds__(1024) attn_finalize_kernel(const __grid_consta
     }
     if (tid < p.heads * 32) {
         const int h = tid >> 5, j = tid & 31;
-        const float *S = p.stats + ((long long)b * p.heads + h) * 1024;
-        rq[h][j] = j < NF ? 1.0f / fmaxf(sqrtf(S[31 * 32 + j]), 1e-12f) : 0.f;
+        const long long *S = p.stats + ((long long)b * p.heads + h) * 1024;
+        rq[h][j] = j < NF ? 1.0f / fmaxf(sqrtf((float)((double)S[31 * 32 + j] * (1.0 / STAT_SCALE))), 1e-12f) : 0.f;
     }
     __syncthreads();
     // softmax rows: one thread per (head, i)
     if (tid < p.heads * NF) {
         const int h = tid / NF, i = tid - h * NF;
-        const float *S = p.stats + ((long long)b * p.heads + h) * 1024;
-        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf(S[i * 32 + 31]), 1e-12f);
+        const long long *S = p.stats + ((long long)b * p.heads + h) * 1024;
+        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf((float)((double)S[i * 32 + 31] * (1.0 / STAT_SCALE))), 1e-12f);
         float row[NF], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-            row[j] = S[i * 32 + j] * (sc * rq[h][j]);
+            row[j] = (float)((double)S[i * 32 + j] * (1.0 / STAT_SCALE)) * (sc * rq[h][j]);
             mx = fmaxf(mx, row[j]);
         }
         float sum = 0.f;
@@ -1132,7 +1136,8 @@ static bool pack_model(Packer &pk, Model &M, const float *params, int64_t count)
 
 // ------------------------------------------------------------------------------------ host: schedule
 struct Workspace {
-    float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0, *stats;
+    float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0;
+    long long *stats;
     bf16 *qkv, *p1, *p2, *ln, *hid1, *hid2, *M;
     size_t bytes;
 };
@@ -1143,7 +1148,8 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 #define WS_F(name, elems) { float *ptr = (float *)take((elems) * 4); if (w) w->name = ptr; }
 #define WS_B(name, elems) { bf16 *ptr = (bf16 *)take((elems) * 2); if (w) w->name = ptr; }
     WS_F(x0, n0 * 32) WS_F(hA, n0 * 32) WS_F(hB, n0 * 32) WS_F(f0, n0 * 32) WS_F(f1, n1 * 64) WS_F(f2, n2 * 128)
-    WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32) WS_F(stats, (size_t)B * 4 * 1024)
+    WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32)
+    { long long *ptr = (long long *)take((size_t)B * 4 * 1024 * 8); if (w) w->stats = ptr; }
     WS_B(qkv, n0 * 96) WS_B(p1, n0 * 32) WS_B(p2, n0 * 32) WS_B(ln, n0 * 32) WS_B(hid1, n0 * 128) WS_B(hid2, n0 * 128)
     WS_B(M, (size_t)B * 128 * 128)
 #undef WS_F
@@ -1267,13 +1273,15 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         GemmP p = gemm_defaults();
         p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.Np = 3 * Cp; p.rows = rows;
         p.out = ws.qkv; p.ldo = 3 * Cp; p.out_bf16 = 1;
-        p.zero_ptr = ws.stats; p.zero_n = cx.B * m.heads * 1024;       // the statistics pass accumulates with atomics
+        p.zero_ptr = reinterpret_cast<float *>(ws.stats); p.zero_n = 2 * cx.B * m.heads * 1024;      // int64 entries, accumulated with atomics
         launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_qkv");
     }
     // Gram + norms over all pixels
     {
         AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
-        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 4 / std::max(1, cx.B * m.heads)));
+        // the split depends on the patch geometry only, never on the batch size: a patch gives the same bits
+        // whether it runs alone, in a batch, or in one of several concurrent forwards
+        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 4 / std::max(1, m.heads)));
         p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
         AVB_TIMED("k4_attn_stats", cx.st);

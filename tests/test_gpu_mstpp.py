@@ -109,9 +109,9 @@ def test_safe_norm_maps():
 
 
 def test_concurrent_forwards_match_single_stream():
-    """forward_nhwc_streams cuts the batch into parts that run on their own streams (own workspaces);
-    results agree with the single-stream forward up to the order of the float atomics in the attention
-    statistics."""
+    """forward_nhwc_streams cuts the batch into parts that run on their own streams (own workspaces).
+    The forward is bit-reproducible and batch invariant (the attention statistics accumulate in 64-bit
+    fixed point with a split that depends on the patch geometry only), so the results are identical."""
     import torch
     from animal_vision_b200.mstpp import MSTPlusPlus
     from oracle import mstpp as O
@@ -122,4 +122,5 @@ def test_concurrent_forwards_match_single_stream():
         got = net.forward_nhwc_streams(x, parts)
         torch.cuda.synchronize()
         assert got.shape == ref.shape
-        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3, parts
+        assert torch.equal(got, ref), parts
+    assert torch.equal(net.forward_nhwc(x[2:3]), ref[2:3]), "a patch alone gives the same bits as inside a batch"
