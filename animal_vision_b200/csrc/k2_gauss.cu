@@ -592,19 +592,32 @@ static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, 
     return AVB_OK;
 }
 
-// rows per segment: enough CTAs to fill the machine a few times over, but tall enough that the
-// 2*RP halo rows re-produced per segment stay a small fraction
-static int pick_seg_h(int n, int H, int W, int radius) {
-    const int strips = (W + G_TW - 1) / G_TW;
-    const long target = 4L * 3 * sm_count();                 // ~4 waves at 3 CTAs/SM
-    long segs = (target + (long)strips * n - 1) / ((long)strips * n);
-    const int min_h = 16 * radius;                             // halo rows re-produced per segment <= 12.5 %
-    long max_segs = (H + min_h - 1) / min_h;
-    if (segs > max_segs) segs = max_segs;
-    if (segs < 1) segs = 1;
-    int seg_h = (int)((H + segs - 1) / segs);
-    seg_h = (seg_h + G_RB - 1) / G_RB * G_RB;
-    return seg_h;
+// Rows per segment.  Every CTA of a launch does the same amount of work, so the launch runs in waves of
+// (SMs x resident CTAs per SM): the segment count is chosen to maximise
+//     (fill of the last wave) x (useful rows / produced rows),
+// i.e. it trades the 2R halo rows re-produced per segment against a nearly empty last wave (1 800 CTAs on
+// 296 slots run seven waves, the seventh 8 % full).
+static int pick_seg_h(int n, int H, int W, int radius, int ctas_per_sm) {
+    const long strips = (long)((W + G_TW - 1) / G_TW) * n;
+    const long slots = (long)sm_count() * ctas_per_sm;
+    const int min_h = std::max(G_RB, 8 * radius);               // halo rows re-produced per segment <= 25 %
+    const int max_segs = std::max(1, (H + min_h - 1) / min_h);
+    int best = 1;
+    double best_score = -1.0;
+    for (int segs = 1; segs <= max_segs && segs <= 64; ++segs) {
+        int seg_h = (H + segs - 1) / segs;
+        seg_h = (seg_h + G_RB - 1) / G_RB * G_RB;
+        const long real_segs = (H + seg_h - 1) / seg_h;
+        const long ctas = strips * real_segs;
+        const long waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);
+        const double useful = (double)seg_h / (double)(seg_h + 2 * radius);
+        // a launch of less than ~2 waves cannot hide its ramp-up: prefer more, smaller CTAs there
+        const double score = fill * useful * (waves >= 2 ? 1.0 : 0.85);
+        if (score > best_score + 1e-9) { best_score = score; best = segs; }
+    }
+    int seg_h = (H + best - 1) / best;
+    return (seg_h + G_RB - 1) / G_RB * G_RB;
 }
 
 // T (3x3, applied as out = T lin) = P (3x2) Q (2x3) if it has rank <= 2: Q = the two most independent
@@ -645,7 +658,7 @@ static bool rank2_factor(const float *T, float *Q /*6*/, float *P /*6*/) {
 
 template <class Prod>
 static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp, cudaStream_t st) {
-    gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius);
+    gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius, radius <= G_MINB3_R ? 3 : G_MINB);
     float Q[6];
     const float T[9] = {pp.M.m[0], pp.M.m[1], pp.M.m[2], pp.M.m[3], pp.M.m[4], pp.M.m[5], pp.M.m[6], pp.M.m[7], pp.M.m[8]};
     const bool two = rank2_factor(T, Q, gc.P);
