@@ -44,6 +44,9 @@ constexpr int UV_RH = UV_RH_ROWS;        // output rows per strip
 #ifndef UV_MINB
 #define UV_MINB 4
 #endif
+#ifndef UV_HIST_WAVES
+#define UV_HIST_WAVES 1
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { MAP_OPPONENT = 0, MAP_FALSECOLOR = 1, MAP_MATRIX = 2, MAP_PURPLE = 3, MAP_MIXED = 4 };
@@ -895,7 +898,7 @@ template <int QS, int R, bool BANDS>
 static int launch_percentiles(const UvParams &p, cudaStream_t st) {
     {
         AVB_TIMED("k3_uv_hist", st);
-        uv_hist_kernel<QS, R, BANDS><<<walk_grid(p, 4), UV_THREADS, 0, st>>>(p);
+        uv_hist_kernel<QS, R, BANDS><<<walk_grid(p, 4 * UV_HIST_WAVES), UV_THREADS, 0, st>>>(p);
     }
     {
         AVB_TIMED("k3_uv_scan", st);
