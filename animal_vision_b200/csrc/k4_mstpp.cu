@@ -602,6 +602,133 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_pw_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------ row-streaming 3x3 convolution
+// Conv2d(32, 32, 3, padding 1) on the full-resolution level (embedding / mapping convs of every MST
+// body and conv_out).  The K-chunked kernel above gathers every input pixel nine times through L2
+// (288 MB per launch, ~3.6 TB/s: 75-90 us).  Here a CTA owns a strip of 128 columns and walks down a
+// segment of rows; each input row enters shared memory ONCE (fp32 -> bf16, canonical K-major rows of
+// 16 bytes, 130 pixels incl. the x halo, zeros outside the map) into a ring of four row slots, and an
+// output row is 9 taps x 2 tcgen05.mma (M = 128 pixels, N = 32, K = 16) whose A descriptors simply
+// start (dx * 16 B) into the slot of row y + dy - 1 -- the canonical layout is linear in the pixel
+// index, so a shifted window is a shifted start address.  Software pipeline per output row:
+//   store row y+1 (registers -> slot), barrier, issue the 18 MMAs of row y into TMEM buffer y&1,
+//   fetch row y+2 (registers), wait for row y-1, epilogue of row y-1 (residual, store / crop).
+constexpr int C3_PXP = 138;                       // pixels per slot row (130 used); 138 staggers the four k-chunks over the banks
+constexpr int C3_LBO = C3_PXP * 16;               // bytes between k-chunks of 8 channels
+constexpr int C3_SLOT = 4 * C3_LBO;               // 32 channels
+constexpr int C3_SLOTS = 4;
+constexpr int C3_B_LBO = (32 / 8) * 128;          // weights: 32 output channels per k-chunk
+constexpr int C3_SMEM = C3_SLOTS * C3_SLOT + 36 * C3_B_LBO;
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) conv3_stream_kernel(const __grid_constant__ GemmP p, int seg_rows) {
+    pdl_wait();
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *ring = dsm;                                   // [C3_SLOTS][4 k-chunks][C3_PXP][16 B]
+    uint8_t *Bs = dsm + C3_SLOTS * C3_SLOT;                // [36 k-chunks][32 n][16 B]
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, x0 = blockIdx.x * BM;
+    const int H = p.Hi, W = p.Wi;
+    const int y_begin = blockIdx.y * seg_rows, y_end = min(H, y_begin + seg_rows);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // resident weights: [32][288] bf16 -> canonical K-major
+    for (int idx = tid; idx < 32 * 36; idx += GEMM_THREADS) {
+        const int n = idx / 36, q = idx - n * 36;
+        *reinterpret_cast<uint4 *>(Bs + q * C3_B_LBO + (n >> 3) * 128 + (n & 7) * 16) =
+            __ldg(reinterpret_cast<const uint4 *>(p.W + (long long)n * 288) + q);
+    }
+    // ---- row loader: 130 pixels x 32 fp32 channels = 1040 float4 quads -> 5 per thread (last partial)
+    constexpr int QPT = (130 * 8 + GEMM_THREADS - 1) / GEMM_THREADS;       // 5
+    float4 rreg[QPT];
+    const float *A = reinterpret_cast<const float *>(p.A1) + (long long)b * H * W * 32;
+    auto fetch = [&](int y) {
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int idx = tid + u * GEMM_THREADS;         // quad index: pixel idx / 8, channels 4*(idx % 8) ..
+            const int px = idx >> 3, xx = x0 - 1 + px;
+            const bool ok = idx < 130 * 8 && (unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W;
+            rreg[u] = ok ? __ldg(reinterpret_cast<const float4 *>(A + ((long long)y * W + xx) * 32) + (idx & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store = [&](int y) {                              // row y -> slot y & 3 (y may be -1: slot 3)
+        uint8_t *slot = ring + ((y + 4) & 3) * C3_SLOT;
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int idx = tid + u * GEMM_THREADS;
+            if (idx < 130 * 8) {
+                const int px = idx >> 3, q = idx & 7;      // channels 4q .. 4q+3: k-chunk q/2, bytes 8*(q&1) ..
+                *reinterpret_cast<uint2 *>(slot + (q >> 1) * C3_LBO + px * 16 + (q & 1) * 8) =
+                    make_uint2(pack_bf16(rreg[u].x, rreg[u].y), pack_bf16(rreg[u].z, rreg[u].w));
+            }
+        }
+    };
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    auto issue = [&](int y, uint32_t tmem_d) {             // one thread: 9 taps x 2 MMAs of output row y
+        tc_fence_after();
+        const uint32_t r0 = smem_u32(ring), b0 = smem_u32(Bs);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t % 3;
+            const uint32_t a0 = r0 + (uint32_t)(((y + dy - 1 + 4) & 3) * C3_SLOT) + (uint32_t)(dx * 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                mma_f16(tmem_d + (uint32_t)((y & 1) * 32), make_desc(a0 + 2 * j * C3_LBO, C3_LBO, 128),
+                        make_desc(b0 + (4 * t + 2 * j) * C3_B_LBO, C3_B_LBO, 128), IDESC, (t > 0 || j > 0) ? 1u : 0u);
+        }
+        mma_commit(&mbar[y & 1]);
+    };
+
+    fetch(y_begin - 1);
+    store(y_begin - 1);
+    fetch(y_begin);
+    store(y_begin);
+    fetch(y_begin + 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    uint32_t ph[2] = {0u, 0u};
+    for (int y = y_begin; y < y_end; ++y) {
+        // slot (y+1)&3 last held row y-3, read by the MMAs of row y-2 whose completion was awaited in
+        // iteration y-1; TMEM buffer y&1 was drained by the epilogue of row y-2 (iteration y-1)
+        store(y + 1);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) issue(y, tmem_d);
+        if (y + 1 < y_end) fetch(y + 2);
+        if (y > y_begin) {
+            const int yp = y - 1;
+            mbar_wait(&mbar[yp & 1], ph[yp & 1]);
+            ph[yp & 1] ^= 1u;
+            tc_fence_after();
+            epilogue_tile<32, EPI>(p, tmem_d + (uint32_t)((yp & 1) * 32), b, yp * W + x0, 0, warp, lane);
+        }
+    }
+    {
+        const int yp = y_end - 1;
+        mbar_wait(&mbar[yp & 1], ph[yp & 1]);
+        tc_fence_after();
+        epilogue_tile<32, EPI>(p, tmem_d + (uint32_t)((yp & 1) * 32), b, yp * W + x0, 0, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(64) : "memory");
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------ conv_in
@@ -1247,12 +1374,50 @@ static GemmP gemm_defaults() {
     return p;
 }
 
+// 3x3 conv on [B, H, W, 32]: the row-streaming kernel when the map is a whole number of 128-column strips,
+// the K-chunked implicit GEMM otherwise
+static void launch_conv3(Ctx &cx, const GemmP &p, const char *name) {
+    const int H = p.Hi, W = p.Wi;
+    if (W % BM != 0 || H < 2) {
+        launch_gemm<false, MODE_C3>(cx, p, name);
+        return;
+    }
+    // rows per CTA: ~2 CTAs per SM over the batch, at least 8 rows (2 halo rows are re-read per segment)
+    const int strips = W / BM;
+    int segs = std::max(1, (2 * sm_count()) / std::max(1, strips * cx.B));
+    int seg_rows = std::max(8, (H + segs - 1) / segs);
+    segs = (H + seg_rows - 1) / seg_rows;
+    const dim3 grid(strips, segs, cx.B);
+    const int epi = tc::epi_of(p);
+    AVB_TIMED(name, cx.st);
+#define C3_CASE(EPI_) \
+    if (epi == (EPI_) && p.out_mode != OUT_CROP) { \
+        static bool attr_set = false; \
+        if (!attr_set) { cudaFuncSetAttribute(tc::conv3_stream_kernel<(EPI_)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::C3_SMEM); attr_set = true; } \
+        cudaLaunchConfig_t cfg = {}; cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = tc::C3_SMEM; cfg.stream = cx.st; \
+        cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1; \
+        cfg.attrs = attr; cfg.numAttrs = 1; \
+        cudaLaunchKernelEx(&cfg, tc::conv3_stream_kernel<(EPI_)>, p, seg_rows); \
+        return; \
+    }
+    C3_CASE(0) C3_CASE(tc::EPI_RES1)
+#undef C3_CASE
+    {   // conv_out: cropped store (runtime epilogue flags)
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(tc::conv3_stream_kernel<tc::EPI_RUNTIME>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::C3_SMEM); attr_set = true; }
+        cudaLaunchConfig_t cfg = {}; cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = tc::C3_SMEM; cfg.stream = cx.st;
+        cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, tc::conv3_stream_kernel<tc::EPI_RUNTIME>, p, seg_rows);
+    }
+}
+
 static void conv3x3(Ctx &cx, const float *in, const bf16 *w, float *out, const float *res, int H, int W) {
     GemmP p = gemm_defaults();
     p.A1 = in; p.lda1 = 32; p.K1 = p.K = 288; p.W = w; p.Np = 32; p.rows = H * W;
     p.Hi = p.Ho = H; p.Wi = p.Wo = W; p.Cpin = 32;
     p.res1 = res; p.ldr1 = 32; p.out = out; p.ldo = 32;
-    launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
+    launch_conv3(cx, p, "k4_conv3x3");
 }
 
 static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const float *w, int H, int W, int Cp, int gelu_out, const char *name) {
@@ -1442,7 +1607,7 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
         p.A1 = hin; p.lda1 = 32; p.K1 = p.K = 288; p.W = M->conv_out; p.Np = 32; p.rows = Hp * Wp;
         p.Hi = p.Ho = Hp; p.Wi = p.Wo = Wp; p.Cpin = 32;
         p.res1 = ws.x0; p.ldr1 = 32; p.out = out; p.out_mode = OUT_CROP; p.Hreal = H; p.Wreal = W; p.crop_top = top; p.crop_left = left;
-        launch_gemm<false, MODE_C3>(cx, p, "k4_conv3x3");
+        launch_conv3(cx, p, "k4_conv3x3");
     }
     AVB_REQUIRE(!cx.unsupported, "layer shape without a kernel");
     AVB_CUDA_OK(cudaGetLastError());
