@@ -2,10 +2,12 @@
 //
 // One CTA (384 threads) owns a vertical strip of 128 pixels and streams down a segment of rows in
 // blocks of 8 input rows.  Per block:
-//   produce   decode + 3x3 into a planar fp32 tile with an R-pixel x halo.  Interior strips of the
-//             LUT producer take a vector path: 16-byte loads of the packed rows into a raw byte
-//             tile, then 4 pixels (12 bytes) per thread; border strips and the cat warp producer
-//             go pixel by pixel;
+//   produce   decode + 3x3 into a planar fp32 tile with an R-pixel x halo.  The packed uint8 rows of a
+//             block (strip + halo columns, REFLECT_101 halo rows resolved per row) are staged by the
+//             TMA engine: one cp.async.bulk per row into a double-buffered raw byte tile, completion
+//             on an mbarrier, issued one block ahead -- no thread waits on a global load.  The LUT
+//             producer then decodes 4 pixels (12 bytes) per thread, the cat warp producer gathers its
+//             bilinear taps from the tile; unaligned frames and image-border strips go pixel by pixel;
 //   H pass    8 outputs per thread from an (8+2R)-wide register window (LDS.128), taps from the
 //             kernel-parameter constant bank;
 //   V pass    accumulator ("scatter") form: every thread owns one (column, channel) and keeps the
@@ -279,6 +281,24 @@ struct CatProducer {
     }
 };
 
+// ------------------------------------------------------------------------------------ bulk-copy (TMA) helpers
+__device__ __forceinline__ uint32_t gauss_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gauss_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gauss_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void gauss_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gauss_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gauss_smem(dst)), "l"(src), "r"(bytes), "r"(gauss_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void gauss_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = gauss_smem(bar);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ kernel
 #ifndef G_MINB
 #define G_MINB 2
@@ -300,8 +320,9 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     float *Y = X + NCH * C::X_PLANE;                           // [NCH][RB][X_PITCH] fully blurred rows
     float *prod_smem = Y + NCH * C::X_PLANE;
     uint32_t *enc_s = reinterpret_cast<uint32_t *>(prod_smem + Prod::SMEM_FLOATS);
-    uint8_t *rawt = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);               // [RB][RAW_PITCH] packed input rows
-    constexpr int RAW_PITCH = Prod::RAW_PITCH, PF_N = Prod::PF_N;
+    uint8_t *rawt0 = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);              // [2][RB][RAW_PITCH] packed input rows (TMA double buffer)
+    constexpr int RAW_PITCH = Prod::RAW_PITCH;
+    __shared__ __align__(8) uint64_t rbar[2];                                       // completion of the bulk copies of each buffer
     __shared__ int gat[3];                                                          // gather producer: span lo, hi, eye mode
 
     const int frame = blockIdx.z;
@@ -360,7 +381,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
         vec_in = (gat[2] == 1 || gat[2] == 2) && in16 && n_chunks > 0 && 16 * n_chunks + 32 <= RAW_PITCH &&
                  a0 + 16 * n_chunks <= (int)p.io.in_rs;
     }
-    vec_in = vec_in && G_RB * n_chunks <= PF_N * THREADS;
+    vec_in = vec_in && 16 * n_chunks + (Prod::GATHER ? 32 : 0) <= RAW_PITCH;
 
     const int n_in_rows = (y_end - y_start) + 2 * R;
     const int n_in_blocks = (n_in_rows + G_RB - 1) / G_RB;
@@ -373,39 +394,34 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) A[i] = 0.f;
 
-    // raw-tile prefetch registers: chunk c = tid + k*THREADS -> (row c / n_chunks, chunk c % n_chunks)
-    uint4 pf[PF_N];
-    auto raw_fetch = [&](int yb_) {
-#pragma unroll
-        for (int k = 0; k < PF_N; ++k) {
-            const int c = tid + k * THREADS;
-            if (c < G_RB * n_chunks) {
-                const int r = c / n_chunks, q = c - r * n_chunks;
-                pf[k] = __ldg(reinterpret_cast<const uint4 *>(src_frame + (int64_t)reflect101(yb_ + r, H) * p.io.in_rs + a0) + q);
-            }
+    // Raw-tile staging: thread r < G_RB issues the bulk copy of row r of a block (bytes [a0, a0 + 16 n_chunks)
+    // of input row reflect101(yb + r)) and arrives on the buffer's mbarrier with the byte count.
+    if (tid == 0) {
+        gauss_mbar_init(&rbar[0], G_RB);
+        gauss_mbar_init(&rbar[1], G_RB);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto raw_issue = [&](int yb_, int buf) {
+        if (tid < G_RB) {
+            const uint8_t *g = src_frame + (int64_t)reflect101(yb_ + tid, H) * p.io.in_rs + a0;
+            gauss_bulk_load(rawt0 + buf * (G_RB * RAW_PITCH) + (Prod::GATHER ? 16 : 0) + tid * RAW_PITCH, g, 16u * (uint32_t)n_chunks, &rbar[buf]);
         }
     };
-    auto raw_publish = [&]() {
-#pragma unroll
-        for (int k = 0; k < PF_N; ++k) {
-            const int c = tid + k * THREADS;
-            if (c < G_RB * n_chunks) {
-                const int r = c / n_chunks, q = c - r * n_chunks;
-                reinterpret_cast<uint4 *>(rawt + (Prod::GATHER ? 16 : 0) + r * RAW_PITCH)[q] = pf[k];
-            }
-        }
-    };
-    if (vec_in) raw_fetch(y_start - R);
+    uint32_t rphase = 0;                             // bit b: parity the next wait on buffer b expects
+    if (vec_in) raw_issue(y_start - R, 0);
 
     for (int ib = 0; ib < n_in_blocks; ++ib) {
         const int yb = y_start - R + ib * G_RB;      // first input row of this block
         // ---- produce RB rows x IN_W columns of linear-light values
         if (vec_in) {
-            // the packed rows of this block were fetched one block ahead (registers); publish them,
-            // then put the next block's loads in flight before any arithmetic
-            raw_publish();
-            __syncthreads();
-            if (ib + 1 < n_in_blocks) raw_fetch(yb + G_RB);
+            // the packed rows of this block were requested one block ahead: wait for the copies, then put
+            // the next block's copies in flight (its buffer was last read two barriers ago)
+            const int buf = ib & 1;
+            const uint8_t *rawt = rawt0 + buf * (G_RB * RAW_PITCH);
+            gauss_mbar_wait(&rbar[buf], (rphase >> buf) & 1u);
+            rphase ^= 1u << buf;
+            if (ib + 1 < n_in_blocks) raw_issue(yb + G_RB, buf ^ 1);
             if (Prod::GATHER) {
                 // taps gather from the shared raw tile: a task is one column x 4 rows.  The 2 * IN_W tasks
                 // do not divide by the thread count: the tasks beyond the first THREADS are split into
@@ -582,7 +598,7 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
 template <int R, class Prod, int NCH>
 static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
     using C = GaussCfg<R>;
-    const size_t smem = (size_t)(NCH * C::S_PLANE + 2 * NCH * C::X_PLANE + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + (size_t)G_RB * Prod::RAW_PITCH;
+    const size_t smem = (size_t)(NCH * C::S_PLANE + 2 * NCH * C::X_PLANE + Prod::SMEM_FLOATS + G_ENC_SMEM) * 4 + 2 * (size_t)G_RB * Prod::RAW_PITCH;
     auto kern = gauss_stream_kernel<R, Prod, NCH>;
     AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
