@@ -37,6 +37,20 @@ struct StreakParams {
     float chroma_keep;       // float32(1 - strength), animal_utils.py:181
 };
 
+__device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(st_smem(dst)), "l"(src), "r"(bytes), "r"(st_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = st_smem(bar);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+}
+
 template <int R>
 __device__ __forceinline__ void streak_row_blur(const float *P, float *O, const float *taps_s, int ch, int g) {
     // outputs x = 8g .. 8g+7 of channel ch; window P[8g + (16-R) .. 8g + (16-R) + 8 + 2R)
@@ -69,6 +83,10 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
     __shared__ __align__(16) uint32_t stage[ST_TW * 3 / 4];
     __shared__ float lut_s[256];
     __shared__ float tab_s[ST_TAB];
+    // interior strips: the packed bytes of a row (strip + 16-px halo each side = 1632 B) are staged by the TMA
+    // engine one row ahead (cp.async.bulk, mbarrier completion) instead of being gathered byte by byte
+    __shared__ __align__(16) uint8_t raw_s[2][3 * ST_PW];
+    __shared__ __align__(8) uint64_t rbar[2];
     __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
 
     const int frame = blockIdx.z;
@@ -89,10 +107,29 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
     const bool vec_ok = (npx == ST_TW) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
     uint32_t seen = 0;
+    const bool tma = x0 >= ST_RMAX && x0 + ST_TW + ST_RMAX <= W && ((p.io.in_rs & 15) == 0) && ((p.io.in_fs & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(&rbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem(&rbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto raw_issue = [&](int y, int buf) {          // one thread
+        st_bulk_load(raw_s[buf], src + (int64_t)y * p.io.in_rs + 3 * (x0 - ST_RMAX), 3 * ST_PW, &rbar[buf]);
+    };
+    uint32_t rphase = 0;
+    if (tma && tid == 0 && y_begin < y_end) raw_issue(y_begin, 0);
 
     for (int y = y_begin; y < y_end; ++y) {
         if (tid < ST_TAB) tab_s[tid] = __ldg(p.row_tab + (int64_t)y * ST_TAB + tid);
-        __syncthreads();      // also fences the previous row's readers of P / O / stage
+        __syncthreads();      // also fences the previous row's readers of P / O / stage / raw_s
+        const int buf = (y - y_begin) & 1;
+        if (tma) {
+            if (tid == 0 && y + 1 < y_end) raw_issue(y + 1, buf ^ 1);      // its buffer was read two barriers ago
+            st_mbar_wait(&rbar[buf], (rphase >> buf) & 1u);
+            rphase ^= 1u << buf;
+        }
         // ---- produce: decode -> per-row 3x3 (channel mix x dichromat)
         {
             float m[9];
@@ -100,8 +137,7 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
             for (int i = 0; i < 9; ++i) m[i] = tab_s[33 + i];
             const uint8_t *row = src + (int64_t)y * p.io.in_rs;
             for (int i = tid; i < ST_PW; i += ST_THREADS) {
-                const int x = reflect101(x0 - ST_RMAX + i, W);
-                const uint8_t *q = row + 3 * x;
+                const uint8_t *q = tma ? raw_s[buf] + 3 * i : row + 3 * reflect101(x0 - ST_RMAX + i, W);
                 const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
                 seen |= b0 | b1 | b2;
                 const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
