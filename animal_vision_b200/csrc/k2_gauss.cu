@@ -77,7 +77,6 @@ struct DogProducer {
     static constexpr bool VEC = true;      // has a 4-pixel vector path (three packed 32-bit words -> 4 px)
     static constexpr bool GATHER = false;
     static constexpr int RAW_PITCH = 528;  // bytes per row of the raw tile: 33 chunks of 16 B
-    static constexpr int PF_N = 1;         // prefetched 16-byte chunks per thread
     const float *lut_s;
     const uint8_t *src;
     int64_t rs;
@@ -136,7 +135,6 @@ struct CatProducer {
     static constexpr bool VEC = false;
     static constexpr bool GATHER = true;   // source columns of a strip are staged in shared memory, taps gather from there
     static constexpr int RAW_PITCH = 960;  // 16 B slack + 58 chunks of 16 B + slack: (128 + 2*16) columns x 2.1 source px x 3 B + alignment slack
-    static constexpr int PF_N = 2;
     const float *norm_s;
     const uint8_t *src;
     int64_t rs;

@@ -46,14 +46,13 @@ SPECIES = ("Dog", "Cat", "HoneyBee")
 ALGO_BYTES_PER_PX = {"Dog": 6, "Cat": 9, "HoneyBee": 6}
 # per KERNEL: bytes it must read + write per output pixel (cat warp: u8 frame in, cat view out; the
 # centre zoom's output belongs to cat_center_zoom), and DRAM bytes per pixel measured once with
-# `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_all_r1e.txt)
+# `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_all_r1h.txt)
 KERNEL_ALGO_BYTES_PER_PX = {"k2_gauss_dichromat": 6.0, "k2_gauss_cat_warp": 6.0, "cat_center_zoom": 3.0 + 3.0 / 2.25,
                             "k3_uv_map": 6.0, "k3_uv_hist": 3.0, "k3_uv_stats": 3.0, "k3_uv_compact": 8.0, "k2_streak": 6.0}
-KERNEL_NCU_DRAM_BYTES_PER_PX = {"k2_gauss_dichromat": 4.51, "k2_gauss_cat_warp": 4.49, "cat_center_zoom": 2.29,
-                                "k3_uv_map": 4.49, "k3_uv_hist": 9.12, "k3_uv_stats": 3.07, "k3_uv_compact": 8.21}
+KERNEL_NCU_DRAM_BYTES_PER_PX = {"k2_gauss_dichromat": 4.39, "k2_gauss_cat_warp": 4.53, "cat_center_zoom": 2.32,
+                                "k3_uv_map": 4.54, "k3_uv_hist": 9.16, "k3_uv_stats": 3.04, "k3_uv_compact": 8.16}
 KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
-                  "k3_uv_stats": "HoneyBee", "k3_uv_hist1": "HoneyBee", "k3_uv_hist2": "HoneyBee",
-                  "k3_uv_hist3": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_collect": "HoneyBee", "k3_uv_compact": "HoneyBee",
+                  "k3_uv_stats": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_compact": "HoneyBee",
                   "k3_uv_prep": "HoneyBee", "k3_uv_scan": "HoneyBee", "k3_uv_select": "HoneyBee", "k2_streak": "Dog"}
 
 
@@ -410,7 +409,7 @@ def run_b200(args):
     achieved = algo_bytes / (shares[dom]["ms_per_launch"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None if ncu_bpp is None else ncu_bpp * frames_per_launch * H * W, "peak_source": peak_src,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per pixel (profiles/r1_ncu_all_r1e.txt), scaled to this launch",
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per pixel (profiles/r1_ncu_all_r1h.txt), scaled to this launch",
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": f"{bpp:g} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
                 "kernel_shares": shares}
