@@ -16,6 +16,7 @@
 //   phase 1  q,k,v = x Wqkv^T (one GEMM), Gram + norms reduced over all pixels (fp32 atomics)
 //   phase 2  M = Wproj . blockdiag(attn)  (c x c, per image), out = v M^T + b + pos_emb(v) + x
 // -- i.e. attention-apply and the output projection become ONE pointwise GEMM on v.
+#include <cuda.h>          // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched through the runtime
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -597,6 +598,129 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_pw_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ TMA-fed pointwise GEMM
+// The layers whose A operand already is bf16 (attention projection on v, FFN out on the hidden
+// activations) are fed by the TMA engine: a 3-D tensor map {8 channels, rows, K/8} over the row-major
+// activation matrix makes ONE cp.async.bulk.tensor per 128-row tile land in shared memory exactly in the
+// canonical K-major UMMA layout (k-chunks of 8 channels, 128 rows of 16 bytes each) -- no thread loads,
+// no register staging, no shared-memory stores, no proxy fence.  A ring of NS stages keeps NS tiles in
+// flight; one thread waits on the stage's mbarrier and issues the tcgen05.mma of tile i+1 into the other
+// TMEM buffer while all threads run the epilogue of tile i (residual rows prefetched one tile ahead).
+template <int BN, int KP, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tma_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap tmA) {
+    pdl_wait();
+    constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;
+    constexpr int A_STAGE = (KP / 8) * A_LBO;
+    constexpr int NS = KP <= 64 ? 4 : 3;
+    constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    constexpr int BUF1 = TMEM_COLS / 2;
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *As = dsm;                                        // [NS][A_STAGE]
+    uint8_t *Bs = dsm + NS * A_STAGE;                         // [B_BYTES]
+    __shared__ __align__(8) uint64_t full_bar[NS];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, n_base = blockIdx.y * BN;
+    const int m_tiles = (p.rows + BM - 1) / BM;
+    const int n_my = ((int)blockIdx.x < m_tiles) ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // resident weight tile
+        const bf16 *Wb = p.W + (long long)b * p.w_bstride;
+        constexpr int NVEC = BN * (KP / 8), BATCH = 8;
+        for (int i0 = 0; i0 < NVEC; i0 += BATCH * GEMM_THREADS) {
+            uint4 wv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 8), q = idx - n * (KP / 8);
+                    wv[u] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K) + q);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 8), q = idx - n * (KP / 8);
+                    *reinterpret_cast<uint4 *>(Bs + q * B_LBO + (n >> 3) * 128 + (n & 7) * 16) = wv[u];
+                }
+            }
+        }
+    }
+    constexpr bool PRE = ((EPI & (EPI_RES1 | EPI_RES2)) != 0) && BN <= 64;
+    constexpr int NR1 = (PRE && (EPI & EPI_RES1)) ? BN / 8 : 1, NR2 = (PRE && (EPI & EPI_RES2)) ? BN / 16 : 1;
+    uint4 rreg1[NR1], rreg2[NR2];
+    auto r_fetch = [&](int tile) {
+        if (!PRE) return;
+        const int m = tile * BM + 32 * (warp & 3) + lane;
+        if (m >= p.rows) return;
+        const long long row = (long long)b * p.rows + m;
+        const int n0 = n_base + (warp >> 2) * (BN / 2);
+        if (EPI & EPI_RES1) {
+#pragma unroll
+            for (int i = 0; i < NR1; ++i) rreg1[i] = *(reinterpret_cast<const uint4 *>(p.res1 + row * p.ldr1 + n0) + i);
+        }
+        if (EPI & EPI_RES2) {
+#pragma unroll
+            for (int i = 0; i < NR2; ++i) rreg2[i] = *(reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0) + i);
+        }
+    };
+    auto tma_load = [&](int i) {                              // one thread: tile i of this CTA -> stage i % NS
+        const int st = i % NS;
+        const int row0 = b * p.rows + (blockIdx.x + i * gridDim.x) * BM;
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)A_STAGE) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(As + st * A_STAGE)), "l"(&tmA), "r"(0), "r"(row0), "r"(0), "r"(bar) : "memory");
+    };
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    auto issue = [&](int i, uint32_t tmem_d) {                // one thread: wait for the stage, KP/16 MMAs
+        mbar_wait(&full_bar[i % NS], (uint32_t)((i / NS) & 1));
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(As + (i % NS) * A_STAGE), b0 = smem_u32(Bs);
+#pragma unroll
+        for (int j = 0; j < KP / 16; ++j)
+            mma_f16(tmem_d + (uint32_t)((i & 1) * BUF1), make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128),
+                    IDESC, j > 0 ? 1u : 0u);
+        mma_commit(&mma_bar[i & 1]);
+    };
+
+    fence_async_smem();                                       // weight tile (generic stores) -> tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) {
+        for (int i = 0; i < NS && i < n_my; ++i) tma_load(i);
+        if (n_my > 0) issue(0, tmem_d);
+    }
+    for (int i = 0; i < n_my; ++i) {
+        r_fetch(blockIdx.x + i * gridDim.x);
+        if (tid == 0 && i + 1 < n_my) issue(i + 1, tmem_d);    // TMEM buffer (i+1)&1 was drained before the barrier below
+        mbar_wait(&mma_bar[i & 1], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        if (tid == 0 && i + NS < n_my) tma_load(i + NS);       // stage i % NS: its MMAs have completed
+        epilogue_tile<BN, EPI, PRE>(p, tmem_d + (uint32_t)((i & 1) * BUF1), b, (blockIdx.x + i * gridDim.x) * BM, n_base, warp, lane, rreg1, rreg2);
+        tc_fence_before();
+        __syncthreads();
+    }
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
@@ -1328,6 +1452,64 @@ static void launch_pw_t(Ctx &cx, const GemmP &p, const char *name) {
     launch_pdl(tc::gemm_pw_kernel<BN, KP, A_BF16, LN, EPI>, dim3(gx, ny, cx.B), dim3(GEMM_THREADS), smem, cx.st, p);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 activation matrix [total_rows, lda] (K used columns) as {8 channels, rows, K/8}: a box of
+// {8, 128, K/8} is one operand tile in canonical K-major layout
+static bool make_a_map(CUtensorMap *tm, const bf16 *A, long long total_rows, int lda, int K) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)total_rows, (cuuint64_t)(K / 8)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)lda * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)BM, (cuuint32_t)(K / 8)};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16 *>(A), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int KP, int EPI>
+static bool launch_tma_t(Ctx &cx, const GemmP &p, const char *name) {
+    if (p.K1 < p.K || (reinterpret_cast<uintptr_t>(p.A1) & 15) || (p.lda1 & 7)) return false;
+    alignas(64) CUtensorMap tm;
+    if (!make_a_map(&tm, static_cast<const bf16 *>(p.A1), (long long)cx.B * p.rows, p.lda1, KP)) return false;
+    constexpr int NS = KP <= 64 ? 4 : 3;
+    constexpr int smem = NS * (KP / 8) * (BM / 8) * 128 + (KP / 8) * (BN / 8) * 128;
+    constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::gemm_tma_kernel<BN, KP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
+    const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
+    int gx = std::max(1, std::min(m_tiles, sm_count() * per_sm / std::max(1, ny * cx.B)));
+    const int per_cta = (m_tiles + gx - 1) / gx;
+    gx = (m_tiles + per_cta - 1) / per_cta;
+    AVB_TIMED(name, cx.st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, ny, cx.B); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = cx.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tma_kernel<BN, KP, EPI>, p, tm) == cudaSuccess;
+}
+
 // Shapes of the MST++ pointwise layers that take the pipelined kernel (anything else falls through
 // to the generic K-chunked kernel): K = the padded channel count of the level, N a multiple of it.
 template <bool A_BF16>
@@ -1340,6 +1522,12 @@ static bool launch_pw(Ctx &cx, const GemmP &p, const char *name) {
     using namespace tc;
     if constexpr (A_BF16) {
         constexpr int PROJ = EPI_BIAS | EPI_RES1 | EPI_RES2;                     // x = v M^T + b + pos_emb + x
+        // bf16 activations: operand tiles come through the TMA engine (thread-loader kernel as fall-back when
+        // the tensor map cannot be built: unaligned views)
+#define TMA_CASE(BN_, KP_, EPI_) \
+        if (!ln && p.K == KP_ && p.Np % BN_ == 0 && epi == (EPI_) && launch_tma_t<BN_, KP_, (EPI_)>(cx, p, name)) return true;
+        TMA_CASE(32, 32, PROJ) TMA_CASE(64, 64, PROJ) TMA_CASE(128, 128, PROJ) TMA_CASE(32, 128, EPI_RES1)
+#undef TMA_CASE
         PW_CASE(32, 32, false, PROJ) PW_CASE(64, 64, false, PROJ) PW_CASE(128, 128, false, PROJ)
         PW_CASE(32, 128, false, EPI_RES1)                                        // FFN out, full-resolution level
     } else {
