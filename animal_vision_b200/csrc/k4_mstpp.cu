@@ -88,6 +88,7 @@ struct GemmP {
     const void *A1, *A2;       // MODE_PW: [B*rows, lda]; conv modes: feature map [B, Hi, Wi, lda1]
     int lda1, lda2, K1, K;     // K1: extent of K taken from A1 (the rest from A2), K multiple of 32
     const bf16 *W;             // [Np][K] row-major (k contiguous)
+    const float *W32;          // the same matrix in fp32 (tf32 TMA kernel only)
     long long w_bstride;       // element stride between batch items (0: shared weights)
     int Np;
     int rows;                  // output rows (pixels) per batch item
@@ -148,6 +149,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
@@ -726,6 +731,128 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tma_kernel(const __grid_con
     }
 }
 
+// The same pipeline for a layer whose A operand is the fp32 residual stream (q | k | v): the tensor map is
+// over fp32 rows {4 channels, rows, K/4} and the contraction runs as tcgen05.mma kind::tf32 (the tensor
+// core reads the fp32 bits, 10 mantissa bits -- no less than the bf16 operands of the other layers), so
+// the activations go HBM -> TMA -> shared memory -> tensor core without passing through a thread.
+template <int BN, int KP, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tma32_kernel(const __grid_constant__ GemmP p, const __grid_constant__ CUtensorMap tmA) {
+    pdl_wait();
+    constexpr int A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128;
+    constexpr int A_STAGE = (KP / 4) * A_LBO;               // fp32 operands: k-chunks of 4 elements (16 bytes)
+    constexpr int NS = KP <= 32 ? 4 : (KP <= 64 ? 3 : 2);
+    constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    constexpr int BUF1 = TMEM_COLS / 2;
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *As = dsm;                                        // [NS][A_STAGE]
+    uint8_t *Bs = dsm + NS * A_STAGE;                         // [B_BYTES]
+    __shared__ __align__(8) uint64_t full_bar[NS];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, n_base = blockIdx.y * BN;
+    const int m_tiles = (p.rows + BM - 1) / BM;
+    const int n_my = ((int)blockIdx.x < m_tiles) ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.zero_ptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = tid; i < p.zero_n; i += GEMM_THREADS) p.zero_ptr[i] = 0.f;
+    {   // resident weight tile (fp32 / tf32)
+        const float *Wb = p.W32;
+        constexpr int NVEC = BN * (KP / 4), BATCH = 8;
+        for (int i0 = 0; i0 < NVEC; i0 += BATCH * GEMM_THREADS) {
+            uint4 wv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 4), q = idx - n * (KP / 4);
+                    wv[u] = __ldg(reinterpret_cast<const uint4 *>(Wb + (long long)(n_base + n) * p.K) + q);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int idx = i0 + u * GEMM_THREADS + tid;
+                if (idx < NVEC) {
+                    const int n = idx / (KP / 4), q = idx - n * (KP / 4);
+                    *reinterpret_cast<uint4 *>(Bs + q * B_LBO + (n >> 3) * 128 + (n & 7) * 16) = wv[u];
+                }
+            }
+        }
+    }
+    constexpr bool PRE = ((EPI & (EPI_RES1 | EPI_RES2)) != 0) && BN <= 64;
+    constexpr int NR1 = (PRE && (EPI & EPI_RES1)) ? BN / 8 : 1, NR2 = (PRE && (EPI & EPI_RES2)) ? BN / 16 : 1;
+    uint4 rreg1[NR1], rreg2[NR2];
+    auto r_fetch = [&](int tile) {
+        if (!PRE) return;
+        const int m = tile * BM + 32 * (warp & 3) + lane;
+        if (m >= p.rows) return;
+        const long long row = (long long)b * p.rows + m;
+        const int n0 = n_base + (warp >> 2) * (BN / 2);
+        if (EPI & EPI_RES1) {
+#pragma unroll
+            for (int i = 0; i < NR1; ++i) rreg1[i] = *(reinterpret_cast<const uint4 *>(p.res1 + row * p.ldr1 + n0) + i);
+        }
+        if (EPI & EPI_RES2) {
+#pragma unroll
+            for (int i = 0; i < NR2; ++i) rreg2[i] = *(reinterpret_cast<const uint4 *>(p.res2 + row * p.ldr2 + n0) + i);
+        }
+    };
+    auto tma_load = [&](int i) {                              // one thread: tile i of this CTA -> stage i % NS
+        const int st = i % NS;
+        const int row0 = b * p.rows + (blockIdx.x + i * gridDim.x) * BM;
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)A_STAGE) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(As + st * A_STAGE)), "l"(&tmA), "r"(0), "r"(row0), "r"(0), "r"(bar) : "memory");
+    };
+    // instruction descriptor: D = F32, A = B = TF32 (format 2), both K-major
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    auto issue = [&](int i, uint32_t tmem_d) {                // one thread: wait for the stage, KP/8 MMAs (K = 8 each)
+        mbar_wait(&full_bar[i % NS], (uint32_t)((i / NS) & 1));
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(As + (i % NS) * A_STAGE), b0 = smem_u32(Bs);
+#pragma unroll
+        for (int j = 0; j < KP / 8; ++j)
+            mma_tf32(tmem_d + (uint32_t)((i & 1) * BUF1), make_desc(a0 + 2 * j * A_LBO, A_LBO, 128), make_desc(b0 + 2 * j * B_LBO, B_LBO, 128),
+                    IDESC, j > 0 ? 1u : 0u);
+        mma_commit(&mma_bar[i & 1]);
+    };
+
+    fence_async_smem();                                       // weight tile (generic stores) -> tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) {
+        for (int i = 0; i < NS && i < n_my; ++i) tma_load(i);
+        if (n_my > 0) issue(0, tmem_d);
+    }
+    for (int i = 0; i < n_my; ++i) {
+        r_fetch(blockIdx.x + i * gridDim.x);
+        if (tid == 0 && i + 1 < n_my) issue(i + 1, tmem_d);    // TMEM buffer (i+1)&1 was drained before the barrier below
+        mbar_wait(&mma_bar[i & 1], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        if (tid == 0 && i + NS < n_my) tma_load(i + NS);       // stage i % NS: its MMAs have completed
+        epilogue_tile<BN, EPI, PRE>(p, tmem_d + (uint32_t)((i & 1) * BUF1), b, (blockIdx.x + i * gridDim.x) * BM, n_base, warp, lane, rreg1, rreg2);
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ row-streaming 3x3 convolution
 // Conv2d(32, 32, 3, padding 1) on the full-resolution level (embedding / mapping convs of every MST
 // body and conv_out).  The K-chunked kernel above gathers every input pixel nine times through L2
@@ -1235,6 +1362,7 @@ struct MsabW {
     const float *rescale, *wproj_f32, *bproj, *ln_g, *ln_b;       // device fp32
     const float *pos0, *pos2, *ffn_dw;                            // device fp32 [9][Cp] / [9][Hp]
     const bf16 *wqkv, *ffn0, *ffn4;                               // device bf16
+    const float *wqkv32;                                          // device fp32 [3*Cp][Cp] (tf32 TMA kernel)
 };
 struct BodyW {
     const bf16 *embedding, *mapping;     // [32][9*32]
@@ -1325,6 +1453,11 @@ static bool pack_msab(Packer &pk, Cursor &cur, MsabW &m, int c) {
     // q | k | v stacked along N: rows [0,c), [Cp,Cp+c), [2Cp,2Cp+c)
     { uint16_t *d = pk.b16((const void **)&m.wqkv, (size_t)3 * Cp * Cp);
       put_dense(d, Cp, wq, c, c, 0, 0); put_dense(d, Cp, wk, c, c, Cp, 0); put_dense(d, Cp, wv, c, c, 2 * Cp, 0); }
+    { float *d = pk.f32((const void **)&m.wqkv32, (size_t)3 * Cp * Cp);
+      const float *src[3] = {wq, wk, wv};
+      for (int t = 0; t < 3; ++t)
+          for (int r = 0; r < c; ++r)
+              for (int k = 0; k < c; ++k) d[(size_t)(t * Cp + r) * Cp + k] = src[t][(size_t)r * c + k]; }
     { uint16_t *d = pk.b16((const void **)&m.ffn0, (size_t)Hp * Cp); put_dense(d, Cp, f0, 4 * c, c, 0, 0); }
     { uint16_t *d = pk.b16((const void **)&m.ffn4, (size_t)Cp * Hp); put_dense(d, Hp, f4, c, 4 * c, 0, 0); }
     return true;
@@ -1482,6 +1615,45 @@ static bool make_a_map(CUtensorMap *tm, const bf16 *A, long long total_rows, int
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool make_a_map_f32(CUtensorMap *tm, const float *A, long long total_rows, int lda, int K) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {4, (cuuint64_t)total_rows, (cuuint64_t)(K / 4)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)lda * 4, 16};
+    const cuuint32_t box[3] = {4, (cuuint32_t)BM, (cuuint32_t)(K / 4)};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(A), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int KP, int EPI>
+static bool launch_tma32_t(Ctx &cx, const GemmP &p, const char *name) {
+    if (!p.W32 || p.K1 < p.K || p.w_bstride != 0 || (reinterpret_cast<uintptr_t>(p.A1) & 15) || (p.lda1 & 3)) return false;
+    alignas(64) CUtensorMap tm;
+    if (!make_a_map_f32(&tm, static_cast<const float *>(p.A1), (long long)cx.B * p.rows, p.lda1, KP)) return false;
+    constexpr int NS = KP <= 32 ? 4 : (KP <= 64 ? 3 : 2);
+    constexpr int smem = NS * (KP / 4) * (BM / 8) * 128 + (KP / 4) * (BN / 8) * 128;
+    constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::gemm_tma32_kernel<BN, KP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
+    const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
+    int gx = std::max(1, std::min(m_tiles, sm_count() * per_sm / std::max(1, ny * cx.B)));
+    const int per_cta = (m_tiles + gx - 1) / gx;
+    gx = (m_tiles + per_cta - 1) / per_cta;
+    AVB_TIMED(name, cx.st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, ny, cx.B); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = cx.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tma32_kernel<BN, KP, EPI>, p, tm) == cudaSuccess;
+}
+
 template <int BN, int KP, int EPI>
 static bool launch_tma_t(Ctx &cx, const GemmP &p, const char *name) {
     if (p.K1 < p.K || (reinterpret_cast<uintptr_t>(p.A1) & 15) || (p.lda1 & 7)) return false;
@@ -1533,6 +1705,11 @@ static bool launch_pw(Ctx &cx, const GemmP &p, const char *name) {
     } else {
         constexpr int FFN0 = EPI_GELU | EPI_OUTBF16, UP = EPI_BIAS | EPI_CONVT;
         PW_CASE(128, 32, true, FFN0) PW_CASE(256, 64, true, FFN0) PW_CASE(256, 128, true, FFN0)
+        // q | k | v: fp32 activations through the TMA engine, tf32 tensor cores (thread-loader kernel as fall-back)
+#define TMA32_CASE(BN_, KP_, EPI_) \
+        if (!ln && p.W32 && p.K == KP_ && p.Np % BN_ == 0 && epi == (EPI_) && launch_tma32_t<BN_, KP_, (EPI_)>(cx, p, name)) return true;
+        TMA32_CASE(96, 32, EPI_OUTBF16) TMA32_CASE(192, 64, EPI_OUTBF16) TMA32_CASE(128, 128, EPI_OUTBF16)
+#undef TMA32_CASE
         PW_CASE(96, 32, false, EPI_OUTBF16) PW_CASE(192, 64, false, EPI_OUTBF16) PW_CASE(192, 128, false, EPI_OUTBF16)   // q | k | v
         PW_CASE(256, 128, false, UP) PW_CASE(128, 64, false, UP)                 // ConvTranspose2d(2, 2)
         PW_CASE(64, 128, false, 0) PW_CASE(32, 64, false, 0)                     // 1x1 fusion of cat([up, skip])
@@ -1624,7 +1801,7 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
     // q | k | v
     {
         GemmP p = gemm_defaults();
-        p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.Np = 3 * Cp; p.rows = rows;
+        p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.W32 = m.wqkv32; p.Np = 3 * Cp; p.rows = rows;
         p.out = ws.qkv; p.ldo = 3 * Cp; p.out_bf16 = 1;
         p.zero_ptr = reinterpret_cast<float *>(ws.stats); p.zero_n = 2 * cx.B * m.heads * 1024;      // int64 entries, accumulated with atomics
         launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_qkv");
