@@ -302,13 +302,15 @@ __device__ __forceinline__ void gauss_mbar_wait(uint64_t *bar, uint32_t parity) 
 #define G_MINB 2
 #endif
 #ifndef G_MINB3_R
-#define G_MINB3_R 8
+#define G_MINB3_R 14
 #endif
-template <int R>
-struct GaussOcc { static constexpr int MIN_BLOCKS = (R <= G_MINB3_R) ? 3 : G_MINB; };
+// two-plane CTAs (256 threads) fit three per SM up to radius 14 (72 registers with the TMA-staged tiles);
+// three-plane CTAs (384 threads) keep the earlier split
+template <int R, int NCH>
+struct GaussOcc { static constexpr int MIN_BLOCKS = (R <= (NCH == 2 ? G_MINB3_R : 8)) ? 3 : G_MINB; };
 
 template <int R, class Prod, int NCH>
-__global__ void __launch_bounds__(G_THREADS_PER_PLANE * NCH, GaussOcc<R>::MIN_BLOCKS)
+__global__ void __launch_bounds__(G_THREADS_PER_PLANE * NCH, GaussOcc<R, NCH>::MIN_BLOCKS)
 gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant__ typename Prod::Params pp) {
     using C = GaussCfg<R>;
     constexpr int THREADS = G_THREADS_PER_PLANE * NCH;
