@@ -801,13 +801,34 @@ __global__ void __launch_bounds__(128) center_zoom_kernel(FrameIO io, const int3
     for (int j = 0; j < 4; ++j) tx[j] = __ldg(reinterpret_cast<const int4 *>(tab) + min(x4 + j, W - 1));
     int sa[12], sb[12];                       // (a0*xw0 + a1*xw1) >> 4 of source rows ia, ib
     int ia = -1, ib = -1;
+    // the packed words of a source row: three 32-bit words per output pixel hold its two horizontal taps
+    // (6 bytes from byte 3*xi0).  Rows are FETCHED one step before they are needed (the next source row is
+    // always ib + 1 when upscaling) and only converted when the walk reaches them.
+    uint32_t pw[12];
+    int pw_row = -2;
+    int wi[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int ob = 3 * tx[j].x; wi[j] = ob >> 2; sh[j] = (ob & 3) * 8; }
+    auto fetch = [&](int r) {
+        const uint32_t *row32 = reinterpret_cast<const uint32_t *>(src + (int64_t)r * io.in_rs);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            pw[3 * j] = __ldg(row32 + wi[j]);
+            pw[3 * j + 1] = __ldg(row32 + min(wi[j] + 1, last_word));
+            pw[3 * j + 2] = __ldg(row32 + min(wi[j] + 2, last_word));
+        }
+        pw_row = r;
+    };
     auto hrow = [&](int r, int (&s)[12]) {
         const uint8_t *row = src + (int64_t)r * io.in_rs;
+        if (aligned_in && pw_row != r) fetch(r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t a0[3], a1[3];
             if (aligned_in) {
-                zoom_taps(reinterpret_cast<const uint32_t *>(row), tx[j].x, last_word, a0, a1);
+                const uint32_t lo = __funnelshift_r(pw[3 * j], pw[3 * j + 1], sh[j]), hi = __funnelshift_r(pw[3 * j + 1], pw[3 * j + 2], sh[j]);
+                a0[0] = lo & 0xffu; a0[1] = (lo >> 8) & 0xffu; a0[2] = (lo >> 16) & 0xffu;       // pixel xi0
+                a1[0] = lo >> 24; a1[1] = hi & 0xffu; a1[2] = (hi >> 8) & 0xffu;                  // pixel xi0 + 1
                 // (xi1 == xi0 only where its weight is 0: the neighbour's bytes then multiply 0)
             } else {
 #pragma unroll
@@ -816,6 +837,7 @@ __global__ void __launch_bounds__(128) center_zoom_kernel(FrameIO io, const int3
 #pragma unroll
             for (int c = 0; c < 3; ++c) s[3 * j + c] = ((int)a0[c] * tx[j].z + (int)a1[c] * tx[j].w) >> 4;
         }
+        if (aligned_in && r + 1 < H) fetch(r + 1);          // the row the walk will need next
     };
     uint8_t *o = io.out + (int64_t)blockIdx.z * io.out_fs + (int64_t)y_begin * io.out_rs + 3 * x4;
     for (int y = y_begin; y < y_end; ++y, o += io.out_rs) {
