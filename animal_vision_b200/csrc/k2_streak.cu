@@ -21,7 +21,7 @@ constexpr int ST_TW = 512;                 // output pixels per CTA per row
 constexpr int ST_RMAX = 16;                // combined radius limit (ksize <= 33)
 constexpr int ST_THREADS = 192;            // 3 channels x 64 groups of 8 outputs
 constexpr int ST_ROWS = 16;                // rows a CTA walks down
-constexpr int ST_TAB = 48;                 // floats per row-table entry: 33 taps, 9 matrix, radius, pad
+constexpr int ST_TAB = 56;                 // floats per row-table entry: 33 taps, 9 matrix, radius, 3x2 P_y, 2x3 Q, flag
 constexpr int ST_PW = ST_TW + 2 * ST_RMAX; // produced columns
 constexpr int ST_PITCH = ST_PW + 4;        // 548: 16 B aligned rows, odd multiple of 16 B
 constexpr int ST_OPITCH = ST_TW + 4;
@@ -130,11 +130,13 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
             st_mbar_wait(&rbar[buf], (rphase >> buf) & 1u);
             rphase ^= 1u << buf;
         }
-        // ---- produce: decode -> per-row 3x3 (channel mix x dichromat)
+        // ---- produce: decode -> per-row 3x3 (channel mix x dichromat), or -- every dichromat matrix has
+        // rank 2 -- the two planes Q lin whose 3x2 expansion P_y follows the filter (a third fewer taps)
+        const bool two = tab_s[55] != 0.f;                 // uniform: the same for every row of the table
         {
             float m[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) m[i] = tab_s[33 + i];
+            for (int i = 0; i < 9; ++i) m[i] = two ? (i < 6 ? tab_s[49 + i] : 0.f) : tab_s[33 + i];
             const uint8_t *row = src + (int64_t)y * p.io.in_rs;
             for (int i = tid; i < ST_PW; i += ST_THREADS) {
                 const uint8_t *q = tma ? raw_s[buf] + 3 * i : row + 3 * reflect101(x0 - ST_RMAX + i, W);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
                 const float l0 = lut_s[b0], l1 = lut_s[b1], l2 = lut_s[b2];
                 P[i] = m[0] * l0 + m[1] * l1 + m[2] * l2;
                 P[ST_PITCH + i] = m[3] * l0 + m[4] * l1 + m[5] * l2;
-                P[2 * ST_PITCH + i] = m[6] * l0 + m[7] * l1 + m[8] * l2;
+                if (!two) P[2 * ST_PITCH + i] = m[6] * l0 + m[7] * l1 + m[8] * l2;
             }
         }
         __syncthreads();
@@ -151,18 +153,29 @@ __global__ void __launch_bounds__(ST_THREADS) streak_kernel(const __grid_constan
         {
             const int r = (int)tab_s[42];
             const int ch = tid >> 6, g = tid & 63;
-            if (r <= 4) streak_row_blur<4>(P, O, tab_s, ch, g);
-            else if (r <= 8) streak_row_blur<8>(P, O, tab_s, ch, g);
-            else if (r <= 12) streak_row_blur<12>(P, O, tab_s, ch, g);
-            else streak_row_blur<16>(P, O, tab_s, ch, g);
+            if (!two || ch < 2) {
+                if (r <= 4) streak_row_blur<4>(P, O, tab_s, ch, g);
+                else if (r <= 8) streak_row_blur<8>(P, O, tab_s, ch, g);
+                else if (r <= 12) streak_row_blur<12>(P, O, tab_s, ch, g);
+                else streak_row_blur<16>(P, O, tab_s, ch, g);
+            }
         }
         __syncthreads();
         // ---- tail: [chroma compression] -> encode; 4 pixels (12 bytes) per thread
         if (tid < ST_TW / 4) {
             const float4 a = reinterpret_cast<const float4 *>(O)[tid];
             const float4 b = reinterpret_cast<const float4 *>(O + ST_OPITCH)[tid];
-            const float4 c = reinterpret_cast<const float4 *>(O + 2 * ST_OPITCH)[tid];
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!two) c = reinterpret_cast<const float4 *>(O + 2 * ST_OPITCH)[tid];
             float v[4][3] = {{a.x, b.x, c.x}, {a.y, b.y, c.y}, {a.z, b.z, c.z}, {a.w, b.w, c.w}};
+            if (two) {                                      // expand: rgb = P_y (plane0, plane1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float p0 = v[j][0], p1 = v[j][1];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v[j][k] = fmaf(tab_s[43 + 2 * k + 1], p1, tab_s[43 + 2 * k] * p0);
+                }
+            }
             uint32_t bytes[12];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

@@ -17,7 +17,7 @@
 namespace avb {
 namespace f32path {
 
-constexpr int TAB = 48;          // floats per streak row-table entry (tables.streak_row_table)
+constexpr int TAB = 56;          // floats per streak row-table entry (tables.streak_row_table)
 constexpr int TAB_CENTRE = 16;   // index of the centre tap
 
 __device__ __forceinline__ float srgb_decode(float v) {          // animal_utils.py:5-11, float32 like NumPy

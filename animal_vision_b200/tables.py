@@ -206,7 +206,26 @@ def _reflect101(i: int, n: int) -> int:
 
 
 STREAK_RMAX = 16      # combined radius limit of the device kernel (k2_streak.cu ST_RMAX)
-STREAK_TAB = 48       # floats per row: 33 taps (centred at index 16), 9 matrix entries, radius, pad
+STREAK_TAB = 56       # floats per row: 33 taps (centred at index 16), 9 matrix entries, radius, two-plane factors
+
+
+def rank2_factor(M: np.ndarray):
+    """M (3x3, float32 values) = P (3x2) Q (2x3) if it has rank <= 2, else None.  Q is an exact copy of the two
+    most independent rows of M, P the coefficients of every row in that basis (least squares, float64);
+    accepted when the residual is within a few float32 ulps of the largest entry (M itself was rounded)."""
+    M = np.asarray(M, np.float64)
+    best, pair = -1.0, (0, 1)
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        a = np.linalg.norm(np.cross(M[i], M[j]))
+        if a > best:
+            best, pair = a, (i, j)
+    Q = M[list(pair)]
+    if best <= 0.0:
+        return None
+    P = M @ np.linalg.pinv(Q)
+    if np.abs(P @ Q - M).max() > 4e-7 * np.abs(M).max():
+        return None
+    return P, Q
 
 
 def streak_row_table(H: int, M: np.ndarray, y_center: float, s_streak: float, s_far: float, falloff: float) -> np.ndarray:
@@ -215,11 +234,15 @@ def streak_row_table(H: int, M: np.ndarray, y_center: float, s_streak: float, s_
               symmetric tap vector, centred at index 16, zero padded;
       [33:42] row-major 3x3 = (REFLECT_101 channel mix of the sigmaX taps over a width of 3) @ M,
               M being the species' dichromat matrix (applied as out = A @ lin);
-      [42]    combined radius r1 + r2.
+      [42]    combined radius r1 + r2;
+      [43:49] row-major 3x2 P_y, [49:55] row-major 2x3 Q, [55] 1.0 when they are valid: every dichromat matrix
+              has rank 2 (L and M are merged), M = P Q, so the row's 3x3 is (mix_y P) Q and only the TWO
+              planes Q lin need filtering; the 3x2 expansion P_y = mix_y P follows the filter.
     Composed in float64 from the float32 taps OpenCV would use, rounded once."""
     sx, sy = streak_sigmas(H, y_center, s_streak, s_far, falloff)
     tab = np.zeros((H, STREAK_TAB), np.float32)
     M64 = np.asarray(M, np.float64)
+    fac = rank2_factor(M64)
     cache = {}
     for y in range(H):
         key = (sx[y], sy[y])
@@ -239,6 +262,11 @@ def streak_row_table(H: int, M: np.ndarray, y_center: float, s_streak: float, s_
             row[STREAK_RMAX - r:STREAK_RMAX + r + 1] = comb.astype(np.float32)
             row[33:42] = (mix @ M64).astype(np.float32).ravel()
             row[42] = float(r)
+            if fac is not None:
+                P, Q = fac
+                row[43:49] = (mix @ P).astype(np.float32).ravel()
+                row[49:55] = Q.astype(np.float32).ravel()
+                row[55] = 1.0
             cache[key] = row
         tab[y] = cache[key]
     return tab

@@ -56,9 +56,18 @@ def test_streak_row_table_reproduces_reference(name, golden, golden_meta):
 
 def test_streak_row_table_shape_and_radius():
     tab = tables.streak_row_table(2160, tables.dichromat_matrix(0.6, 0.95), 0.5, 0.8, 2.6, 8.0)
-    assert tab.shape == (2160, 48) and tab.dtype == np.float32
+    assert tab.shape == (2160, tables.STREAK_TAB) and tab.dtype == np.float32
     assert tab[:, 42].max() <= 16
     np.testing.assert_allclose(tab[:, :33].sum(1), 1.0, atol=2e-6)      # composed taps stay normalised
+    # rank-2 factors: (mix_y P) Q reproduces the row's 3x3 to float32 rounding for every dichromat matrix
+    assert (tab[:, 55] == 1.0).all()
+    for y in (0, 700, 1080, 2159):
+        A = tab[y, 33:42].reshape(3, 3).astype(np.float64)
+        PQ = tab[y, 43:49].reshape(3, 2).astype(np.float64) @ tab[y, 49:55].reshape(2, 3).astype(np.float64)
+        assert np.abs(PQ - A).max() <= 4e-7 * np.abs(A).max()
+    full = np.array([[0.9, 0.1, 0.0], [0.0, 0.3, 0.8], [0.5, 0.5, 0.1]], np.float32)       # rank 3: no factors
+    assert tables.rank2_factor(full) is None
+    assert (tables.streak_row_table(64, full, 0.5, 0.8, 2.6, 8.0)[:, 55] == 0.0).all()
 
 
 def test_encode_thresholds_are_the_reference_step_function():
