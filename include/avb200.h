@@ -100,7 +100,7 @@ AVB_API int avb_dichromat_blur_u8(const uint8_t *in, uint8_t *out, int n, int H,
  * apply_anisotropic_acuity_blur_with_streak (animals/animal_utils.py:147-172) as it actually behaves
  * (x blur + 3-wide colour-channel leak with sigmaX(y), x blur with sigmaY(y), never any vertical
  * blur) and apply_chroma_compression (animal_utils.py:174-181).
- *   row_tab_dev     H x 48 float32 (host-built: animal_vision_b200/tables.py streak_row_table):
+ *   row_tab_dev     H x 56 float32 (host-built: animal_vision_b200/tables.py streak_row_table):
  *                   [0:33] combined x taps centred at 16, [33:42] row-major 3x3 (channel mix @ species
  *                   matrix), [42] combined radius (<= 16), [43:55] the rank-2 factors (3x2 P_y, 2x3 Q), [55] 1 when valid; 56 floats per row
  *   chroma_strength 0 = no chroma compression (panda/rabbit: 0.06) */
