@@ -1147,6 +1147,88 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
     }
 }
 
+// ------------------------------------------------------------------------------------ fused positional embedding
+// pos_emb(v) = dw3x3(GELU(dw3x3(v)))  (MST_Plus_Plus.py:104-108) in ONE kernel: a CTA owns a 16 x 8 pixel tile
+// of 32 channels, stages v with a 2-pixel halo in shared memory, evaluates the first conv + GELU on the
+// tile plus a 1-pixel halo (rounded to bf16 exactly where the two-kernel pipeline stored it; zero outside
+// the map -- that is the second conv's padding) and the second conv from there.  The intermediate map
+// never goes to HBM and one launch per attention block disappears; the arithmetic order is unchanged, so
+// the result is bit-identical to the two-kernel form.
+struct DwPosP {
+    const bf16 *in; int ldi;
+    bf16 *out; int ldo;
+    const float *w1, *w2;         // [9][Cp]
+    int B, H, W, Cp;
+};
+constexpr int DP_TX = 16, DP_TY = 8, DP_CB = 32;
+__global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant__ DwPosP p) {
+    pdl_wait();
+    constexpr int IW = DP_TX + 4, IH = DP_TY + 4, MW = DP_TX + 2, MH = DP_TY + 2;
+    __shared__ __align__(16) bf16 sin[IH * IW][DP_CB];
+    __shared__ __align__(16) bf16 smid[MH * MW][DP_CB];
+    __shared__ __align__(16) float sw[2][9][DP_CB];
+    const int tid = threadIdx.x;
+    const int cblocks = p.Cp / DP_CB;
+    const int b = blockIdx.z / cblocks, c0 = (blockIdx.z - b * cblocks) * DP_CB;
+    const int x0 = blockIdx.x * DP_TX, y0 = blockIdx.y * DP_TY;
+    for (int i = tid; i < 2 * 9 * DP_CB; i += 256) {
+        const int which = i / (9 * DP_CB), r = i - which * 9 * DP_CB, t = r / DP_CB, c = r - t * DP_CB;
+        sw[which][t][c] = __ldg((which ? p.w2 : p.w1) + t * p.Cp + c0 + c);
+    }
+    // stage v: (IH x IW) pixels x 32 channels = 4 x 16-byte vectors per pixel, zeros outside the map
+    for (int i = tid; i < IH * IW * 4; i += 256) {
+        const int px = i >> 2, q = i & 3;
+        const int yy = y0 - 2 + px / IW, xx = x0 - 2 + px % IW;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W)
+            v = __ldg(reinterpret_cast<const uint4 *>(p.in + (((long long)b * p.H + yy) * p.W + xx) * p.ldi + c0) + q);
+        reinterpret_cast<uint4 *>(&sin[px][0])[q] = v;
+    }
+    __syncthreads();
+    auto conv_at = [&](const bf16 (*src)[DP_CB], int pitch, int px_centre, int g, int which, float (&acc)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const uint2 raw = *reinterpret_cast<const uint2 *>(&src[px_centre + (ky - 1) * pitch + (kx - 1)][4 * g]);
+                const float4 w = *reinterpret_cast<const float4 *>(&sw[which][ky * 3 + kx][4 * g]);
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+                acc[0] = fmaf(__low2float(h2[0]), w.x, acc[0]);
+                acc[1] = fmaf(__high2float(h2[0]), w.y, acc[1]);
+                acc[2] = fmaf(__low2float(h2[1]), w.z, acc[2]);
+                acc[3] = fmaf(__high2float(h2[1]), w.w, acc[3]);
+            }
+    };
+    // first conv + GELU on the tile and its 1-pixel halo
+    for (int i = tid; i < MH * MW * 8; i += 256) {
+        const int px = i >> 3, g = i & 7;
+        const int my = px / MW, mx = px - my * MW;
+        const int yy = y0 - 1 + my, xx = x0 - 1 + mx;
+        uint2 o = make_uint2(0u, 0u);
+        if ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W) {
+            float acc[4];
+            conv_at(sin, IW, (my + 1) * IW + (mx + 1), g, 0, acc);
+            o = make_uint2(pack_bf16(gelu(acc[0]), gelu(acc[1])), pack_bf16(gelu(acc[2]), gelu(acc[3])));
+        }
+        *reinterpret_cast<uint2 *>(&smid[px][4 * g]) = o;
+    }
+    __syncthreads();
+    // second conv
+    for (int i = tid; i < DP_TY * DP_TX * 8; i += 256) {
+        const int px = i >> 3, g = i & 7;
+        const int ty = px / DP_TX, tx = px - ty * DP_TX;
+        const int yy = y0 + ty, xx = x0 + tx;
+        if (yy < p.H && xx < p.W) {
+            float acc[4];
+            conv_at(smid, MW, (ty + 1) * MW + (tx + 1), g, 1, acc);
+            *reinterpret_cast<uint2 *>(p.out + (((long long)b * p.H + yy) * p.W + xx) * p.ldo + c0 + 4 * g) =
+                make_uint2(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ attention statistics
 // Per image and head: G[i][j] = sum_px k[px][i] q[px][j], nk[i] = sum k^2, nq[j] = sum q^2
 // (MST_Plus_Plus.py:127-129: the L2 normalisation runs over ALL pixels, so the reduction is global).
@@ -1823,8 +1905,11 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         launch_pdl(attn_finalize_kernel, dim3(cx.B, Cp / 32), dim3(1024), 0, cx.st, p);
     }
     // pos_emb(v): dw3x3 -> GELU -> dw3x3
-    dwconv(cx, ws.qkv + 2 * Cp, 3 * Cp, ws.p1, Cp, m.pos0, H, W, Cp, 1, "k4_dw_pos");
-    dwconv(cx, ws.p1, Cp, ws.p2, Cp, m.pos2, H, W, Cp, 0, "k4_dw_pos");
+    {
+        DwPosP p{ws.qkv + 2 * Cp, 3 * Cp, ws.p2, Cp, m.pos0, m.pos2, cx.B, H, W, Cp};
+        AVB_TIMED("k4_dw_pos", cx.st);
+        launch_pdl(dwpos_fused_kernel, dim3((W + DP_TX - 1) / DP_TX, (H + DP_TY - 1) / DP_TY, cx.B * (Cp / DP_CB)), dim3(256), 0, cx.st, p);
+    }
     // x = v M^T + b + pos + x
     {
         GemmP p = gemm_defaults();
