@@ -9,12 +9,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import warnings
 
 from . import _build
 
 _lock = threading.Lock()
 _lib = None
 
+AVB_VERSION = 110            # include/avb200.h AVB_VERSION
 AVB_NORM_DIV255 = 0
 AVB_NORM_AUTO = 1
 AVB_ENC_TABLE_MAX = 2048
@@ -29,6 +31,7 @@ _f = C.c_float
 SIGNATURES = {
     "avb_version": (_i, []),
     "avb_last_error": (C.c_char_p, []),
+    "avb_header_sha": (C.c_char_p, []),
     "avb_profile_begin": (_i, []),
     "avb_profile_end": (_i, [_p, _i, _p, _i]),
     "avb_build_encode_table": (_i, [_p, _p, _i]),
@@ -66,12 +69,28 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         if build_if_missing and not _build.is_current():
             try:
                 _build.build()
-            except Exception as e:  # a prebuilt .so that travelled with the snapshot is still usable
+            except Exception as e:
+                # a stale binary is only used on explicit request, and never if its ABI differs (checked below)
                 if not os.path.exists(path):
                     raise AvbError(f"libavb200.so is missing and could not be built: {e}") from e
+                if os.environ.get("AVB_ALLOW_STALE_LIB") != "1":
+                    raise AvbError(f"libavb200.so is out of date and the rebuild failed ({e}); set AVB_ALLOW_STALE_LIB=1 "
+                                   "to load the stale binary anyway") from e
+                warnings.warn(f"loading a STALE libavb200.so (rebuild failed: {e})", RuntimeWarning)
         if not os.path.exists(path):
             raise AvbError(f"{path} not found: run `python -m animal_vision_b200._build` (no CPU fallback exists)")
         lib = C.CDLL(path)
+        try:
+            sha_fn = lib.avb_header_sha
+            sha_fn.restype = C.c_char_p
+            built_against = sha_fn().decode()
+        except AttributeError:
+            built_against = "absent"
+        if built_against != _build.header_sha():
+            raise AvbError(f"{path} was compiled against another include/avb200.h (library {built_against}, header "
+                           f"{_build.header_sha()}): rebuild with `python -m animal_vision_b200._build --force`")
+        if int(lib.avb_version()) != AVB_VERSION:
+            raise AvbError(f"{path}: avb_version() = {int(lib.avb_version())}, binding expects {AVB_VERSION}")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the .so does not export it
             fn.restype = res

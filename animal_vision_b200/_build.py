@@ -37,6 +37,15 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libavb200.so cannot be built (there is no CPU fallback)")
 
 
+HEADER = os.path.join(os.path.dirname(HERE), "include", "avb200.h")
+
+
+def header_sha() -> str:
+    """What avb_header_sha() of a library built from the current header returns."""
+    with open(HEADER, "rb") as fh:
+        return hashlib.sha256(fh.read()).hexdigest()[:16]
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -72,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, "-c", src, "-o", obj] + [f for f in NVCC_FLAGS if f != "-shared"] + _extra_flags()
+        cmd = [nvcc, "-c", src, "-o", obj, f'-DAVB_HEADER_SHA="{header_sha()}"'] + [f for f in NVCC_FLAGS if f != "-shared"] + _extra_flags()
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -12,6 +12,8 @@ import numpy as np
 
 
 class Animal:
+    N_OUTPUTS = 1          # device outputs of visualize_batch (Cat: 2, the panorama species: baseline + view)
+
     def visualize(self, image: np.ndarray) -> Optional[Tuple[np.ndarray, np.ndarray]]:
         pass
 

@@ -12,6 +12,7 @@ from .animal import Animal, run_single
 
 
 class Cat(Animal):
+    N_OUTPUTS = 2
     # geometry parameters, cat.py:17-21
     CAMERA_HFOV_DEG = 100.0
     CAT_PER_EYE_HALF_FOV_DEG = 105.0

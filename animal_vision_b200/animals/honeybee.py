@@ -3,6 +3,7 @@ visualize :99-175).  The RGB->HSI step is the analytic 3-lobe model of
 ml/classic_rgb_to_hsi/classic_rgb_to_hsi.py:47-82; the cube is never materialised."""
 from __future__ import annotations
 
+import hashlib
 from typing import Callable, Literal, Optional, Tuple
 
 import numpy as np
@@ -57,6 +58,7 @@ class HoneyBee(Animal):
         sens = np.stack([self.UV_curve, self.Blue_curve, self.Green_curve])
         E = self.E(self.lambdas).astype(np.float32) if assume_hsi_is_reflectance else None
         self._band_tab, self._denom_eps = tables.uv_band_table(self.lambdas, sens, E)
+        self._band_key = hashlib.sha1(np.ascontiguousarray(self._band_tab).tobytes()).hexdigest()   # cache by CONTENT, not id()
         self._M3 = tables.uv_collapsed_matrix(self.lambdas, sens, E)
         self._taps = tables.uv_blur_taps(self.blur_sigma_px)
         self._map_params = tables.uv_map_params(custom_matrix)
@@ -66,7 +68,7 @@ class HoneyBee(Animal):
     def _run(self, eng, frames, out, dbg=None):
         bands = None
         if self.spectral_mode == "bands":
-            bands = eng.cached(("bee_bands", id(self)), lambda: eng._dev(self._band_tab))
+            bands = eng.cached(("bee_bands", self._band_key), lambda: eng._dev(self._band_tab))
         eng.uv_map(frames, out, self._M3, bands, self._denom_eps, _ADAPT[self.adaptation], self._taps,
                    _MAP[self.mapping_mode], self._map_params, 0.45, dbg)       # honeybee.py:161: alpha=0.45
 

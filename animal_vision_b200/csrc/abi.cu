@@ -91,6 +91,11 @@ int avb_profile_end(char *names, int name_stride, float *ms, int capacity) {
 
 int avb_version(void) { return AVB_VERSION; }
 
+#ifndef AVB_HEADER_SHA
+#define AVB_HEADER_SHA "unknown"
+#endif
+const char *avb_header_sha(void) { return AVB_HEADER_SHA; }
+
 const char *avb_last_error(void) { return avb::g_err; }
 
 int avb_build_encode_table(const float *thr_host, uint32_t *table_host, int capacity) {

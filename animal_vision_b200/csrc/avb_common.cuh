@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/avb200.h"
 
 namespace avb {
@@ -28,6 +30,23 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int sm_count();  // multiprocessors of the current device (cached)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember, per call
+// site, on which devices it has been set (a process may drive several GPUs, one Engine per device).
+struct SmemOptIn {
+    std::atomic<uint64_t> done{0};
+    template <class K>
+    cudaError_t ensure(K kern, int bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const bool tracked = dev >= 0 && dev < 64;
+        if (tracked && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && tracked) done.fetch_or(1ull << dev, std::memory_order_release);   // idempotent: a race only repeats it
+        return e;
+    }
+};
 
 // ---------------------------------------------------------------- per-kernel timing (bench only)
 // Between avb_profile_begin() and avb_profile_end() every kernel launched by the library on the

@@ -288,12 +288,9 @@ static int launch_k1(const K1Params &p, cudaStream_t st) {
         int64_t blocks = (total_units + K1_WARPS - 1) / K1_WARPS;
         const int64_t cap = (int64_t)sm_count() * K1_CTAS_PER_SM;   // persistent: every resident CTA walks its share of the units
         if (blocks > cap) blocks = cap;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k1_contig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
-            cudaFuncSetAttribute(k1_contig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
-            attr_set = true;
-        }
+        static SmemOptIn opt_gain, opt_plain;
+        AVB_CUDA_OK(opt_gain.ensure(k1_contig_kernel<true>, (int)sizeof(K1Smem)));
+        AVB_CUDA_OK(opt_plain.ensure(k1_contig_kernel<false>, (int)sizeof(K1Smem)));
         if (p.row_gain) k1_contig_kernel<true><<<(unsigned)blocks, K1_THREADS, sizeof(K1Smem), st>>>(p);
         else k1_contig_kernel<false><<<(unsigned)blocks, K1_THREADS, sizeof(K1Smem), st>>>(p);
     } else {

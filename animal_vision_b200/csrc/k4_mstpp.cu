@@ -1633,11 +1633,8 @@ struct Ctx {
 template <int BN, bool A_BF16, int MODE, bool DEEP>
 static void launch_gemm_td(Ctx &cx, const GemmP &p, dim3 grid, const char *name) {
     constexpr int smem = 2 * (BK / 8) * (BM / 8) * 128 + 2 * (BK / 8) * (BN / 8) * 128;
-    static bool attr_set = false;       // per instantiation; the attribute is idempotent, a race only repeats it
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::gemm_tc_kernel<BN, A_BF16, MODE, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    static SmemOptIn opt_in;              // per instantiation, per device
+    opt_in.ensure(tc::gemm_tc_kernel<BN, A_BF16, MODE, DEEP>, smem);
     AVB_TIMED(name, cx.st);
     launch_pdl(tc::gemm_tc_kernel<BN, A_BF16, MODE, DEEP>, grid, dim3(GEMM_THREADS), smem, cx.st, p);
 }
@@ -1652,11 +1649,8 @@ template <int BN, int KP, bool A_BF16, bool LN, int EPI>
 static void launch_pw_t(Ctx &cx, const GemmP &p, const char *name) {
     constexpr int smem = 2 * (KP / 8) * (BM / 8) * 128 + (KP / 8) * (BN / 8) * 128 + (LN ? 2 * KP * 4 : 0);
     constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::gemm_pw_kernel<BN, KP, A_BF16, LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    static SmemOptIn opt_in;              // per instantiation, per device
+    opt_in.ensure(tc::gemm_pw_kernel<BN, KP, A_BF16, LN, EPI>, smem);
     // resident CTAs per SM: TMEM columns, shared memory, and no more than the pipeline needs
     const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
     const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
@@ -1672,15 +1666,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeTiledFn fn = [] {             // thread-safe function-local static: resolved exactly once
         void *ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
+            return reinterpret_cast<EncodeTiledFn>(ptr);
+        return static_cast<EncodeTiledFn>(nullptr);
+    }();
     return fn;
 }
 
@@ -1716,11 +1708,8 @@ static bool launch_tma32_t(Ctx &cx, const GemmP &p, const char *name) {
     constexpr int NS = KP <= 32 ? 4 : (KP <= 64 ? 3 : 2);
     constexpr int smem = NS * (KP / 4) * (BM / 8) * 128 + (KP / 4) * (BN / 8) * 128;
     constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::gemm_tma32_kernel<BN, KP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    static SmemOptIn opt_in;              // per instantiation, per device
+    opt_in.ensure(tc::gemm_tma32_kernel<BN, KP, EPI>, smem);
     const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
     const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
     int gx = std::max(1, std::min(m_tiles, sm_count() * per_sm / std::max(1, ny * cx.B)));
@@ -1744,11 +1733,8 @@ static bool launch_tma_t(Ctx &cx, const GemmP &p, const char *name) {
     constexpr int NS = KP <= 64 ? 4 : 3;
     constexpr int smem = NS * (KP / 8) * (BM / 8) * 128 + (KP / 8) * (BN / 8) * 128;
     constexpr int tmem_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::gemm_tma_kernel<BN, KP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    static SmemOptIn opt_in;              // per instantiation, per device
+    opt_in.ensure(tc::gemm_tma_kernel<BN, KP, EPI>, smem);
     const int per_sm = std::max(1, std::min(std::min(512 / tmem_cols, (200 * 1024) / (smem + 1024)), 4));
     const int m_tiles = (p.rows + BM - 1) / BM, ny = p.Np / BN;
     int gx = std::max(1, std::min(m_tiles, sm_count() * per_sm / std::max(1, ny * cx.B)));
@@ -1839,8 +1825,8 @@ static void launch_conv3(Ctx &cx, const GemmP &p, const char *name) {
     AVB_TIMED(name, cx.st);
 #define C3_CASE(EPI_) \
     if (epi == (EPI_) && p.out_mode != OUT_CROP) { \
-        static bool attr_set = false; \
-        if (!attr_set) { cudaFuncSetAttribute(tc::conv3_stream_kernel<(EPI_)>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::C3_SMEM); attr_set = true; } \
+        static SmemOptIn opt_in; \
+        opt_in.ensure(tc::conv3_stream_kernel<(EPI_)>, tc::C3_SMEM); \
         cudaLaunchConfig_t cfg = {}; cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = tc::C3_SMEM; cfg.stream = cx.st; \
         cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1; \
         cfg.attrs = attr; cfg.numAttrs = 1; \
@@ -1850,8 +1836,8 @@ static void launch_conv3(Ctx &cx, const GemmP &p, const char *name) {
     C3_CASE(0) C3_CASE(tc::EPI_RES1)
 #undef C3_CASE
     {   // conv_out: cropped store (runtime epilogue flags)
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(tc::conv3_stream_kernel<tc::EPI_RUNTIME>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::C3_SMEM); attr_set = true; }
+        static SmemOptIn opt_in;
+        opt_in.ensure(tc::conv3_stream_kernel<tc::EPI_RUNTIME>, tc::C3_SMEM);
         cudaLaunchConfig_t cfg = {}; cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = tc::C3_SMEM; cfg.stream = cx.st;
         cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
@@ -2034,6 +2020,12 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
     AVB_REQUIRE(n > 0 && n <= 65535 && H > 1 && W > 1, "bad geometry");
     AVB_REQUIRE(pad_multiple > 0 && pad_multiple % 8 == 0, "pad_multiple must be a positive multiple of 8");
     Model *M = static_cast<Model *>(handle);
+    int cur_dev = -1;
+    AVB_CUDA_OK(cudaGetDevice(&cur_dev));
+    if (cur_dev != M->device) {            // the weights live on the device the model was created on
+        set_error("avb_mstpp_forward: model was created on device %d, current device is %d", M->device, cur_dev);
+        return AVB_E_ARG;
+    }
     int Hp, Wp, top, left;
     padded_geometry(H, W, pad_multiple, centred, Hp, Wp, top, left);
     AVB_REQUIRE(Hp - H < H && Wp - W < W, "frame too small for reflect padding");

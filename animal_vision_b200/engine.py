@@ -7,6 +7,7 @@ libavb200.so.  No CPU fallback: constructing an Engine without a CUDA device rai
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import threading
 from typing import Dict, Tuple
 
@@ -32,6 +33,16 @@ def get_engine(device=None) -> "Engine":
 
 def _fptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def _on_device(fn):
+    """Run an Engine method with the engine's device current: kernel launches, sm_count() and the
+    per-device shared-memory opt-in all act on the CURRENT device, the stream belongs to self.device."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self.torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 class Engine:
@@ -93,6 +104,7 @@ class Engine:
         return n, h, w, frames.stride(0), frames.stride(1)
 
     # ------------------------------------------------------------------ C-ABI wrappers
+    @_on_device
     def colorimetric(self, frames, out, M: np.ndarray, row_gain=None, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, ofs, ors = self.check_frames(out, "out")
@@ -105,6 +117,7 @@ class Engine:
         check(rc, "avb_colorimetric_u8")
         self.launches += 2 if norm == AVB_NORM_AUTO else 1
 
+    @_on_device
     def dichromat_blur(self, frames, out, M: np.ndarray, taps: np.ndarray, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, ofs, ors = self.check_frames(out, "out")
@@ -117,6 +130,7 @@ class Engine:
         check(rc, "avb_dichromat_blur_u8")
         self.launches += 2 if norm == AVB_NORM_AUTO else 1
 
+    @_on_device
     def streak_blur(self, frames, out, M: np.ndarray, streak, chroma: float = 0.0, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, ofs, ors = self.check_frames(out, "out")
@@ -130,6 +144,7 @@ class Engine:
         check(rc, "avb_streak_blur_u8")
         self.launches += 2 if norm == AVB_NORM_AUTO else 1
 
+    @_on_device
     def dichromat_f32(self, frames, out, tmp, M: np.ndarray, kind: int, taps=None, streak=None, row_gain=None,
                       chroma: float = 0.0, quantize: bool = False):
         """Float-frame path (include/avb200.h avb_dichromat_f32): packed float32 CUDA tensors [N,H,W,3]."""
@@ -152,6 +167,7 @@ class Engine:
         check(rc, "avb_dichromat_f32")
         self.launches += 3 + (kind != 0) + (kind == 1)
 
+    @_on_device
     def cat(self, frames, out_human, out_cat, M: np.ndarray, taps: np.ndarray, warp_dev, zoom_dev, norm=AVB_NORM_AUTO):
         n, h, w, fs, rs = self.check_frames(frames)
         _, _, _, hfs, hrs = self.check_frames(out_human, "out_human")
@@ -167,6 +183,7 @@ class Engine:
         check(rc, "avb_cat_u8")
         self.launches += 3 if norm == AVB_NORM_AUTO else 2
 
+    @_on_device
     def uv_map(self, frames, out, M3: np.ndarray, bands_dev, denom_eps: float, adapt_mode: int,
                blur_taps: np.ndarray, map_mode: int = 0, map_params=None, mix_alpha: float = 0.45, dbg_catches=None):
         n, h, w, fs, rs = self.check_frames(frames)
@@ -194,9 +211,10 @@ class Engine:
         self.launches += 3 + (4 if map_mode != 2 else 0)      # stats, prep, [hist, scan, collect, select], map
 
     # ------------------------------------------------------------------ NumPy shim staging
+    @_on_device
     def staging(self, shape, slots: int = 1):
         """(pinned_in, dev_in, [dev_out...], [pinned_out...]) for one HxWx3 uint8 frame."""
-        key = (tuple(shape), slots)
+        key = (tuple(shape), slots, threading.get_ident())     # one buffer set per calling thread: visualize() is re-entrant
         s = self._staging.get(key)
         if s is None:
             t = self.torch

@@ -84,6 +84,33 @@ def flatten_state_dict(state_dict: Mapping[str, object]) -> np.ndarray:
     return flat
 
 
+def synthetic_state_dict(seed: int = 0) -> "OrderedDict[str, object]":
+    """Deterministic synthetic weights in the reference's state_dict naming -- the reference ships no
+    checkpoint (`model_zoo` is git-ignored), so benchmarks and smoke tests run on these.  Fan-in scaled
+    normals for matrices / kernels; LayerNorm / rescale / bias values moved OFF their init values (1 / 1 / 0)
+    so that every parameter matters.  Same generator and draw order as the test oracle's make_weights
+    (tests/test_mstpp_host.py holds the two equal)."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    sd: "OrderedDict[str, object]" = OrderedDict()
+    for name, shape in param_order().items():
+        if name.endswith("norm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("rescale"):
+            t = 1.0 + 0.25 * torch.rand(shape, generator=g)
+        elif name.endswith("bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if ".decoder_layers." in name and name.endswith(".0.weight"):
+                fan_in = shape[0]                       # ConvTranspose2d k=2,s=2: one tap per output
+            t = torch.randn(shape, generator=g) * (0.7 / fan_in ** 0.5)   # gain 0.7: |y| stays O(1)
+        sd[name] = t.float()
+    return sd
+
+
 class MSTPlusPlus:
     def __init__(self, state_dict: Mapping[str, object], device=None):
         self.eng = get_engine(device)
@@ -113,6 +140,13 @@ class MSTPlusPlus:
         if not (isinstance(frames, t.Tensor) and frames.is_cuda and frames.dim() == 4 and frames.shape[3] == 3
                 and frames.dtype in (t.float32, t.uint8)):
             raise AvbError("MSTPlusPlus: expected a CUDA tensor [N,H,W,3] of float32 or uint8")
+        if frames.device != self.eng.device:
+            raise AvbError(f"MSTPlusPlus: frames live on {frames.device}, the model on {self.eng.device}")
+        with t.cuda.device(self.eng.device):           # launches act on the CURRENT device
+            return self._run_on_device(frames, pad_multiple, centred, out)
+
+    def _run_on_device(self, frames, pad_multiple: int, centred: bool, out=None):
+        t = self.eng.torch
         frames = frames.contiguous()
         n, h, w, _ = frames.shape
         need = int(self.eng.lib.avb_mstpp_workspace_bytes(n, h, w, pad_multiple, int(centred)))
@@ -174,13 +208,15 @@ class MSTPlusPlus:
         t = self.eng.torch
         a = np.asarray(image)
         assert a.ndim == 3 and a.shape[2] == 3, "Input must be HxWx3"
-        if not np.issubdtype(a.dtype, np.integer):              # predict_torch.py:12-19
+        if a.dtype == np.uint8:                                  # the uint8 path divides by 255 on the device
+            dev = t.from_numpy(np.ascontiguousarray(a)).to(self.eng.device)
+        elif np.issubdtype(a.dtype, np.integer):                 # predict_torch.py:12-15: any integer dtype is /255, never wrapped
+            dev = t.from_numpy(np.ascontiguousarray(a.astype(np.float32) / np.float32(255.0))).to(self.eng.device)
+        else:                                                    # predict_torch.py:16-19
             a = a.astype(np.float32)
             if a.max() > 1.001:
                 a = np.clip(a / 255.0, 0.0, 1.0)
             dev = t.from_numpy(np.ascontiguousarray(a)).to(self.eng.device)
-        else:
-            dev = t.from_numpy(np.ascontiguousarray(a.astype(np.uint8))).to(self.eng.device)
         return self._run(dev[None], 16, True)[0].cpu().numpy()
 
     def project_bands(self, cube, weights: np.ndarray):
@@ -193,8 +229,9 @@ class MSTPlusPlus:
         wd = t.from_numpy(w).to(self.eng.device)
         out = t.empty(tuple(cube.shape[:-1]) + (w.shape[0],), dtype=t.float32, device=self.eng.device)
         npx = cube.numel() // cube.shape[-1]
-        rc = self.eng.lib.avb_band_project_f32(cube.data_ptr(), wd.data_ptr(), out.data_ptr(), npx, w.shape[1], w.shape[0],
-                                               self.eng.stream_ptr())
+        with t.cuda.device(self.eng.device):
+            rc = self.eng.lib.avb_band_project_f32(cube.data_ptr(), wd.data_ptr(), out.data_ptr(), npx, w.shape[1], w.shape[0],
+                                                   self.eng.stream_ptr())
         check(rc, "avb_band_project_f32")
         return out
 
@@ -209,7 +246,8 @@ def safe_norm_maps(maps):
     r = maps.shape[-1]
     out = t.empty_like(maps)
     scratch = t.empty(2 * r, dtype=t.int32, device=maps.device)
-    rc = eng.lib.avb_safe_norm_f32(maps.data_ptr(), out.data_ptr(), maps.numel() // r, r, r, scratch.data_ptr(), eng.stream_ptr())
+    with t.cuda.device(eng.device):
+        rc = eng.lib.avb_safe_norm_f32(maps.data_ptr(), out.data_ptr(), maps.numel() // r, r, r, scratch.data_ptr(), eng.stream_ptr())
     check(rc, "avb_safe_norm_f32")
     return out
 

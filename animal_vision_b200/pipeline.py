@@ -38,7 +38,7 @@ class HostBatchPipeline:
 
     @staticmethod
     def n_outputs(species) -> int:
-        return 2 if type(species).__name__ == "Cat" else 1
+        return int(getattr(species, "N_OUTPUTS", 1))         # class attribute: Cat (and its subclasses) produce two frames
 
     def pinned_like(self, frames, n_out: int):
         t = self.eng.torch

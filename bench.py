@@ -32,6 +32,20 @@ import sys
 import threading
 import time
 
+
+def _affinity_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is ONE process that may use every core
+    # this process is allowed on.  BLAS / OpenMP read these at import time, so set them before numpy / torch.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_affinity_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -45,15 +59,35 @@ SPECIES = ("Dog", "Cat", "HoneyBee")
 # algorithmic bytes per pixel (uint8 in + uint8 out(s)); SURVEY.md 8(d)
 ALGO_BYTES_PER_PX = {"Dog": 6, "Cat": 9, "HoneyBee": 6}
 # per KERNEL: bytes it must read + write per output pixel (cat warp: u8 frame in, cat view out; the
-# centre zoom's output belongs to cat_center_zoom), and DRAM bytes per pixel measured once with
-# `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_all_r1h.txt)
+# centre zoom's output belongs to cat_center_zoom)
 KERNEL_ALGO_BYTES_PER_PX = {"k2_gauss_dichromat": 6.0, "k2_gauss_cat_warp": 6.0, "cat_center_zoom": 3.0 + 3.0 / 2.25,
                             "k3_uv_map": 6.0, "k3_uv_hist": 3.0, "k3_uv_stats": 3.0, "k3_uv_compact": 8.0, "k2_streak": 6.0}
-KERNEL_NCU_DRAM_BYTES_PER_PX = {"k2_gauss_dichromat": 4.39, "k2_gauss_cat_warp": 4.53, "cat_center_zoom": 2.32,
-                                "k3_uv_map": 4.54, "k3_uv_hist": 9.16, "k3_uv_stats": 3.04, "k3_uv_compact": 8.16}
+# measured DRAM traffic per launch comes from a committed ncu capture of THIS launch shape, never from a constant:
+# tools/ncu_dram_table.py turns an .ncu-rep (ncu --set full on `tools/prof_one.py ... 20` = the bench's 20-frame 4K
+# launches) into this JSON; a kernel / shape that is not in it reports traffic = null.
+NCU_DRAM_TABLE = os.path.join(ROOT, "profiles", "ncu_dram_table.json")
 KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
                   "k3_uv_stats": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_compact": "HoneyBee",
                   "k3_uv_prep": "HoneyBee", "k3_uv_scan": "HoneyBee", "k3_uv_select": "HoneyBee", "k2_streak": "Dog"}
+
+
+def bench_config():
+    """`config` of the JSON line: byte-identical in the GPU arm and the --impl reference arm (extras go to `detail`)."""
+    return {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
+            "resolution": f"{W4K}x{H4K}", "frames_per_gpu": FRAMES_PER_GPU, "species": list(SPECIES)}
+
+
+def ncu_traffic(kernel: str, frames: int, H: int, W: int):
+    """(bytes per launch, source) measured by ncu for this kernel at exactly this launch shape, else (None, why)."""
+    try:
+        with open(NCU_DRAM_TABLE) as fh:
+            tab = json.load(fh)
+    except Exception:
+        return None, "no profiles/ncu_dram_table.json"
+    for rec in tab.get("kernels", []):
+        if rec.get("bench_name") == kernel and (rec.get("frames"), rec.get("H"), rec.get("W")) == (frames, H, W):
+            return float(rec["dram_bytes_per_launch"]), f"{tab.get('source', 'profiles/ncu_dram_table.json')}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one {frames}-frame {W}x{H} launch"
+    return None, f"profiles/ncu_dram_table.json has no capture of {kernel} at {frames} x {W}x{H}"
 
 
 def log(*a):
@@ -196,8 +230,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = _affinity_cores()
+    try:                                            # one process, every core it may run on (see the top of this file)
+        import cv2
+        cv2.setNumThreads(cores)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
     threads = host_threads()
-    cores = threads.get("sched_affinity") or threads.get("os_cpu_count") or 1
     # size the per-step sample so that (warmup + steps) steps finish in ~150 s
     probe = cpu_sample(270)
     t_probe = oracle_step_time(probe)                         # 3 x 270x3840 frames
@@ -213,13 +257,13 @@ def run_reference(args):
         oracle_step_time(sample)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     mpix = px / dt / 1e6
-    desc = f"per step: 1 Dog + 1 Cat + 1 HoneyBee frame of {rows}x{W4K} (full-width band of a 4K frame), oracle port, all host threads"
+    desc = (f"per step: 1 Dog + 1 Cat + 1 HoneyBee frame of {rows}x{W4K} (full-width band of a 4K frame of the config's video: a bounded "
+            f"sample, the metric is a rate), oracle port, ONE process on {cores} host cores (rank 0 only when launched under torchrun)")
     line = {
         "impl": "reference", "metric": "Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
-                   "resolution": f"{W4K}x{H4K}", "frames_per_gpu": FRAMES_PER_GPU, "species": list(SPECIES)},
+        "config": bench_config(),
         "fps_4k": mpix * 1e6 / (H4K * W4K),
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc, "threads": threads},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -227,6 +271,80 @@ def run_reference(args):
         "probe": {"px": px_probe, "seconds": t_probe},
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- per-config legs
+CONFIG_TEXT = {"Dog": "BASELINE configs[0]: Dog dichromat transform on one synthetic 1920x1080 image",
+               "Cat": "BASELINE configs[1]: Cat LMS + acuity blur + wide-vision remap on 1080p frames",
+               "HoneyBee": "BASELINE configs[2]: HoneyBee UV via 31-band reconstruction + receptor projection at 1080p"}
+
+
+def run_config_legs(dev, species, peak, with_cpu: bool):
+    """BASELINE configs[0..2]: ONE synthetic 1080p uint8 frame.
+      visualize_*   the reference-facing call `Animal.visualize(np.ndarray)` (NumPy in, NumPy out: pinned H2D, kernels,
+                    D2H and one synchronise inside) -- median latency of 10 calls after 3 warm-up calls
+      device_*      `visualize_batch` on one device-resident frame, CUDA events; the frames rotate through a ring of 24
+                    distinct frames (149 MB in + >= 149 MB out, larger than the 126 MB L2) so no call finds its input in L2
+      roofline      whole species path (all its kernels) on one frame: algorithmic bytes (uint8 in + uint8 out(s)) / device time
+      cpu_reference the oracle port on the same frame on this host's cores (best of 2), N = 1 only"""
+    import torch
+    H, W = 1080, 1920
+    px = H * W
+    ring_n = 24
+    ring = torch.empty((ring_n, H, W, 3), dtype=torch.uint8)
+    for i in range(ring_n):
+        ring[i] = torch.from_numpy(np.random.default_rng(i).integers(0, 256, (H, W, 3), dtype=np.uint8))
+    f0 = ring[0].numpy().copy()
+    d_ring = ring.to(dev)
+    out = {}
+    for name in SPECIES:
+        sp = species[name]
+        n_out = int(getattr(sp, "N_OUTPUTS", 1))
+        for _ in range(3):
+            sp.visualize(f0)
+        lat = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            sp.visualize(f0)
+            lat.append(time.perf_counter() - t0)
+        lat_s = float(np.median(lat))
+        outs = [torch.empty_like(d_ring) for _ in range(n_out)]
+
+        def one(i):
+            o = tuple(t[i:i + 1] for t in outs) if n_out == 2 else outs[0][i:i + 1]
+            sp.visualize_batch(d_ring[i:i + 1], out=o)
+        for i in range(ring_n):
+            one(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for rep in range(2):
+            for i in range(ring_n):
+                one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms = e0.elapsed_time(e1) / (2 * ring_n)
+        bpp = ALGO_BYTES_PER_PX[name]
+        ach = bpp * px / (dev_ms * 1e-3) / 1e9
+        rec = {"config": CONFIG_TEXT[name], "frame": f"{W}x{H} uint8, default_rng(0)",
+               "visualize_ms": lat_s * 1e3, "visualize_mpix_per_s": px / lat_s / 1e6, "visualize_fps": 1.0 / lat_s,
+               "device_ms": dev_ms, "device_mpix_per_s": px / (dev_ms * 1e-3) / 1e6,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "algorithmic_bytes_per_frame": bpp * px,
+                            "note": f"{bpp} B/px x {W}x{H}; one frame per call, ring of {ring_n} frames (> L2), all kernels of the species path"}}
+        if with_cpu:
+            from oracle import mammals as M
+            from oracle import uv
+            fn = {"Dog": lambda: M.mammal_visualize(f0, "dog"), "Cat": lambda: M.cat_visualize(f0), "HoneyBee": lambda: uv.honeybee_visualize(f0)}[name]
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            rec["cpu_reference"] = {"ms": min(ts) * 1e3, "mpix_per_s": px / min(ts) / 1e6, "kind": "port", "cores": _affinity_cores()}
+        out[name] = rec
+        del outs
+    return out
 
 
 # ----------------------------------------------------------------------------- K4 leg
@@ -239,9 +357,8 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
     import torch
     if args.mstpp_batch <= 0:
         return None
-    from animal_vision_b200.mstpp import MSTPlusPlus
-    from oracle import mstpp as O                       # only for the seeded synthetic weights
-    net = MSTPlusPlus(O.make_weights(0), dev)
+    from animal_vision_b200.mstpp import MSTPlusPlus, synthetic_state_dict
+    net = MSTPlusPlus(synthetic_state_dict(0), dev)
     nb = args.mstpp_batch
     x = torch.rand(nb, 482, 512, 3, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
     parts = min(4, nb)             # patches are independent: the batch runs as `parts` concurrent forwards
@@ -262,7 +379,36 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
     except Exception:
         peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
     tf = MSTPP_FLOP_PER_PATCH * nb * world / (ms * 1e-3) / 1e12
-    return {"workload": f"MST++ forward, {nb} x 3x482x512 patches per GPU (BASELINE configs[3]), seeded weights, bf16 operands / fp32 accumulate",
+    # single patch, one stream (latency), then the ten mantis-shrimp bands + safe_norm on its cube (configs[3])
+    from animal_vision_b200.mstpp import mantis_bands, safe_norm_maps
+    x1 = x[:1].contiguous()
+    for _ in range(3):
+        cube = net.forward_nhwc(x1)
+    s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    s0.record()
+    for _ in range(iters):
+        cube = net.forward_nhwc(x1)
+    s1.record()
+    for _ in range(iters):
+        bands = safe_norm_maps(mantis_bands(cube, net))
+    s2.record()
+    barrier()
+    single_ms, bands_ms = s0.elapsed_time(s1) / iters, s1.elapsed_time(s2) / iters
+    cpu_ref = None
+    if world == 1 and not args.no_cpu:
+        from oracle import mstpp as O                    # the checker, timed as the CPU baseline of configs[3]
+        torch.set_num_threads(_affinity_cores())
+        xc = x1.permute(0, 3, 1, 2).cpu().contiguous()
+        sd = synthetic_state_dict(0)
+        t0 = time.perf_counter()
+        yc = O.forward(xc, sd)
+        cpu_s = time.perf_counter() - t0
+        rel = float((cube.permute(0, 3, 1, 2).cpu() - yc).abs().max() / yc.abs().max())
+        cpu_ref = {"ms_per_patch": cpu_s * 1e3, "patches_per_s": 1.0 / cpu_s, "kind": "port", "cores": _affinity_cores(),
+                   "what": "fp32 torch-CPU forward of the reference architecture (oracle restatement, pinned to the reference module), one 482x512 patch, all host threads",
+                   "gpu_vs_cpu_max_abs_rel": rel}
+    return {"single_patch_ms": single_ms, "mantis_bands_ms": bands_ms, "cpu_reference": cpu_ref,
+            "workload": f"MST++ forward, {nb} x 3x482x512 patches per GPU (BASELINE configs[3]), seeded weights, bf16 operands / fp32 accumulate",
             "patches_per_s": nb * world / (ms * 1e-3), "ms_per_forward": ms, "batch_per_gpu": nb, "concurrent_forwards": parts,
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,
                          "peak_source": src, "algorithmic_flop_per_patch": MSTPP_FLOP_PER_PATCH,
@@ -404,12 +550,11 @@ def run_b200(args):
     frames_per_launch = dev_in[dom_sp].shape[0]
     bpp = KERNEL_ALGO_BYTES_PER_PX.get(dom, ALGO_BYTES_PER_PX[dom_sp])
     algo_bytes = bpp * frames_per_launch * H * W
-    ncu_bpp = KERNEL_NCU_DRAM_BYTES_PER_PX.get(dom)
+    traffic, traffic_src = ncu_traffic(dom, frames_per_launch, H, W)
     peak, peak_src = peak_numbers()
     achieved = algo_bytes / (shares[dom]["ms_per_launch"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None if ncu_bpp is None else ncu_bpp * frames_per_launch * H * W, "peak_source": peak_src,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per pixel (profiles/r1_ncu_all_r1h.txt), scaled to this launch",
+                "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": f"{bpp:g} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
                 "kernel_shares": shares}
@@ -452,6 +597,10 @@ def run_b200(args):
     # ---- K4 leg (BASELINE configs[3]): MST++ forward on 482x512 patches, tensor-pipe roofline
     mstpp = run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier)
 
+    # ---- BASELINE configs[0..2]: one 1080p frame per species through visualize(np.ndarray) (rank 0 only)
+    configs = run_config_legs(dev, species, peak, with_cpu=(world == 1 and not args.no_cpu)) if rank == 0 and not args.no_configs else None
+    barrier()
+
     # sanity: the e2e outputs equal the device-resident outputs (same kernels, same inputs)
     ok = bool(torch.equal(host_out["Dog"][0][:2], dev_out["Dog"][:2].cpu()))
 
@@ -466,8 +615,8 @@ def run_b200(args):
         "metric": "Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "4K 60-frame mixed-species video batch per GPU (Dog/Cat/HoneyBee round-robin), BASELINE configs[4]",
-                   "resolution": f"{W}x{H}", "frames_per_gpu": nf, "species": list(SPECIES), "parallelism": f"frame-sharded x{world}, no collective",
+        "config": dict(bench_config(), resolution=f"{W}x{H}", frames_per_gpu=nf),
+        "detail": {"parallelism": f"frame-sharded x{world}, no collective",
                    "streams": f"{3 * nsplit} CUDA streams: every species batch in {nsplit} part(s), fork/join on the timed stream; outputs equal the single-stream step: {streams_ok}" if nsplit else "single stream",
                    "l2": f"inputs {nf * H * W * 3 / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
                    "normalisation": "AVB_NORM_AUTO (reference semantics, decided per frame on device)"},
@@ -481,6 +630,7 @@ def run_b200(args):
         "roofline": roofline,
     }
     line["mstpp"] = mstpp
+    line["configs"] = configs
     line["colorimetric"] = colorimetric
     if world == 1 and not args.no_cpu:
         threads = host_threads()
@@ -510,6 +660,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the 3840-wide CPU-baseline sample frames")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config 1080p single-frame legs")
     ap.add_argument("--streams", type=int, default=1, help="streams per species batch in the device-resident step (the batch is cut into that many parts); 0: a single stream")
     ap.add_argument("--mstpp-batch", type=int, default=4, help="482x512 patches per GPU in the MST++ leg (0: skip)")
     args = ap.parse_args()

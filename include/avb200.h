@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AVB_VERSION 100            /* 0.1.0 */
+#define AVB_VERSION 110            /* 0.1.1 */
 
 #define AVB_OK 0
 #define AVB_E_ARG (-1)             /* bad argument (null pointer, non-positive size, unsupported radius ...) */
@@ -44,6 +44,10 @@ typedef void *avb_stream_t;        /* cudaStream_t */
 
 AVB_API int avb_version(void);
 AVB_API const char *avb_last_error(void);
+/* First 16 hex digits of the SHA-256 of the include/avb200.h this library was compiled against: a binding
+ * compares it with its own copy of the header before typing any symbol, so that a stale binary whose
+ * argument lists differ is refused instead of being called with the wrong stack layout. */
+AVB_API const char *avb_header_sha(void);
 
 /* Per-kernel timing for benchmarks.  After avb_profile_begin(), every kernel the library launches
  * from the calling thread is bracketed by CUDA events on its stream; avb_profile_end() waits for

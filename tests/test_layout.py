@@ -21,9 +21,9 @@ def test_header_symbols_exported_and_typed():
         assert hasattr(lib, n), f"libavb200.so does not export {n}"
         assert n in _abi.SIGNATURES, f"_abi.SIGNATURES does not type {n}"
     assert sorted(_abi.SIGNATURES) == names, "ctypes table and header disagree"
-    assert lib.avb_version() == 100
+    assert lib.avb_version() == _abi.AVB_VERSION
     raw = ctypes.CDLL(_abi.lib_path())
-    assert raw.avb_version() == 100
+    assert raw.avb_version() == _abi.AVB_VERSION
 
 
 def test_product_never_imports_oracle_or_reference():

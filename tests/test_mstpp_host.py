@@ -30,3 +30,11 @@ def test_oracle_forward_matches_reference_golden(golden, golden_meta):
     y = O.forward(x, O.make_weights(0)).numpy()
     ref = golden("mstpp")["y"]
     assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_synthetic_state_dict_equals_oracle_weights():
+    """bench.py / tools take their seeded weights from the product (nothing product-side imports oracle/)."""
+    from animal_vision_b200 import mstpp
+    a, b = mstpp.synthetic_state_dict(0), O.make_weights(0)
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)

@@ -9,7 +9,7 @@ import torch
 
 from animal_vision_b200 import _abi
 from animal_vision_b200.mstpp import MSTPlusPlus
-from oracle import mstpp as O
+from animal_vision_b200.mstpp import synthetic_state_dict
 
 FLOP_PER_PATCH = 169.2e9     # SURVEY.md 8a-19, 482x512, 2 x MAC, unpadded channel counts
 
@@ -18,7 +18,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (482, 512)
     check = "--check" in sys.argv
-    sd = O.make_weights(0)
+    sd = synthetic_state_dict(0)
     net = MSTPlusPlus(sd)
     x = torch.rand(n, h, w, 3, generator=torch.Generator().manual_seed(1)).cuda()
     for _ in range(3):

@@ -2,8 +2,8 @@ import sys, os
 sys.path.insert(0, os.getcwd())
 import torch
 from animal_vision_b200.mstpp import MSTPlusPlus
-from oracle import mstpp as O
-net = MSTPlusPlus(O.make_weights(0))
+from animal_vision_b200.mstpp import synthetic_state_dict
+net = MSTPlusPlus(synthetic_state_dict(0))
 for nb, parts in ((4, 4), (8, 4), (8, 8), (16, 8)):
     x = torch.rand(nb, 482, 512, 3, generator=torch.Generator().manual_seed(1)).cuda()
     for _ in range(3): net.forward_nhwc_streams(x, parts)

@@ -10,7 +10,7 @@ import torch
 import animal_vision_b200.animals as A
 import frames
 from animal_vision_b200.mstpp import MSTPlusPlus
-from oracle import mstpp as O
+from animal_vision_b200.mstpp import synthetic_state_dict
 
 for (h, w) in ((37, 53), (96, 400), (130, 1100)):
     fs = np.stack([frames.noise(h, w, 1), frames.natural(h, w), frames.le1(h, w)])
@@ -23,7 +23,7 @@ for (h, w) in ((37, 53), (96, 400), (130, 1100)):
     wide = torch.zeros((3, h, w + 9, 3), dtype=torch.uint8, device="cuda")
     for name in ("Dog", "Cow", "Cat", "HoneyBee"):
         getattr(A, name)().visualize_batch(wide[:, :, 5:5 + w])
-net = MSTPlusPlus(O.make_weights(0))
+net = MSTPlusPlus(synthetic_state_dict(0))
 net(torch.rand(2, 3, 42, 52).cuda())
 net.predict_rgb_to_hsi(np.random.default_rng(0).integers(0, 256, (45, 70, 3), dtype=np.uint8))
 torch.cuda.synchronize()
