@@ -1,0 +1,389 @@
+// K6: generic float32 image operators -- the building blocks of every path that is NOT a fused uint8
+// kernel: float / wide-integer frames of Cat and HoneyBee, HoneyBee's hsi_downsample route and large
+// blur sigmas, and the UV species that are compositions of these steps (reference uv_helpers.py).
+//
+//   avb_img_to_float01   uv_helpers.py:15-23 to_float01 / animals/animal_utils.py:41-50 get_normalized_image
+//   avb_img_resample     cv2.resize as uv_helpers.py:57-64 / :84-99 / :155-183 use it (INTER_AREA, INTER_LINEAR,
+//                        INTER_CUBIC): one axis at a time with host-built (index, weight) tap tables, the
+//                        horizontal pass first as OpenCV does
+//   avb_img_blur         cv2.GaussianBlur(BORDER_REFLECT101) with explicit taps (uv_helpers.py:67-73), any radius
+//   avb_img_stats        per frame and channel min / max / mean (safe_norm :47-53, von Kries :195-206)
+//   avb_img_percentile   numpy.percentile(method="linear") of strided planes: exact radix select
+//
+// Images are device float32, packed [n, H, W, C] (C <= 4), contiguous unless strides are passed.  These
+// kernels are plain grid-stride CUDA: the fused uint8 kernels (K1-K3) are the throughput path, this file
+// is the generality path; every step still runs on the GPU (no CPU fallback anywhere).
+#include <algorithm>
+
+#include "avb_common.cuh"
+
+namespace avb {
+namespace img {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+static unsigned grid_for(long long items, int per_sm = 16) {
+    const long long want = (items + 255) / 256, cap = (long long)sm_count() * per_sm;
+    return (unsigned)std::max<long long>(1, std::min(want, cap));
+}
+
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// order-preserving map float -> uint32 (negative floats included) and back
+__device__ __forceinline__ uint32_t ord_bits(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// ------------------------------------------------------------------ frame maximum (u8 or f32 input)
+template <class T>
+__global__ void __launch_bounds__(256) frame_max_kernel(const T *__restrict__ in, long long per_frame, long long frame_stride, uint32_t *maxbits) {
+    const T *f = in + (long long)blockIdx.y * frame_stride;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per_frame; i += (long long)gridDim.x * 256) m = fmaxf(m, (float)f[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxbits + blockIdx.y, __float_as_uint(m));
+}
+
+struct ToFloatP {
+    const void *in; float *out;
+    long long per_frame, total;
+    int in_is_u8, mode;
+    const uint32_t *maxbits;
+};
+__global__ void __launch_bounds__(256) to_float01_kernel(const __grid_constant__ ToFloatP p) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.total; i += (long long)gridDim.x * 256) {
+        const float mx = __uint_as_float(p.maxbits[i / p.per_frame]);
+        float v = p.in_is_u8 ? (float)static_cast<const uint8_t *>(p.in)[i] : static_cast<const float *>(p.in)[i];
+        if (p.mode == AVB_IMG_NORM_UV) {
+            // uv_helpers.py:15-23: uint8 is always divided; other dtypes only when max > 1.001 (then clipped)
+            if (p.in_is_u8) v = __fdiv_rn(v, 255.0f);
+            else if (mx > 1.001f) v = clip01(__fdiv_rn(v, 255.0f));
+        } else {
+            // animal_utils.py:41-50: divide when max > 1, always clip
+            if (mx > 1.0f) v = __fdiv_rn(v, 255.0f);
+            v = clip01(v);
+        }
+        p.out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------ resample along one axis
+struct ResampleP {
+    const float *in; float *out;
+    int n, Hout, Wout, C, taps, axis;
+    long long in_fs, in_rs;          // element strides of the input (frame, row); pixels are packed (C floats)
+    const int *idx; const float *w;  // [len(axis)][taps]
+};
+__global__ void __launch_bounds__(256) resample_kernel(const __grid_constant__ ResampleP p) {
+    const long long total = (long long)p.n * p.Hout * p.Wout * p.C;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % p.C);
+        long long r = e / p.C;
+        const int x = (int)(r % p.Wout); r /= p.Wout;
+        const int y = (int)(r % p.Hout);
+        const long long f = r / p.Hout;
+        const float *base = p.in + f * p.in_fs;
+        float acc = 0.f;
+        if (p.axis == 0) {
+            const float *row = base + (long long)y * p.in_rs + c;
+            const int *ix = p.idx + (long long)x * p.taps;
+            const float *wt = p.w + (long long)x * p.taps;
+            for (int t = 0; t < p.taps; ++t) acc = fmaf(__ldg(wt + t), row[(long long)__ldg(ix + t) * p.C], acc);
+        } else {
+            const float *col = base + (long long)x * p.C + c;
+            const int *ix = p.idx + (long long)y * p.taps;
+            const float *wt = p.w + (long long)y * p.taps;
+            for (int t = 0; t < p.taps; ++t) acc = fmaf(__ldg(wt + t), col[(long long)__ldg(ix + t) * p.in_rs], acc);
+        }
+        p.out[e] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ blur along one axis (REFLECT_101)
+struct BlurP {
+    const float *in; float *out;
+    int n, H, W, C, R, axis;
+    const float *taps;               // device, 2R+1
+};
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ BlurP p) {
+    extern __shared__ float taps_s[];
+    for (int i = threadIdx.x; i < 2 * p.R + 1; i += 256) taps_s[i] = __ldg(p.taps + i);
+    __syncthreads();
+    const long long total = (long long)p.n * p.H * p.W * p.C;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % p.C);
+        const long long px = e / p.C;
+        const int x = (int)(px % p.W), y = (int)((px / p.W) % p.H);
+        const long long fbase = (px / ((long long)p.H * p.W)) * p.H * p.W;
+        float acc = 0.f;
+        if (p.axis == 0) {
+            const long long rbase = fbase + (long long)y * p.W;
+            if (x >= p.R && x + p.R < p.W) {
+                const float *q = p.in + (rbase + x - p.R) * p.C + c;
+                for (int k = 0; k <= 2 * p.R; ++k) acc = fmaf(taps_s[k], q[(long long)k * p.C], acc);
+            } else {
+                for (int k = -p.R; k <= p.R; ++k) acc = fmaf(taps_s[k + p.R], p.in[(rbase + reflect101(x + k, p.W)) * p.C + c], acc);
+            }
+        } else {
+            if (y >= p.R && y + p.R < p.H) {
+                const float *q = p.in + (fbase + (long long)(y - p.R) * p.W + x) * p.C + c;
+                for (int k = 0; k <= 2 * p.R; ++k) acc = fmaf(taps_s[k], q[(long long)k * p.W * p.C], acc);
+            } else {
+                for (int k = -p.R; k <= p.R; ++k) acc = fmaf(taps_s[k + p.R], p.in[(fbase + (long long)reflect101(y + k, p.H) * p.W + x) * p.C + c], acc);
+            }
+        }
+        p.out[e] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ per frame / channel min, max, sum
+struct StatsAcc {                    // scratch per (frame, channel)
+    uint32_t mn, mx;
+    double sum;
+};
+__global__ void __launch_bounds__(256) stats_kernel(const float *__restrict__ in, long long npx, int C, StatsAcc *acc) {
+    const int frame = blockIdx.y;
+    const float *f = in + (long long)frame * npx * C;
+    uint32_t mn[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[4] = {0u, 0u, 0u, 0u};
+    double sm[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
+        for (int c = 0; c < C; ++c) {
+            const float v = f[i * C + c];
+            const uint32_t o = ord_bits(v);
+            mn[c] = min(mn[c], o); mx[c] = max(mx[c], o);
+            sm[c] += (double)v;
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = min(mn[c], __shfl_xor_sync(FULL, mn[c], o));
+            mx[c] = max(mx[c], __shfl_xor_sync(FULL, mx[c], o));
+            sm[c] += __shfl_xor_sync(FULL, sm[c], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            StatsAcc *a = acc + (long long)frame * C + c;
+            atomicMin(&a->mn, mn[c]); atomicMax(&a->mx, mx[c]); atomicAdd(&a->sum, sm[c]);
+        }
+    }
+}
+__global__ void stats_init_kernel(StatsAcc *acc, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { acc[i].mn = 0xffffffffu; acc[i].mx = 0u; acc[i].sum = 0.0; }
+}
+__global__ void stats_finish_kernel(const StatsAcc *acc, int count, double npx, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        out[4 * i] = ord_float(acc[i].mn);
+        out[4 * i + 1] = ord_float(acc[i].mx);
+        out[4 * i + 2] = (float)(acc[i].sum / npx);
+        out[4 * i + 3] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ exact percentiles
+constexpr int PCT_MAX = 16, PCT_BINS = 2048;
+struct PctState {
+    uint32_t prefix, rank, cnt_le, min_gt;
+};
+struct PctP {
+    const float *in;
+    long long npx, stride;
+    int nreq, level;
+    long long off[PCT_MAX], k_lo[PCT_MAX], k_hi[PCT_MAX];
+    double gamma[PCT_MAX];
+    uint32_t *hist;                  // [nreq][PCT_BINS]
+    PctState *st;                    // [nreq]
+    float *out;                      // [nreq]
+};
+__device__ __constant__ int PCT_SHIFT[3] = {21, 10, 0};
+__device__ __constant__ int PCT_NBITS[3] = {11, 11, 10};
+
+__global__ void pct_init_kernel(const __grid_constant__ PctP p) {
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < PCT_BINS; i += blockDim.x) p.hist[r * PCT_BINS + i] = 0u;
+    if (threadIdx.x == 0) p.st[r] = PctState{0u, (uint32_t)p.k_lo[r], 0u, 0xffffffffu};
+}
+
+// level pass: histogram of this level's digit among the values that match the prefix found so far
+__global__ void __launch_bounds__(256) pct_hist_kernel(const __grid_constant__ PctP p) {
+    __shared__ uint32_t hs[PCT_BINS];
+    const int r = blockIdx.y, lv = p.level;
+    for (int i = threadIdx.x; i < PCT_BINS; i += 256) hs[i] = 0u;
+    __syncthreads();
+    const int sh = PCT_SHIFT[lv], nb = PCT_NBITS[lv];
+    const uint32_t mask = (1u << nb) - 1u, prefix = p.st[r].prefix;
+    const float *src = p.in + p.off[r];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.npx; i += (long long)gridDim.x * 256) {
+        const uint32_t b = ord_bits(src[i * p.stride]);
+        if (lv == 0 || (b >> (sh + nb)) == prefix) atomicAdd(&hs[(b >> sh) & mask], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PCT_BINS; i += 256)
+        if (hs[i]) atomicAdd(&p.hist[r * PCT_BINS + i], hs[i]);
+}
+// pick the bin that holds the rank, extend the prefix, clear the histogram for the next level
+__global__ void __launch_bounds__(1024) pct_pick_kernel(const __grid_constant__ PctP p) {
+    __shared__ uint32_t part[1024];
+    __shared__ uint32_t found[2];
+    const int r = blockIdx.x, tid = threadIdx.x, nb = PCT_NBITS[p.level], nbins = 1 << nb;
+    uint32_t *h = p.hist + r * PCT_BINS;
+    const uint32_t a = 2 * tid < nbins ? h[2 * tid] : 0u, b = 2 * tid + 1 < nbins ? h[2 * tid + 1] : 0u;
+    part[tid] = a + b;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    const uint32_t rank = p.st[r].rank, run = part[tid];
+    if (rank >= run && rank < run + a) { found[0] = 2 * tid; found[1] = rank - run; }
+    else if (rank >= run + a && rank < run + a + b) { found[0] = 2 * tid + 1; found[1] = rank - run - a; }
+    __syncthreads();
+    if (tid == 0) { p.st[r].prefix = (p.st[r].prefix << nb) | found[0]; p.st[r].rank = found[1]; }
+    h[2 * tid] = 0u; h[2 * tid + 1] = 0u;
+}
+// a = value of rank k_lo is known: count values <= a and the smallest value above it
+__global__ void __launch_bounds__(256) pct_upper_kernel(const __grid_constant__ PctP p) {
+    const int r = blockIdx.y;
+    const uint32_t a = p.st[r].prefix;
+    const float *src = p.in + p.off[r];
+    uint32_t le = 0, mg = 0xffffffffu;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.npx; i += (long long)gridDim.x * 256) {
+        const uint32_t b = ord_bits(src[i * p.stride]);
+        if (b <= a) ++le; else mg = min(mg, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        le += __shfl_xor_sync(FULL, le, o);
+        mg = min(mg, __shfl_xor_sync(FULL, mg, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&p.st[r].cnt_le, le); atomicMin(&p.st[r].min_gt, mg); }
+}
+__global__ void pct_finish_kernel(const __grid_constant__ PctP p) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.nreq) return;
+    const PctState s = p.st[r];
+    uint32_t hi = s.prefix;
+    if ((uint32_t)p.k_hi[r] >= s.cnt_le && s.min_gt != 0xffffffffu) hi = s.min_gt;
+    const double a = (double)ord_float(s.prefix), b = (double)ord_float(hi);
+    p.out[r] = (float)(a + (b - a) * p.gamma[r]);       // numpy _lerp with a float64 weight
+}
+
+}  // namespace img
+}  // namespace avb
+
+using namespace avb;
+using namespace avb::img;
+
+extern "C" int avb_img_to_float01(const void *in_dev, int in_is_u8, float *out_dev, int n, int64_t per_frame, int mode,
+                                  uint32_t *scratch_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && scratch_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && n <= 65535 && per_frame > 0, "bad geometry");
+    AVB_REQUIRE(mode == AVB_IMG_NORM_UV || mode == AVB_IMG_NORM_MAMMAL, "unknown mode");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AVB_CUDA_OK(cudaMemsetAsync(scratch_dev, 0, sizeof(uint32_t) * n, st));
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((per_frame + 255) / 256, sm_count() * 8 / n + 1));
+    {
+        AVB_TIMED("k6_frame_max", st);
+        if (in_is_u8) frame_max_kernel<uint8_t><<<dim3(bx, n), 256, 0, st>>>(static_cast<const uint8_t *>(in_dev), per_frame, per_frame, scratch_dev);
+        else frame_max_kernel<float><<<dim3(bx, n), 256, 0, st>>>(static_cast<const float *>(in_dev), per_frame, per_frame, scratch_dev);
+    }
+    ToFloatP p{in_dev, out_dev, per_frame, per_frame * n, in_is_u8, mode, scratch_dev};
+    {
+        AVB_TIMED("k6_to_float01", st);
+        to_float01_kernel<<<grid_for(p.total), 256, 0, st>>>(p);
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_img_resample(const float *in_dev, float *out_dev, int n, int Hout, int Wout, int C, int axis,
+                                int64_t in_frame_stride, int64_t in_row_stride, const int32_t *idx_dev, const float *w_dev,
+                                int taps, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && idx_dev && w_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && Hout > 0 && Wout > 0 && C >= 1 && C <= 64 && taps >= 1 && (axis == 0 || axis == 1), "bad geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ResampleP p{in_dev, out_dev, n, Hout, Wout, C, taps, axis, in_frame_stride, in_row_stride, idx_dev, w_dev};
+    AVB_TIMED(axis == 0 ? "k6_resample_x" : "k6_resample_y", st);
+    resample_kernel<<<grid_for((long long)n * Hout * Wout * C), 256, 0, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_img_blur(const float *in_dev, float *out_dev, float *tmp_dev, int n, int H, int W, int C,
+                            const float *taps_x_dev, int kx, const float *taps_y_dev, int ky, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && tmp_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && H > 0 && W > 0 && C >= 1 && C <= 64, "bad geometry");
+    AVB_REQUIRE(kx >= 1 && (kx & 1) && ky >= 1 && (ky & 1) && kx <= 4097 && ky <= 4097 && taps_x_dev && taps_y_dev, "tap counts must be odd");
+    AVB_REQUIRE(tmp_dev != in_dev && tmp_dev != out_dev, "tmp must not alias in / out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned g = grid_for((long long)n * H * W * C);
+    AVB_TIMED("k6_blur", st);
+    BlurP p{in_dev, tmp_dev, n, H, W, C, kx / 2, 0, taps_x_dev};          // rows first, as cv2.GaussianBlur
+    blur_kernel<<<g, 256, sizeof(float) * kx, st>>>(p);
+    p.in = tmp_dev; p.out = out_dev; p.R = ky / 2; p.axis = 1; p.taps = taps_y_dev;
+    blur_kernel<<<g, 256, sizeof(float) * ky, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_img_stats(const float *in_dev, int n, int64_t npx, int C, float *out_dev, void *scratch_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && scratch_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && n <= 65535 && npx > 0 && C >= 1 && C <= 4, "bad geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StatsAcc *acc = static_cast<StatsAcc *>(scratch_dev);
+    const int count = n * C;
+    AVB_TIMED("k6_stats", st);
+    stats_init_kernel<<<(count + 127) / 128, 128, 0, st>>>(acc, count);
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((npx + 255) / 256, sm_count() * 8 / n + 1));
+    stats_kernel<<<dim3(bx, n), 256, 0, st>>>(in_dev, npx, C, acc);
+    stats_finish_kernel<<<(count + 127) / 128, 128, 0, st>>>(acc, count, (double)npx, out_dev);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int64_t avb_img_percentile_scratch_bytes(int nreq) {
+    return nreq > 0 ? (int64_t)nreq * (PCT_BINS * sizeof(uint32_t) + sizeof(PctState)) + 256 : 0;
+}
+
+extern "C" int avb_img_percentile(const float *in_dev, int64_t npx, int64_t stride, const int64_t *offsets_host,
+                                  const double *q_host, int nreq, float *out_dev, void *scratch_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && offsets_host && q_host && out_dev && scratch_dev, "null pointer");
+    AVB_REQUIRE(npx > 0 && npx < (1LL << 32) && stride >= 1 && nreq >= 1, "bad geometry");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int r0 = 0; r0 < nreq; r0 += PCT_MAX) {
+        const int nr = std::min(PCT_MAX, nreq - r0);
+        PctP p{};
+        p.in = in_dev; p.npx = npx; p.stride = stride; p.nreq = nr;
+        for (int r = 0; r < nr; ++r) {
+            const double q = q_host[r0 + r];
+            AVB_REQUIRE(q >= 0.0 && q <= 100.0, "percentile outside [0, 100]");
+            const double vi = (q / 100.0) * (double)(npx - 1);       // numpy virtual index
+            p.off[r] = offsets_host[r0 + r];
+            p.k_lo[r] = (long long)vi;
+            p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
+            p.gamma[r] = vi - (double)p.k_lo[r];
+        }
+        p.hist = static_cast<uint32_t *>(scratch_dev);
+        p.st = reinterpret_cast<PctState *>(static_cast<uint8_t *>(scratch_dev) + ((size_t)nr * PCT_BINS * sizeof(uint32_t) + 255) / 256 * 256);
+        p.out = out_dev + r0;
+        AVB_TIMED("k6_percentile", st);
+        pct_init_kernel<<<nr, 256, 0, st>>>(p);
+        const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((npx + 255) / 256, sm_count() * 8 / nr + 1));
+        for (int lv = 0; lv < 3; ++lv) {
+            p.level = lv;
+            pct_hist_kernel<<<dim3(bx, nr), 256, 0, st>>>(p);
+            pct_pick_kernel<<<nr, 1024, 0, st>>>(p);
+        }
+        pct_upper_kernel<<<dim3(bx, nr), 256, 0, st>>>(p);
+        pct_finish_kernel<<<1, 32, 0, st>>>(p);
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
