@@ -21,6 +21,8 @@ AVB_NORM_DIV255 = 0
 AVB_NORM_AUTO = 1
 AVB_ENC_TABLE_MAX = 2048
 AVB_F32_POINT, AVB_F32_GAUSS, AVB_F32_STREAK = 0, 1, 2
+AVB_IMG_NORM_UV, AVB_IMG_NORM_MAMMAL = 0, 1
+AVB_STAT_MIN, AVB_STAT_MAX, AVB_STAT_MEAN = 0, 1, 2
 
 _p = C.c_void_p
 _i = C.c_int
@@ -46,6 +48,16 @@ SIGNATURES = {
     "avb_band_project_f32": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
     "avb_safe_norm_f32": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
     "avb_dichromat_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p]),
+    "avb_img_to_float01": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p]),
+    "avb_img_resample": (_i, [_p, _p, _i, _i, _i, _i, _i, _i64, _i64, _p, _p, _i, _p]),
+    "avb_img_blur": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "avb_img_stats": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
+    "avb_img_divide_channels": (_i, [_p, _p, _i, _i64, _i, _p, _i, _f, _p]),
+    "avb_img_percentile_scratch_bytes": (_i64, [_i]),
+    "avb_img_percentile": (_i, [_p, _i64, _i64, _p, _p, _i, _p, _p, _p]),
+    "avb_cat_warp_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "avb_uv_catches_f32": (_i, [_p, _p, _i64, _p, _p, _i, _f, _p]),
+    "avb_uv_map_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _i64, _i64, _p, _i, _p, _f, _p, _p]),
     "avb_uv_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "avb_uv_map_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i, _f, _i, _p, _i, _i, _p, _f, _p, _p, _p]),
 }

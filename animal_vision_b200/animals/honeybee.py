@@ -10,7 +10,7 @@ import numpy as np
 
 from .. import tables
 from ..engine import get_engine
-from .animal import Animal, run_single
+from .animal import Animal, run_single, run_single_float
 
 _ADAPT = {None: 0, "white_patch": 1, "gray_world": 2}
 _MAP = {"opponent": 0, "falsecolor": 1, "custom_matrix": 2, "uv_purple_yellow": 3, "falsecolor_uv_mixed": 4}   # AVB_MAP_*
@@ -52,8 +52,6 @@ class HoneyBee(Animal):
         if mapping_mode == "custom_matrix":
             assert custom_matrix is not None and np.shape(custom_matrix) == (3, 3), \
                 "Provide custom_matrix as 3\u00d73 for 'custom_matrix' mode."                    # honeybee.py:153-156
-        if self.hsi_downsample:
-            raise NotImplementedError("hsi_downsample=True is not implemented on the GPU path (the default is False)")
         # pixel-independent spectral tables, built once with the reference's own expressions
         sens = np.stack([self.UV_curve, self.Blue_curve, self.Green_curve])
         E = self.E(self.lambdas).astype(np.float32) if assume_hsi_is_reflectance else None
@@ -62,15 +60,47 @@ class HoneyBee(Animal):
         self._M3 = tables.uv_collapsed_matrix(self.lambdas, sens, E)
         self._taps = tables.uv_blur_taps(self.blur_sigma_px)
         self._map_params = tables.uv_map_params(custom_matrix)
-        if self._taps.size > 5:
-            raise NotImplementedError("blur_sigma_px > 2/3 (ksize > 5) is not implemented on the GPU path")
 
-    def _run(self, eng, frames, out, dbg=None):
-        bands = None
-        if self.spectral_mode == "bands":
-            bands = eng.cached(("bee_bands", self._band_key), lambda: eng._dev(self._band_tab))
-        eng.uv_map(frames, out, self._M3, bands, self._denom_eps, _ADAPT[self.adaptation], self._taps,
-                   _MAP[self.mapping_mode], self._map_params, 0.45, dbg)       # honeybee.py:161: alpha=0.45
+    def _bands_dev(self, eng):
+        if self.spectral_mode != "bands":
+            return None
+        return eng.cached(("bee_bands", self._band_key), lambda: eng._dev(self._band_tab))
+
+    def _downsampled(self) -> bool:
+        return self.hsi_downsample and 0.05 <= self.hsi_scale < 1.0                       # honeybee.py:109
+
+    def _fused_ok(self, frames) -> bool:
+        """The fused uint8 kernel (K3) covers uint8 frames at full resolution with a blur of at most 5 taps."""
+        return frames.dtype == get_engine(frames.device).torch.uint8 and not self._downsampled() and self._taps.size <= 5
+
+    def _run(self, eng, frames, out, dbg=None, quantize=False):
+        if self._fused_ok(frames) and out.dtype == frames.dtype:
+            eng.uv_map(frames, out, self._M3, self._bands_dev(eng), self._denom_eps, _ADAPT[self.adaptation], self._taps,
+                       _MAP[self.mapping_mode], self._map_params, 0.45, dbg)       # honeybee.py:161: alpha=0.45
+            return
+        self._run_planes(eng, frames, out, quantize)
+
+    def _run_planes(self, eng, frames, out, quantize):
+        """The float32 plane route (csrc/k6_imgops.cu + the f32 kernels of k3_uv.cu): float / wide-integer frames,
+        hsi_downsample (uv_helpers.py:155-183: INTER_AREA down -> analytic HSI -> INTER_LINEAR up; the band
+        projection is linear, so the three catch planes are up-sampled instead of the 31-band cube) and blur sigmas
+        beyond five taps.  Step order as honeybee.py:105-173."""
+        from .._abi import AVB_STAT_MAX, AVB_STAT_MEAN
+        from ..imgops import get_imgops
+        ops = get_imgops(eng)
+        img01 = ops.to_float01(frames.contiguous())                                        # :106
+        n, H, W, _ = img01.shape
+        if self._downsampled():                                                            # :109-116
+            hs, ws = tables.scaled_hw(H, W, self.hsi_scale)
+            small = ops.resize(img01, (hs, ws), "area")
+            ubg = ops.resize(ops.uv_catches(small, self._M3, self._bands_dev(eng), self._denom_eps), (H, W), "linear")
+        else:
+            ubg = ops.uv_catches(img01, self._M3, self._bands_dev(eng), self._denom_eps)   # :121-135
+        if self.adaptation is not None:                                                    # :138-141
+            ubg = ops.divide_channels(ubg, ops.stats(ubg), AVB_STAT_MAX if self.adaptation == "white_patch" else AVB_STAT_MEAN)
+        if self._taps.size:                                                                # :144-147
+            ubg = ops.blur_taps(ubg, self._taps)
+        ops.uv_map(ubg, out, quantize, _MAP[self.mapping_mode], self._map_params, 0.45)    # :150-173
 
     def visualize_batch(self, frames, out=None):
         eng = get_engine(frames.device)
@@ -91,5 +121,8 @@ class HoneyBee(Animal):
         assert isinstance(image, np.ndarray), "Input must be a numpy ndarray."          # honeybee.py:102-103
         assert image.ndim == 3 and image.shape[2] == 3, "Input must be HxWx3 RGB."
         eng = get_engine()
+        if image.dtype != np.uint8:         # float in => float out, wider integers => x*255+0.5 truncated (honeybee.py:170-173)
+            out = run_single_float(eng, image, lambda d_in, d_out, d_tmp, q: self._run_planes(eng, d_in, d_out, q))
+            return image, out
         (out,) = run_single(eng, image, lambda d_in, d_out: self._run(eng, d_in, d_out[0]))
         return image, out

@@ -152,7 +152,10 @@ struct Catcher {
         divide = p.adapt != 0;
     }
     __device__ __forceinline__ void operator()(uint32_t b0, uint32_t b1, uint32_t b2, float &u, float &b, float &g) const {
-        const float c0 = lut_s[b0], c1 = lut_s[b1], c2 = lut_s[b2];
+        from_linear(lut_s[b0], lut_s[b1], lut_s[b2], u, b, g);
+    }
+    // catches of one pixel from its linear-light channels (the float-frame path decodes with powf instead of the LUT)
+    __device__ __forceinline__ void from_linear(float c0, float c1, float c2, float &u, float &b, float &g) const {
         if constexpr (!BANDS) {
             u = m[0] * c0 + m[1] * c1 + m[2] * c2;
             b = m[3] * c0 + m[4] * c1 + m[5] * c2;
@@ -877,6 +880,179 @@ __global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_map_kernel(const __gri
     }
 }
 
+
+// ------------------------------------------------------------------ float32 plane path
+// The generality route (float / wide-integer frames, hsi_downsample, blur radii beyond the fused walker):
+// the (U,B,G) planes live in HBM as packed float32 [n,H,W,3] and are produced by k6_imgops steps; these
+// kernels are the same mapper / percentile code as above on a plain grid-stride pixel loop.
+__device__ __forceinline__ float srgb_decode_torch(float t) {      // classic_rgb_to_hsi.py:16-22, float32 like torch
+    return t <= 0.04045f ? __fdiv_rn(t, 12.92f) : powf(__fdiv_rn(t + 0.055f, 1.055f), 2.4f);
+}
+__device__ __forceinline__ float srgb_encode_uv(float l) {         // uv_helpers.py:40-44 (1/2.4 acts as a float32 scalar)
+    return l <= 0.0031308f ? __fmul_rn(l, 12.92f) : __fsub_rn(__fmul_rn(1.055f, powf(fmaxf(l, 0.f), 0.41666666f)), 0.055f);
+}
+
+struct CatchF32P {
+    const float *in; float *out; long long npx;      // img01 -> raw catches, both packed x3
+    UvParams uv;
+};
+template <bool BANDS>
+__global__ void __launch_bounds__(256) uv_catches_f32_kernel(const __grid_constant__ CatchF32P p) {
+    Catcher<BANDS> cat;
+    cat.init_raw(p.uv, nullptr);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.npx; i += (long long)gridDim.x * 256) {
+        const float c0 = srgb_decode_torch(p.in[3 * i]), c1 = srgb_decode_torch(p.in[3 * i + 1]), c2 = srgb_decode_torch(p.in[3 * i + 2]);
+        float u, b, g;
+        cat.from_linear(c0, c1, c2, u, b, g);
+        p.out[3 * i] = u; p.out[3 * i + 1] = b; p.out[3 * i + 2] = g;
+    }
+}
+
+struct PlaneP {
+    const float *ubg;           // [n][H*W][3] adapted + blurred catches
+    void *out;                  // uint8 (strided frames) or float32 packed
+    int out_f32, quantize;
+    UvParams uv;
+};
+
+// per-frame channel maxima of the planes -> UvFrameStats.max_bits (bin sizing only)
+__global__ void __launch_bounds__(256) uv_planemax_kernel(const __grid_constant__ PlaneP p) {
+    const int frame = blockIdx.y;
+    const long long npx = (long long)p.uv.io.H * p.uv.io.W;
+    const float *f = p.ubg + (long long)frame * npx * 3;
+    float m[3] = {0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m[k] = fmaxf(m[k], f[3 * i + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[k] = fmaxf(m[k], __shfl_xor_sync(FULL, m[k], o));
+        if ((threadIdx.x & 31) == 0) atomicMax(&p.uv.stats[frame].max_bits[k], __float_as_uint(m[k]));
+    }
+}
+
+template <int QS>
+__global__ void __launch_bounds__(256) uv_hist_f32_kernel(const __grid_constant__ PlaneP p) {
+    __shared__ uint32_t hs[QCount<QS>::value * UV_BINS];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    for (int i = tid; i < QCount<QS>::value * UV_BINS; i += 256) hs[i] = 0u;
+    __syncthreads();
+    const UvFrameStats &st = p.uv.stats[frame];
+    const long long npx = (long long)p.uv.io.H * p.uv.io.W;
+    const float *f = p.ubg + (long long)frame * npx * 3;
+    float *planes = p.uv.planes + (long long)frame * UV_NH * npx;
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < npx; i += (long long)gridDim.x * 256) {
+        const float c[3] = {f[3 * i], f[3 * i + 1], f[3 * i + 2]};
+        float q[UV_NH];
+        quantities<QS>(c, q);
+#pragma unroll
+        for (int h = 0; h < QCount<QS>::value; ++h) {
+            // catches are non-negative by construction (non-negative lobes, illuminant, sensitivities, blur and
+            // area / linear resampling weights), as on the uint8 route
+            atomicAdd(&hs[h * UV_BINS + bin_of(q[h], st.inv_w[h])], 1u);
+            planes[h * npx + i] = q[h];
+        }
+    }
+    __syncthreads();
+    uint32_t *gh = p.uv.hist + (int64_t)frame * UV_NH * UV_BINS;
+    for (int i = tid; i < QCount<QS>::value * UV_BINS; i += 256)
+        if (hs[i]) atomicAdd(gh + i, hs[i]);
+}
+
+__device__ __forceinline__ void fill_map_consts(const UvParams &p, const UvFrameStats &st, int mapper, MapConsts &k) {
+    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
+    k.pL = st.pct[1] + p.eps;
+    k.rpr = __frcp_rn(k.pr);
+    k.rpL = __frcp_rn(k.pL);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { k.d95[i] = fmaxf(st.pct[i], p.eps); k.r95[i] = __frcp_rn(k.d95[i]); }
+    k.d98 = fmaxf(mapper == MAP_PURPLE ? st.pct[0] : st.pct[3], p.eps);
+    k.r98 = __frcp_rn(k.d98);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        k.c0[i] = p.anchors[i];
+        k.c1[i] = p.anchors[3 + i];
+        k.pd[i] = __fsub_rn(k.c0[i], 0.5f);
+        k.m[3 * i] = p.map_m[3 * i]; k.m[3 * i + 1] = p.map_m[3 * i + 1]; k.m[3 * i + 2] = p.map_m[3 * i + 2];
+    }
+    k.alpha = p.mix_alpha;
+}
+
+template <int MAPPER>
+__global__ void __launch_bounds__(256) uv_map_f32_kernel(const __grid_constant__ PlaneP p) {
+    __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
+    const int frame = blockIdx.y;
+    if (!p.out_f32) copy_to_smem(enc_s, p.uv.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.uv.enc + 2)));
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+    MapConsts k;
+    fill_map_consts(p.uv, p.uv.stats[frame], MAPPER, k);
+    const int W = p.uv.io.W;
+    const long long npx = (long long)p.uv.io.H * W;
+    const float *f = p.ubg + (long long)frame * npx * 3;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
+        const float c[3] = {f[3 * i], f[3 * i + 1], f[3 * i + 2]};
+        float rgb[3];
+        map_pixel<MAPPER>(c, k, rgb);
+        if (p.out_f32) {
+            float *o = static_cast<float *>(p.out) + ((long long)frame * npx + i) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float v = srgb_encode_uv(__saturatef(rgb[ch]));        // honeybee.py:166-169
+                if (p.quantize) v = truncf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f));       // :170-171 for integer dtypes
+                o[ch] = v;
+            }
+        } else {
+            const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+            uint8_t *o = static_cast<uint8_t *>(p.out) + (int64_t)frame * p.uv.io.out_fs + (int64_t)y * p.uv.io.out_rs + 3 * x;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)encode_u8(enc, rgb[ch]);
+        }
+    }
+}
+
+template <int MAPPER>
+static int launch_mapper_f32(const PlaneP &pp, cudaStream_t st) {
+    constexpr int QS = MAPPER == MAP_OPPONENT ? QS_OPP : (MAPPER == MAP_PURPLE ? QS_U : QS_UBG);
+    const UvParams &p = pp.uv;
+    const long long npx = (long long)p.io.H * p.io.W;
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((npx + 255) / 256, (long long)sm_count() * 8 / p.io.n + 1));
+    if (p.n_req > 0) {
+        {
+            AVB_TIMED("k3_uv_planemax", st);
+            uv_planemax_kernel<<<dim3(bx, p.io.n), 256, 0, st>>>(pp);
+        }
+        {
+            AVB_TIMED("k3_uv_prep", st);
+            uv_prep_kernel<QS><<<(p.io.n + 63) / 64, 64, 0, st>>>(p);      // adapt = 0: bins sized from the plane maxima
+        }
+        {
+            AVB_TIMED("k3_uv_hist_f32", st);
+            uv_hist_f32_kernel<QS><<<dim3(bx, p.io.n), 256, 0, st>>>(pp);
+        }
+        {
+            AVB_TIMED("k3_uv_scan", st);
+            uv_scan_kernel<<<p.io.n, 256, 0, st>>>(p);
+        }
+        {
+            AVB_TIMED("k3_uv_compact", st);
+            uv_compact_kernel<<<dim3((unsigned)((npx + CP_PER_BLOCK - 1) / CP_PER_BLOCK), p.n_req, p.io.n), 256, 0, st>>>(p);
+        }
+        {
+            AVB_TIMED("k3_uv_select", st);
+            uv_select_kernel<<<dim3(p.n_req, p.io.n), SEL_THREADS, 0, st>>>(p);
+        }
+    }
+    {
+        AVB_TIMED("k3_uv_map_f32", st);
+        uv_map_f32_kernel<MAPPER><<<dim3(bx, p.io.n), 256, 0, st>>>(pp);
+    }
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
 // ------------------------------------------------------------------ launch plumbing
 static int qset_of(int mapper) {
     switch (mapper) {
@@ -1066,5 +1242,77 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
         case 0: return dispatch_mapper<0, false>(p, st);
         case 1: return dispatch_mapper<1, false>(p, st);
         default: return dispatch_mapper<2, false>(p, st);
+    }
+}
+
+// ---- float32 plane route (include/avb200.h: avb_uv_catches_f32 / avb_uv_map_f32)
+extern "C" int avb_uv_catches_f32(const float *img01_dev, float *catches_dev, int64_t npx, const float *m3_host,
+                                  const float *bands_dev, int n_bands, float denom_eps, avb_stream_t stream) {
+    AVB_REQUIRE(img01_dev && catches_dev && m3_host, "null pointer");
+    AVB_REQUIRE(npx > 0, "bad geometry");
+    AVB_REQUIRE(n_bands >= 0 && n_bands <= UV_MAX_BANDS && (n_bands == 0 || bands_dev), "bad band table");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CatchF32P p{};
+    p.in = img01_dev; p.out = catches_dev; p.npx = npx;
+    for (int i = 0; i < 9; ++i) p.uv.M3[i] = m3_host[i];
+    p.uv.bands = bands_dev; p.uv.n_bands = n_bands; p.uv.denom_eps = denom_eps;
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((npx + 255) / 256, (long long)sm_count() * 16));
+    AVB_TIMED("k3_uv_catches_f32", st);
+    if (n_bands) uv_catches_f32_kernel<true><<<bx, 256, 0, st>>>(p);
+    else uv_catches_f32_kernel<false><<<bx, 256, 0, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_uv_map_f32(const float *ubg_dev, void *out, int out_is_f32, int quantize, int n, int H, int W,
+                              int64_t out_frame_stride, int64_t out_row_stride, const uint32_t *enc_dev,
+                              int map_mode, const float *map_params_host, float mix_alpha,
+                              void *workspace_dev, avb_stream_t stream) {
+    AVB_REQUIRE(ubg_dev && out && workspace_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && (long long)H * W < (1LL << 31), "bad frame geometry");
+    AVB_REQUIRE(out_is_f32 || (enc_dev && out_row_stride >= 3LL * W), "uint8 output needs the encode table and a row stride >= 3*W");
+    AVB_REQUIRE(map_mode >= 0 && map_mode <= MAP_MIXED, "unknown map_mode");
+    AVB_REQUIRE(map_mode == MAP_OPPONENT || map_mode == MAP_FALSECOLOR || map_params_host, "this map_mode needs map_params_host");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PlaneP pp{};
+    pp.ubg = ubg_dev; pp.out = out; pp.out_f32 = out_is_f32; pp.quantize = quantize;
+    UvParams &p = pp.uv;
+    p.io = FrameIO{nullptr, out_is_f32 ? nullptr : static_cast<uint8_t *>(out), 0, 0, out_frame_stride, out_row_stride, n, H, W};
+    p.enc = enc_dev;
+    p.adapt = 0;
+    p.eps = 1e-8f;
+    p.mapper = map_mode;
+    if (map_params_host) {
+        for (int i = 0; i < 9; ++i) p.map_m[i] = map_params_host[i];
+        for (int i = 0; i < 6; ++i) p.anchors[i] = map_params_host[9 + i];
+    }
+    p.mix_alpha = mix_alpha;
+    const long long npx = (long long)H * W;
+    uint8_t *ws = static_cast<uint8_t *>(workspace_dev);
+    const size_t stats_bytes = align_up((size_t)n * sizeof(UvFrameStats), 256);
+    const size_t hist_bytes = (size_t)n * UV_NH * UV_BINS * sizeof(uint32_t);
+    const size_t planes_bytes = n_requests(map_mode) ? (size_t)n * UV_NH * (size_t)npx * sizeof(float) : 0;
+    p.stats = reinterpret_cast<UvFrameStats *>(ws);
+    p.hist = reinterpret_cast<uint32_t *>(ws + stats_bytes);
+    p.planes = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes);
+    p.cand = reinterpret_cast<float *>(ws + stats_bytes + hist_bytes + planes_bytes);
+    p.cap = npx;
+    p.n_req = n_requests(map_mode);
+    const double pcts[5][UV_NR] = {{95, 95, 0, 0}, {95, 95, 95, 0}, {0, 0, 0, 0}, {98, 0, 0, 0}, {95, 95, 95, 98}};
+    const int hists[5][UV_NR] = {{0, 1, 0, 0}, {0, 1, 2, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 0}};
+    for (int r = 0; r < p.n_req; ++r) {
+        const double vi = (pcts[map_mode][r] / 100.0) * (double)(npx - 1);
+        p.req_hist[r] = hists[map_mode][r];
+        p.k_lo[r] = (long long)vi;
+        p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
+        p.gamma[r] = vi - (double)p.k_lo[r];
+    }
+    AVB_CUDA_OK(cudaMemsetAsync(ws, 0, stats_bytes + hist_bytes, st));
+    switch (map_mode) {
+        case MAP_OPPONENT: return launch_mapper_f32<MAP_OPPONENT>(pp, st);
+        case MAP_FALSECOLOR: return launch_mapper_f32<MAP_FALSECOLOR>(pp, st);
+        case MAP_MATRIX: return launch_mapper_f32<MAP_MATRIX>(pp, st);
+        case MAP_PURPLE: return launch_mapper_f32<MAP_PURPLE>(pp, st);
+        default: return launch_mapper_f32<MAP_MIXED>(pp, st);
     }
 }

@@ -186,6 +186,56 @@ __global__ void stats_finish_kernel(const StatsAcc *acc, int count, double npx, 
     }
 }
 
+// ------------------------------------------------------------------ cat binocular wide-FOV warp on float frames
+// animals/cat_widevision_utils.py:46-99 on a float32 [0,1] frame: cv2.remap INTER_LINEAR (map coordinate quantised
+// to 1/32 px, two taps, BORDER_CONSTANT 0; the row map is the identity) for the two eye views, cos^2 blend,
+// division by wL + wR + 1e-8, clip.  Table layout as avb_cat_u8's warp_dev: xL, xR, wL, wR, ws, 1/ws (6*W floats).
+struct CatWarpP {
+    const float *in; float *out; const float *tab;
+    int n, H, W;
+};
+__device__ __forceinline__ void warp_tap(const float *row, int W, float xs, float &c0, float &c1, float &c2) {
+    const int sx = __float2int_rn(xs * 32.0f);
+    const int ix = sx >> 5;
+    const float f = (float)(sx & 31) * (1.0f / 32.0f), w0 = 1.0f - f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if ((unsigned)ix < (unsigned)W) { a0 = row[3 * ix]; a1 = row[3 * ix + 1]; a2 = row[3 * ix + 2]; }
+    if ((unsigned)(ix + 1) < (unsigned)W) { b0 = row[3 * ix + 3]; b1 = row[3 * ix + 4]; b2 = row[3 * ix + 5]; }
+    c0 = __fadd_rn(__fmul_rn(a0, w0), __fmul_rn(b0, f));
+    c1 = __fadd_rn(__fmul_rn(a1, w0), __fmul_rn(b1, f));
+    c2 = __fadd_rn(__fmul_rn(a2, w0), __fmul_rn(b2, f));
+}
+__global__ void __launch_bounds__(256) cat_warp_kernel(const __grid_constant__ CatWarpP p) {
+    const long long npx = (long long)p.n * p.H * p.W;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
+        const int x = (int)(i % p.W);
+        const float *row = p.in + (i - x) * 3;
+        const float wL = __ldg(p.tab + 2 * p.W + x), wR = __ldg(p.tab + 3 * p.W + x), ws = __ldg(p.tab + 4 * p.W + x);
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (wL != 0.0f) warp_tap(row, p.W, __ldg(p.tab + x), l0, l1, l2);
+        if (wR != 0.0f) warp_tap(row, p.W, __ldg(p.tab + p.W + x), r0, r1, r2);
+        p.out[3 * i] = clip01(__fdiv_rn(__fadd_rn(__fmul_rn(l0, wL), __fmul_rn(r0, wR)), ws));
+        p.out[3 * i + 1] = clip01(__fdiv_rn(__fadd_rn(__fmul_rn(l1, wL), __fmul_rn(r1, wR)), ws));
+        p.out[3 * i + 2] = clip01(__fdiv_rn(__fadd_rn(__fmul_rn(l2, wL), __fmul_rn(r2, wR)), ws));
+    }
+}
+
+// ------------------------------------------------------------------ von Kries: x / max(stat, eps) per frame and channel
+struct DivideP {
+    const float *in; float *out; const float *stats;     // stats: [n][C][4] = min, max, mean, 0 (avb_img_stats)
+    long long npx, total;
+    int C, which;
+    float eps;
+};
+__global__ void __launch_bounds__(256) divide_kernel(const __grid_constant__ DivideP p) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < p.total; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % p.C);
+        const long long f = e / (p.npx * p.C);
+        const float s = fmaxf(p.stats[(f * p.C + c) * 4 + p.which], p.eps);     // uv_helpers.py:195-206
+        p.out[e] = __fdiv_rn(p.in[e], s);
+    }
+}
+
 // ------------------------------------------------------------------ exact percentiles
 constexpr int PCT_MAX = 16, PCT_BINS = 2048;
 struct PctState {
@@ -344,6 +394,29 @@ extern "C" int avb_img_stats(const float *in_dev, int n, int64_t npx, int C, flo
     const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((npx + 255) / 256, sm_count() * 8 / n + 1));
     stats_kernel<<<dim3(bx, n), 256, 0, st>>>(in_dev, npx, C, acc);
     stats_finish_kernel<<<(count + 127) / 128, 128, 0, st>>>(acc, count, (double)npx, out_dev);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_cat_warp_f32(const float *in01_dev, float *out_dev, int n, int H, int W, const float *warp_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in01_dev && out_dev && warp_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && H > 0 && W > 0 && in01_dev != out_dev, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CatWarpP p{in01_dev, out_dev, warp_dev, n, H, W};
+    AVB_TIMED("k6_cat_warp", st);
+    cat_warp_kernel<<<grid_for((long long)n * H * W), 256, 0, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_img_divide_channels(const float *in_dev, float *out_dev, int n, int64_t npx, int C, const float *stats_dev,
+                                       int which, float eps, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && stats_dev, "null pointer");
+    AVB_REQUIRE(n > 0 && npx > 0 && C >= 1 && C <= 4 && (which == AVB_STAT_MAX || which == AVB_STAT_MEAN), "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DivideP p{in_dev, out_dev, stats_dev, npx, (long long)n * npx * C, C, which, eps};
+    AVB_TIMED("k6_divide", st);
+    divide_kernel<<<grid_for(p.total), 256, 0, st>>>(p);
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }

@@ -386,3 +386,89 @@ MANTIS_BANDS = ((320, 360), (360, 400), (400, 430), (430, 460), (460, 490),
 
 def mantis_band_matrix(lam: np.ndarray) -> np.ndarray:
     return np.stack([bandpass_weights(lam, float(lo), float(hi)) for lo, hi in MANTIS_BANDS]).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- cv2.resize tap tables (float images)
+def _cubic_coeffs(x: np.ndarray) -> np.ndarray:
+    """OpenCV interpolateCubic (A = -0.75), float32 arithmetic; taps at sx-1 .. sx+2."""
+    A = np.float32(-0.75)
+    x = x.astype(np.float32)
+    one = np.float32(1.0)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    c2 = ((A + np.float32(2)) * (one - x) - (A + np.float32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], axis=1).astype(np.float32)
+
+
+def resize_taps(src: int, dst: int, interp: str, *, vertical: bool = False):
+    """(idx int32 [dst, taps], w float32 [dst, taps]) such that one axis of cv2.resize on a float image is
+    out[d] = sum_t w[d, t] * in[idx[d, t]]  (borders already resolved in idx), restating OpenCV's own coordinate
+    arithmetic (imgproc/resize.cpp): `linear` / `cubic` (fx = (d + 0.5) * scale - 0.5 in float32; the horizontal
+    linear pass zeroes the fraction at the borders, everything else clamps indices) and `area` (downscale only:
+    computeResizeAreaTab; integer factors give the uniform 1/factor block mean of resizeAreaFast).
+    Used by uv_helpers.py:57-64 / :84-99 / :155-183 and cat_widevision_utils.py:26 on float frames."""
+    src, dst = int(src), int(dst)
+    scale = float(src) / float(dst)
+    if interp in ("linear", "cubic"):
+        f = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = f - s.astype(np.float32)
+        if interp == "linear":
+            if not vertical:
+                lo = s < 0
+                f[lo] = 0
+                s[lo] = 0
+                hi = s >= src - 1
+                f[hi] = 0
+                s[hi] = src - 1
+            idx = np.stack([s, s + 1], axis=1)
+            w = np.stack([np.float32(1.0) - f, f], axis=1)
+        else:
+            idx = np.stack([s - 1, s, s + 1, s + 2], axis=1)
+            w = _cubic_coeffs(f)
+        return np.clip(idx, 0, src - 1).astype(np.int32), np.ascontiguousarray(w, np.float32)
+    if interp != "area":
+        raise ValueError(f"unknown interpolation {interp}")
+    if dst > src:
+        raise ValueError("INTER_AREA tables are for down-scaling")
+    rows = []
+    for d in range(dst):
+        fsx1 = d * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, src - fsx1)
+        sx1, sx2 = int(math.ceil(fsx1)), int(math.floor(fsx2))
+        sx2 = min(sx2, src - 1)
+        sx1 = min(sx1, sx2)
+        taps = []
+        if sx1 - fsx1 > 1e-3:
+            taps.append((sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            taps.append((sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            taps.append((sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+        rows.append(taps)
+    nt = max(len(r) for r in rows)
+    idx = np.zeros((dst, nt), np.int32)
+    w = np.zeros((dst, nt), np.float32)
+    for d, taps in enumerate(rows):
+        for t, (i, a) in enumerate(taps):
+            idx[d, t], w[d, t] = i, a
+        for t in range(len(taps), nt):
+            idx[d, t] = taps[-1][0]          # zero-weight padding reads a valid sample
+    return idx, w
+
+
+def panorama_geometry(W: int, scale_x: float):
+    """uv_helpers.py:84-99 panorama_warp: (newW, start) of the widen + centre crop, or None when it is the identity."""
+    if abs(scale_x - 1.0) < 1e-3:
+        return None
+    newW = max(2, int(round(W * scale_x)))
+    if newW == W:
+        return newW, 0
+    return newW, (newW - W) // 2
+
+
+def scaled_hw(H: int, W: int, scale: float):
+    """uv_helpers.py:169-171 classic_rgb_to_hsi_scaled: size of the down-sampled frame."""
+    return max(1, int(round(H * scale))), max(1, int(round(W * scale)))

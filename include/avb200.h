@@ -231,6 +231,71 @@ AVB_API int avb_dichromat_f32(const float *in_dev, float *out_dev, float *tmp_de
                               const float *row_tab_dev, const float *row_gain_dev, float chroma, int quantize,
                               uint32_t *maxbits_dev, avb_stream_t stream);
 
+/* ---- K6: generic float32 image operators (csrc/k6_imgops.cu) -------------------------------------
+ * The generality route behind the fused uint8 kernels: float / wide-integer frames, HoneyBee's
+ * hsi_downsample and large blur sigmas, and the UV species composed from uv_helpers.py steps.
+ * Images: device float32, packed [n, H, W, C]. */
+#define AVB_IMG_NORM_UV 0          /* uv_helpers.py:15-23 to_float01: uint8 / 255; other dtypes clip(x/255) only if max > 1.001 */
+#define AVB_IMG_NORM_MAMMAL 1      /* animals/animal_utils.py:41-50 get_normalized_image: / 255 if max > 1, then clip to [0,1] */
+/* in_dev: n frames of per_frame values, uint8 (in_is_u8 = 1) or float32; scratch_dev: n uint32. */
+AVB_API int avb_img_to_float01(const void *in_dev, int in_is_u8, float *out_dev, int n, int64_t per_frame, int mode,
+                               uint32_t *scratch_dev, avb_stream_t stream);
+
+/* One axis of cv2.resize (uv_helpers.py:57-64 resize_preserve_range, :84-99 panorama_warp, :155-183
+ * classic_rgb_to_hsi_scaled; animals/cat_widevision_utils.py:11-29 center_zoom on float frames):
+ *   axis 0: out[f][y][x][c] = sum_t w[x][t] * in[f][y][idx[x][t]][c]      (Hout rows of the input are read)
+ *   axis 1: out[f][y][x][c] = sum_t w[y][t] * in[f][idx[y][t]][x][c]
+ * idx_dev / w_dev: [len(axis)][taps] tables built by the host with OpenCV's own coordinate arithmetic
+ * (animal_vision_b200/tables.py resize_taps: INTER_LINEAR, INTER_CUBIC, INTER_AREA); borders are already
+ * resolved in idx.  in_frame_stride / in_row_stride are in ELEMENTS (a crop is a pointer offset + strides);
+ * the output is contiguous [n, Hout, Wout, C].  OpenCV runs the horizontal pass first. */
+AVB_API int avb_img_resample(const float *in_dev, float *out_dev, int n, int Hout, int Wout, int C, int axis,
+                             int64_t in_frame_stride, int64_t in_row_stride, const int32_t *idx_dev, const float *w_dev,
+                             int taps, avb_stream_t stream);
+
+/* Separable correlation with BORDER_REFLECT_101, rows first: cv2.GaussianBlur(img, (k,k), sigma) as
+ * uv_helpers.py:67-73 gaussian_blur calls it (k = 2*ceil(3*sigma)+1; any odd tap count).  taps on the device. */
+AVB_API int avb_img_blur(const float *in_dev, float *out_dev, float *tmp_dev, int n, int H, int W, int C,
+                         const float *taps_x_dev, int kx, const float *taps_y_dev, int ky, avb_stream_t stream);
+
+/* Per frame and channel {min, max, mean, 0} -> out_dev[n][C][4] (uv_helpers.py:47-53 safe_norm, :195-206 von
+ * Kries).  scratch_dev: 16 * n * C bytes. */
+#define AVB_STAT_MIN 0
+#define AVB_STAT_MAX 1
+#define AVB_STAT_MEAN 2
+AVB_API int avb_img_stats(const float *in_dev, int n, int64_t npx, int C, float *out_dev, void *scratch_dev, avb_stream_t stream);
+/* out = in / max(stats[f][c][which], eps): von_kries_white_patch (AVB_STAT_MAX) / _gray_world (AVB_STAT_MEAN). */
+AVB_API int avb_img_divide_channels(const float *in_dev, float *out_dev, int n, int64_t npx, int C, const float *stats_dev,
+                                    int which, float eps, avb_stream_t stream);
+
+/* numpy.percentile(x, q) (method "linear", float32 result) of nreq strided planes: request r covers the npx
+ * values in_dev[offsets_host[r] + i*stride]; exact (three-level radix select over the float bit patterns, then
+ * numpy's interpolation between the two neighbouring order statistics).  Used by uv_mappers.py:29-43,
+ * animals/rat_uv.py:171-174 and siblings.  scratch_dev: avb_img_percentile_scratch_bytes(min(nreq,16)). */
+AVB_API int64_t avb_img_percentile_scratch_bytes(int nreq);
+AVB_API int avb_img_percentile(const float *in_dev, int64_t npx, int64_t stride, const int64_t *offsets_host,
+                               const double *q_host, int nreq, float *out_dev, void *scratch_dev, avb_stream_t stream);
+
+/* animals/cat_widevision_utils.py:46-99 animal_fov_binocular_warp on float32 [0,1] frames [n,H,W,3] (the float-frame
+ * route of Cat.visualize, animals/cat.py:83-93): both eye views by cv2.remap's 1/32-px bilinear, cos^2 blend, clip.
+ * warp_dev: the 6*W table of avb_cat_u8.  out_dev must not alias in01_dev. */
+AVB_API int avb_cat_warp_f32(const float *in01_dev, float *out_dev, int n, int H, int W, const float *warp_dev, avb_stream_t stream);
+
+/* Float32 plane route of the UV path (animals/honeybee.py:99-175 for float / wide-integer frames,
+ * hsi_downsample = True and blur sigmas beyond the fused walker):
+ *   avb_uv_catches_f32  img01 [npx][3] -> sRGB decode (classic_rgb_to_hsi.py:16-22) -> analytic spectrum ->
+ *                       illuminant -> raw receptor catches [npx][3] (honeybee.py:126-135); tables as avb_uv_map_u8
+ *   avb_uv_map_f32      adapted + blurred (U,B,G) planes [n][H][W][3] -> mapper with its global percentiles
+ *                       (uv_mappers.py) -> clip -> OETF -> uint8 frames (strided) or float32 [n][H][W][3]
+ *                       (quantize = 1: x*255+0.5 truncated, for integer dtypes other than uint8)
+ *   workspace_dev       avb_uv_workspace_bytes(n, H, W, map_mode) bytes */
+AVB_API int avb_uv_catches_f32(const float *img01_dev, float *catches_dev, int64_t npx, const float *m3_host,
+                               const float *bands_dev, int n_bands, float denom_eps, avb_stream_t stream);
+AVB_API int avb_uv_map_f32(const float *ubg_dev, void *out, int out_is_f32, int quantize, int n, int H, int W,
+                           int64_t out_frame_stride, int64_t out_row_stride, const uint32_t *enc_dev,
+                           int map_mode, const float *map_params_host, float mix_alpha,
+                           void *workspace_dev, avb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

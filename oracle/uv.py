@@ -243,11 +243,49 @@ def map_falsecolor_uv_mixed(U, B, G, alpha: float = 0.35) -> np.ndarray:
     return np.clip(mixed.astype(np.float32), 0.0, 1.0)
 
 
+# ----------------------------------------------------------------------------- resampling helpers
+def resize_preserve_range(x: np.ndarray, out_hw, interp: int) -> np.ndarray:
+    """uv_helpers.py:57-64."""
+    import cv2
+    was_float = np.issubdtype(x.dtype, np.floating)
+    y = cv2.resize(x.astype(np.float32, copy=False), (int(out_hw[1]), int(out_hw[0])), interpolation=interp)
+    return y.astype(x.dtype, copy=False) if not was_float else y
+
+
+def analytic_hsi_scaled(rgb01: np.ndarray, wavelengths: np.ndarray, scale: float) -> np.ndarray:
+    """uv_helpers.py:155-183 classic_rgb_to_hsi_scaled: INTER_AREA down -> analytic HSI -> INTER_LINEAR up."""
+    import cv2
+    assert 0.0 < scale <= 1.0
+    H, W = rgb01.shape[:2]
+    hs, ws = max(1, int(round(H * scale))), max(1, int(round(W * scale)))
+    small = resize_preserve_range(rgb01, (hs, ws), cv2.INTER_AREA)
+    cube = analytic_hsi(small, wavelengths.astype(np.float32))
+    return resize_preserve_range(cube, (H, W), cv2.INTER_LINEAR)
+
+
+def panorama_warp(img_lin: np.ndarray, scale_x: float) -> np.ndarray:
+    """uv_helpers.py:84-99: bicubic horizontal widen, centre crop back to the original width."""
+    import cv2
+    if abs(scale_x - 1.0) < 1e-3:
+        return img_lin
+    H, W = img_lin.shape[:2]
+    newW = max(2, int(round(W * scale_x)))
+    widened = cv2.resize(img_lin, (newW, H), interpolation=cv2.INTER_CUBIC)
+    if newW == W:
+        return widened
+    start = (newW - W) // 2
+    return widened[:, start:start + W, :]
+
+
 # ----------------------------------------------------------------------------- HoneyBee
-def honeybee_receptors(image: np.ndarray, lam: np.ndarray | None = None, *, reflectance=True):
+def honeybee_receptors(image: np.ndarray, lam: np.ndarray | None = None, *, reflectance=True,
+                       hsi_downsample: bool = False, hsi_scale: float = 0.1):
     """honeybee.py:105-135: raw (U, B, G) cone catches through the full 31-band cube."""
     lam = default_wavelengths() if lam is None else lam
-    hsi = analytic_hsi(to_float01(image), lam)
+    if hsi_downsample and 0.05 <= hsi_scale < 1.0:                       # honeybee.py:109-116
+        hsi = analytic_hsi_scaled(to_float01(image), lam, hsi_scale)
+    else:
+        hsi = analytic_hsi(to_float01(image), lam)
     radiance = hsi * d65_like(lam).astype(hsi.dtype)[None, None, :] if reflectance else hsi
     cu, cb, cg = honeybee_curves(lam)
     return (np.tensordot(radiance, cu, axes=([2], [0])),
@@ -256,11 +294,11 @@ def honeybee_receptors(image: np.ndarray, lam: np.ndarray | None = None, *, refl
 
 
 def honeybee_visualize(image: np.ndarray, *, adaptation="white_patch", mapping_mode="opponent",
-                       blur_sigma_px=0.2, custom_matrix=None):
+                       blur_sigma_px=0.2, custom_matrix=None, hsi_downsample=False, hsi_scale=0.1):
     """HoneyBee.visualize with constructor defaults (honeybee.py:47-66, :99-175).
     Returns (image, out): the baseline is the input object itself."""
     assert isinstance(image, np.ndarray) and image.ndim == 3 and image.shape[2] == 3
-    U, B, G = honeybee_receptors(image)
+    U, B, G = honeybee_receptors(image, hsi_downsample=hsi_downsample, hsi_scale=hsi_scale)
     U, B, G = von_kries(U, B, G, adaptation)
     sigma = float(blur_sigma_px or 0.0)
     if sigma > 0:
