@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -47,6 +48,31 @@ struct SmemOptIn {
         return e;
     }
 };
+
+// ---------------------------------------------------------------- numpy.percentile(float32 data, python-float q)
+// NumPy divides q by float32(100) and keeps the virtual index (n-1)*q in FLOAT32 (numpy/lib/_function_base_impl.py:
+// percentile -> _quantile -> _lerp); the two neighbouring order statistics are blended in float32, from the upper
+// one when the weight is >= 0.5.  Restated exactly (3000/3000 random cases bit-equal in tools/probe notes).
+struct PctIndex {
+    long long k_lo, k_hi;
+    float gamma;
+};
+inline PctIndex numpy_percentile_index(double q, long long n) {
+    const float qq = (float)q / 100.0f;
+    const float vi = (float)(n - 1) * qq;
+    PctIndex r;
+    r.k_lo = (long long)floorf(vi);
+    if (r.k_lo > n - 1) r.k_lo = n - 1;
+    if (r.k_lo < 0) r.k_lo = 0;
+    r.k_hi = r.k_lo + 1 < n ? r.k_lo + 1 : r.k_lo;
+    r.gamma = vi - (float)r.k_lo;
+    if (r.gamma < 0.f) r.gamma = 0.f;
+    return r;
+}
+__device__ __forceinline__ float numpy_lerp(float a, float b, float g) {
+    const float d = __fsub_rn(b, a);
+    return g >= 0.5f ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+}
 
 // ---------------------------------------------------------------- per-kernel timing (bench only)
 // Between avb_profile_begin() and avb_profile_end() every kernel launched by the library on the

@@ -85,7 +85,7 @@ struct UvParams {
     int n_req;
     int req_hist[UV_NR];
     long long k_lo[UV_NR], k_hi[UV_NR];
-    double gamma[UV_NR];
+    float gamma[UV_NR];
     int mapper;
     float map_m[9];              // MAP_MATRIX
     float anchors[6];            // MAP_PURPLE / MAP_MIXED: linear-light purple and warm anchors
@@ -304,12 +304,15 @@ __device__ __forceinline__ float sqrt_sfu(float x) {
 }
 
 // ------------------------------------------------------------------ mapper quantities
-template <int QS>
+// PRECISE (the float32 plane route, whose float outputs are compared at 1e-5): IEEE sqrt / libm atan2 instead of
+// the SFU forms that are ample for uint8 outputs.
+template <int QS, bool PRECISE = false>
 __device__ __forceinline__ void quantities(const float (&c)[3], float (&q)[UV_NH]) {
     if (QS == QS_OPP) {
         // uv_mappers.py:55-60
         const float O1 = c[2] - c[1], O2 = c[1] - c[0];
-        q[0] = sqrt_sfu(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        const float r2 = __fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2));
+        q[0] = PRECISE ? __fsqrt_rn(r2) : sqrt_sfu(r2);
         q[1] = div_by(__fadd_rn(__fadd_rn(c[0], c[1]), c[2]), 3.0f, 0.333333343267440796f);
         q[2] = 0.f;
     } else {
@@ -686,8 +689,7 @@ __global__ void __launch_bounds__(SEL_THREADS) uv_select_kernel(const __grid_con
     if (tid == 0) {
         uint32_t b_bits = a_bits;
         if (st.rank_hi[r] >= cnt_le && min_gt != 0xffffffffu) b_bits = min_gt;
-        const double a = (double)__uint_as_float(a_bits), b = (double)__uint_as_float(b_bits);
-        st.pct[r] = (float)(a + (b - a) * p.gamma[r]);      // numpy _lerp with a float64 weight
+        st.pct[r] = numpy_lerp(__uint_as_float(a_bits), __uint_as_float(b_bits), p.gamma[r]);
     }
 }
 
@@ -754,16 +756,18 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     return y < 0.f ? -r : r;
 }
 
-template <int MAPPER>
+template <int MAPPER, bool PRECISE = false>
 __device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &k, float (&rgb)[3]) {
     if (MAPPER == MAP_OPPONENT) {
         // uv_mappers.py:53-64 and hsv_to_rgb :14-26
         const float U = c[0], B = c[1], G = c[2];
         const float O1 = G - B, O2 = B - U;
         const float L = div_by(__fadd_rn(__fadd_rn(U, B), G), 3.0f, 0.333333343267440796f);
-        const float radius = sqrt_sfu(__fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2)));
+        const float r2 = __fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2));
+        const float radius = PRECISE ? __fsqrt_rn(r2) : sqrt_sfu(r2);
         const float PI_F = 3.14159274101257324f;          // float32(np.pi)
-                const float hue = div_by(__fadd_rn(atan2_fast(O2, O1), PI_F), 6.28318548202514648f, 0.159154936671257019f);
+        const float ang = PRECISE ? atan2f(O2, O1) : atan2_fast(O2, O1);
+        const float hue = div_by(__fadd_rn(ang, PI_F), 6.28318548202514648f, 0.159154936671257019f);
         const float sat = __saturatef(div_by(radius, k.pr, k.rpr));
         const float val = __saturatef(div_by(L, k.pL, k.rpL));
         const float h6 = __fmul_rn(hue, 6.0f);
@@ -946,7 +950,7 @@ __global__ void __launch_bounds__(256) uv_hist_f32_kernel(const __grid_constant_
     for (long long i = (long long)blockIdx.x * 256 + tid; i < npx; i += (long long)gridDim.x * 256) {
         const float c[3] = {f[3 * i], f[3 * i + 1], f[3 * i + 2]};
         float q[UV_NH];
-        quantities<QS>(c, q);
+        quantities<QS, true>(c, q);
 #pragma unroll
         for (int h = 0; h < QCount<QS>::value; ++h) {
             // catches are non-negative by construction (non-negative lobes, illuminant, sensitivities, blur and
@@ -995,7 +999,7 @@ __global__ void __launch_bounds__(256) uv_map_f32_kernel(const __grid_constant__
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
         const float c[3] = {f[3 * i], f[3 * i + 1], f[3 * i + 2]};
         float rgb[3];
-        map_pixel<MAPPER>(c, k, rgb);
+        map_pixel<MAPPER, true>(c, k, rgb);
         if (p.out_f32) {
             float *o = static_cast<float *>(p.out) + ((long long)frame * npx + i) * 3;
 #pragma unroll
@@ -1214,11 +1218,9 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
     const int hists[5][UV_NR] = {{0, 1, 0, 0}, {0, 1, 2, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 0}};
     (void)qs;
     for (int r = 0; r < p.n_req; ++r) {
-        const double vi = (pcts[map_mode][r] / 100.0) * (double)(npx - 1);
+        const PctIndex pi = numpy_percentile_index(pcts[map_mode][r], npx);    // float32 virtual index, as NumPy computes it
         p.req_hist[r] = hists[map_mode][r];
-        p.k_lo[r] = (long long)vi;
-        p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
-        p.gamma[r] = vi - (double)p.k_lo[r];
+        p.k_lo[r] = pi.k_lo; p.k_hi[r] = pi.k_hi; p.gamma[r] = pi.gamma;
     }
 
     AVB_CUDA_OK(cudaMemsetAsync(ws, 0, stats_bytes + hist_bytes, st));
@@ -1301,11 +1303,9 @@ extern "C" int avb_uv_map_f32(const float *ubg_dev, void *out, int out_is_f32, i
     const double pcts[5][UV_NR] = {{95, 95, 0, 0}, {95, 95, 95, 0}, {0, 0, 0, 0}, {98, 0, 0, 0}, {95, 95, 95, 98}};
     const int hists[5][UV_NR] = {{0, 1, 0, 0}, {0, 1, 2, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 0}};
     for (int r = 0; r < p.n_req; ++r) {
-        const double vi = (pcts[map_mode][r] / 100.0) * (double)(npx - 1);
+        const PctIndex pi = numpy_percentile_index(pcts[map_mode][r], npx);    // float32 virtual index, as NumPy computes it
         p.req_hist[r] = hists[map_mode][r];
-        p.k_lo[r] = (long long)vi;
-        p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
-        p.gamma[r] = vi - (double)p.k_lo[r];
+        p.k_lo[r] = pi.k_lo; p.k_hi[r] = pi.k_hi; p.gamma[r] = pi.gamma;
     }
     AVB_CUDA_OK(cudaMemsetAsync(ws, 0, stats_bytes + hist_bytes, st));
     switch (map_mode) {

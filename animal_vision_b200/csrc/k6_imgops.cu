@@ -246,7 +246,7 @@ struct PctP {
     long long npx, stride;
     int nreq, level;
     long long off[PCT_MAX], k_lo[PCT_MAX], k_hi[PCT_MAX];
-    double gamma[PCT_MAX];
+    float gamma[PCT_MAX];
     uint32_t *hist;                  // [nreq][PCT_BINS]
     PctState *st;                    // [nreq]
     float *out;                      // [nreq]
@@ -321,8 +321,7 @@ __global__ void pct_finish_kernel(const __grid_constant__ PctP p) {
     const PctState s = p.st[r];
     uint32_t hi = s.prefix;
     if ((uint32_t)p.k_hi[r] >= s.cnt_le && s.min_gt != 0xffffffffu) hi = s.min_gt;
-    const double a = (double)ord_float(s.prefix), b = (double)ord_float(hi);
-    p.out[r] = (float)(a + (b - a) * p.gamma[r]);       // numpy _lerp with a float64 weight
+    p.out[r] = numpy_lerp(ord_float(s.prefix), ord_float(hi), p.gamma[r]);
 }
 
 }  // namespace img
@@ -437,11 +436,9 @@ extern "C" int avb_img_percentile(const float *in_dev, int64_t npx, int64_t stri
         for (int r = 0; r < nr; ++r) {
             const double q = q_host[r0 + r];
             AVB_REQUIRE(q >= 0.0 && q <= 100.0, "percentile outside [0, 100]");
-            const double vi = (q / 100.0) * (double)(npx - 1);       // numpy virtual index
+            const PctIndex pi = numpy_percentile_index(q, npx);     // float32 virtual index, as NumPy computes it
             p.off[r] = offsets_host[r0 + r];
-            p.k_lo[r] = (long long)vi;
-            p.k_hi[r] = p.k_lo[r] + 1 < npx ? p.k_lo[r] + 1 : p.k_lo[r];
-            p.gamma[r] = vi - (double)p.k_lo[r];
+            p.k_lo[r] = pi.k_lo; p.k_hi[r] = pi.k_hi; p.gamma[r] = pi.gamma;
         }
         p.hist = static_cast<uint32_t *>(scratch_dev);
         p.st = reinterpret_cast<PctState *>(static_cast<uint8_t *>(scratch_dev) + ((size_t)nr * PCT_BINS * sizeof(uint32_t) + 255) / 256 * 256);
