@@ -28,6 +28,10 @@
 // animals/cat.py:95-101).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+#include <cuda_fp16.h>
 
 #include "avb_common.cuh"
 
@@ -63,6 +67,7 @@ struct GaussCommon {
     uint32_t *flags;       // per-frame "some byte >= 2" (AVB_NORM_AUTO) or nullptr
     int seg_h;             // rows per segment (multiple of G_RB)
     int fixup;             // 1: second launch, only frames whose flag stayed 0 are (re)processed
+    int radius;            // tensor-core variant: the radius is a run-time value there
 };
 
 // ------------------------------------------------------------------------------------ producers
@@ -595,6 +600,363 @@ gauss_stream_kernel(const __grid_constant__ GaussCommon p, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------ tensor-core variant
+// The separable Gaussian of the two-plane LUT path as two banded-Toeplitz matrix products on the tensor cores
+// (mma.sync m16n8k16, f16 operands, f32 accumulate): per output pixel and plane the CUDA cores used to issue
+// 2 x (2R+1) FMAs (116 of Dog's 261 instructions per pixel); here a warp instruction retires 2 048 MACs.
+// Register-fragment MMAs rather than tcgen05: the operator is BANDED, and a 16-wide output tile needs only
+// K = 16 + 2R (padded to 32/48) inputs per output, where a 128-row UMMA tile would multiply 128 + 2R -- the
+// tensor pipe would become the bound of an otherwise CUDA-core kernel (measured mma.sync rate on B200:
+// 555 TFLOP/s, tools/micro/hmma_rate.cu; this kernel needs 0.13 TFLOP per 20 4K frames at 29 taps).
+//
+//   produce   as above (TMA-staged packed rows, LUT decode, 2x3 matrix) into a PLANAR F16 tile S[plane][part]
+//             [16 rows][x halo]; every value is split x = hi + lo (two f16) so the operand keeps 22 mantissa bits
+//   H pass    D[16 rows x 8 cols] += S[16 rows x 16s..16s+15] * T_s,  T_s[k][n] = w[16s + k - n]: the Toeplitz
+//             fragments are pixel independent and live in registers for the whole kernel (6 words)
+//   ring      the H results (hi + lo again) of the last (D+1) blocks of 16 rows, D = ceil(2R/16)
+//   V pass    D[16 out rows x 8 cols] += T'_s[16 x 16] * ring[block ob+s][16 rows x 8 cols] (ldmatrix.trans)
+//   encode    expand the two planes, table encode, packed bytes staged in shared memory, 128-bit stores.
+// Taps are rounded to f16 on the host with the rounding error diffused so that they still sum to 1 (flat
+// regions stay exact); the accumulation is f32.
+constexpr int M_RB = 16;            // rows per block (the M of the H pass, the N tile rows of the V pass)
+constexpr int M_THREADS = 256;      // 8 warps: warp w owns output column tiles 2w, 2w+1 of both planes
+constexpr int M_HP = 136;           // ring pitch in halves: 272 B = 17 x 16 B (ldmatrix rows hit distinct banks)
+constexpr int M_STAGE_PITCH = 3 * G_TW + 16;   // 400 B = 100 words: the 8 fragment rows of a warp land in distinct banks
+constexpr int M_RAW_PITCH = 512;
+constexpr int M_LUT_COPIES = 4;     // decode LUT replicated: lane l reads copy l & 3 (random byte values spread over 4x the banks)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+// x = hi + lo, both f16 (lo carries the rounding error of hi)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = pack_h2(a - f.x, b - f.y);
+}
+
+template <int KSH>
+struct MmaCfg {
+    static constexpr int SP = 120 + 16 * KSH;     // S pitch in halves: 272 / 304 / 336 B = 17 / 19 / 21 x 16 B
+};
+
+struct MmaGeom {
+    int radius, r4;        // blur radius; left halo of the produced tile = radius rounded up to 4 px (word-aligned packed rows)
+    int groups;            // 4-pixel decode groups per row: ceil((128 + r4 + radius) / 4)
+    uint32_t div_groups;   // ceil(2^16 / groups): idx / groups == (idx * div_groups) >> 16 for idx < 16 * groups
+};
+
+template <int KSH, int D, bool SPLIT>
+__global__ void __launch_bounds__(M_THREADS, 2)
+gauss_mma_kernel(const __grid_constant__ GaussCommon p, const __grid_constant__ DogProducer::Params pp, const __grid_constant__ MmaGeom geo) {
+    constexpr int SP = MmaCfg<KSH>::SP;
+    constexpr int NP = SPLIT ? 2 : 1;             // operand parts (hi, lo)
+    constexpr int KSV = D + 1;                    // k-steps of the V pass = ring depth in blocks
+    constexpr int S_PLANE = M_RB * SP;            // halves per (plane, part)
+    constexpr int H_PLANE = KSV * M_RB * M_HP;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __half *S = reinterpret_cast<__half *>(smem_raw);                     // [2][NP][16][SP]
+    __half *HR = S + 2 * NP * S_PLANE;                                     // [2][NP][KSV*16][M_HP]
+    uint8_t *stage = reinterpret_cast<uint8_t *>(HR + 2 * NP * H_PLANE);   // [16][400] encoded bytes of an output block
+    float *lut4 = reinterpret_cast<float *>(stage + M_RB * M_STAGE_PITCH); // [256][M_LUT_COPIES]
+    uint32_t *enc_s = reinterpret_cast<uint32_t *>(lut4 + 256 * M_LUT_COPIES);
+    uint8_t *rawt0 = reinterpret_cast<uint8_t *>(enc_s + G_ENC_SMEM);      // [2][16][M_RAW_PITCH] packed input rows (TMA double buffer)
+    __shared__ __align__(8) uint64_t rbar[2];
+
+    const int frame = blockIdx.z;
+    if (p.fixup && p.flags[frame] != 0) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int H = p.io.H, W = p.io.W, R = geo.radius, R4 = geo.r4;
+    const int x0 = blockIdx.x * G_TW;
+    const int y_start = blockIdx.y * p.seg_h;
+    const int y_end = min(H, y_start + p.seg_h);
+    const int GROUPS = geo.groups, IN_W = 4 * GROUPS;
+
+    const uint8_t *src_frame = p.io.in + (int64_t)frame * p.io.in_fs;
+    for (int i = tid; i < 256 * M_LUT_COPIES; i += M_THREADS) lut4[i] = __ldg(pp.lut + (i / M_LUT_COPIES));
+    copy_to_smem(enc_s, p.enc, min(G_ENC_SMEM, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    // the pad columns of S only ever meet zero Toeplitz entries, but they must hold finite numbers
+    for (int i = tid; i < 2 * NP * S_PLANE / 2; i += M_THREADS) reinterpret_cast<uint32_t *>(S)[i] = 0u;
+    if (tid == 0) {
+        gauss_mbar_init(&rbar[0], M_RB);
+        gauss_mbar_init(&rbar[1], M_RB);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+    const float *lut_l = lut4 + (lane & (M_LUT_COPIES - 1));
+    float qm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) qm[i] = pp.M.m[i];
+    uint32_t seen = 0;
+    auto px2 = [&](uint32_t b0, uint32_t b1, uint32_t b2, float &o0, float &o1) {
+        const float l0 = lut_l[M_LUT_COPIES * b0], l1 = lut_l[M_LUT_COPIES * b1], l2 = lut_l[M_LUT_COPIES * b2];
+        o0 = qm[0] * l0 + qm[1] * l1 + qm[2] * l2;         // same expression as DogProducer::px
+        o1 = qm[3] * l0 + qm[4] * l1 + qm[5] * l2;
+    };
+
+    // Toeplitz fragments, f16x2, zero outside the taps.  H pass (S column i = image column x0 - R4 + i, so the taps
+    // start R4 - R columns into the window): k-step s: b0 = th[2s], b1 = th[2s+1], th[j] = (w[8j + 2t - g - off], next).
+    // V pass k-step s: a0 = a3 = tv[2s], a1 = tv[2s-1], a2 = tv[2s+1], tv[j] = (w[8j + 2t - g], next).
+    uint32_t th[2 * KSH], tv[2 * KSV];
+    {
+        const int off = R4 - R;
+        auto wt = [&](int i) { return (i >= 0 && i <= 2 * R) ? p.taps[i] : 0.f; };
+#pragma unroll
+        for (int j = 0; j < 2 * KSH; ++j) th[j] = pack_h2(wt(8 * j + 2 * t - g - off), wt(8 * j + 2 * t - g - off + 1));
+#pragma unroll
+        for (int j = 0; j < 2 * KSV; ++j) tv[j] = pack_h2(wt(8 * j + 2 * t - g), wt(8 * j + 2 * t - g + 1));
+    }
+
+    uint8_t *dst_frame = p.io.out + (int64_t)frame * p.io.out_fs;
+    const bool vec_ok = (x0 + G_TW <= W) && ((p.io.out_rs & 15) == 0) && ((p.io.out_fs & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.io.out) & 15) == 0);
+    const bool in16 = ((p.io.in_rs & 15) == 0) && ((p.io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.io.in) & 15) == 0);
+    // Interior strips: the produced span [x0 - R4, x0 - R4 + IN_W) lies inside the row; its packed bytes start word aligned.
+    // Border strips: the in-image part of the span is staged, REFLECT_101 columns are resolved against the staged bytes.
+    const int c_lo = max(0, x0 - R4), c_hi = min(W, x0 - R4 + IN_W);
+    const int a_byte = 3 * (x0 - R4);
+    const int a0 = (3 * c_lo) & ~15;
+    const int n_chunks = (3 * c_hi - a0 + 15) >> 4;
+    const bool interior = x0 - R4 >= 0 && x0 - R4 + IN_W <= W;
+    // every reflected column of a border strip must fall inside the staged span
+    const bool refl_ok = reflect101(x0 - R4, W) < c_hi && reflect101(x0 - R4 + IN_W - 1, W) >= c_lo && W > IN_W;
+    const bool staged = in16 && 16 * n_chunks <= M_RAW_PITCH && a0 + 16 * n_chunks <= 3 * W && ((a_byte & 3) == 0) && (interior || refl_ok);
+
+    const int n_out_blocks = (y_end - y_start + M_RB - 1) / M_RB;
+    const int n_blocks = n_out_blocks + D;
+
+    auto raw_issue = [&](int ib_, int buf) {
+        if (tid < M_RB) {
+            const uint8_t *gsrc = src_frame + (int64_t)reflect101(y_start - R + ib_ * M_RB + tid, H) * p.io.in_rs + a0;
+            gauss_bulk_load(rawt0 + buf * (M_RB * M_RAW_PITCH) + tid * M_RAW_PITCH, gsrc, 16u * (uint32_t)n_chunks, &rbar[buf]);
+        }
+    };
+    uint32_t rphase = 0;
+    if (staged) raw_issue(0, 0);
+
+    const uint32_t S_sh = gauss_smem(S), HR_sh = gauss_smem(HR);
+    // ldmatrix lane roles: matrix mi = lane >> 3, row (lane & 7) + 8 (mi & 1), second half of the pair mi >> 1
+    const int l_row = (lane & 7) + 8 * ((lane >> 3) & 1), l_hi = lane >> 4;
+
+    auto store_px = [&](int r, int i, float o0, float o1) {
+        const __half h0 = __float2half_rn(o0), h1 = __float2half_rn(o1);
+        S[r * SP + i] = h0;
+        S[NP * S_PLANE + r * SP + i] = h1;
+        if (SPLIT) {
+            S[S_PLANE + r * SP + i] = __float2half_rn(o0 - __half2float(h0));
+            S[NP * S_PLANE + S_PLANE + r * SP + i] = __float2half_rn(o1 - __half2float(h1));
+        }
+    };
+
+    // ---- produce block ib: 16 rows x IN_W columns of the two planes as f16 (hi, lo)
+    auto produce = [&](int ib) {
+        const int yb = y_start - R + ib * M_RB;
+        if (staged) {
+            const int buf = ib & 1;
+            const uint8_t *rawt = rawt0 + buf * (M_RB * M_RAW_PITCH);
+            gauss_mbar_wait(&rbar[buf], (rphase >> buf) & 1u);
+            rphase ^= 1u << buf;
+            if (ib + 1 < n_blocks) raw_issue(ib + 1, buf ^ 1);
+            if (interior) {
+                const int w_off = (a_byte - a0) >> 2;
+                for (int idx = tid; idx < M_RB * GROUPS; idx += M_THREADS) {
+                    const int r = (int)(((uint32_t)idx * geo.div_groups) >> 16), gq = idx - r * GROUPS;
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rawt + r * M_RAW_PITCH) + w_off + 3 * gq;
+                    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                    seen |= w0 | w1 | w2;
+                    float a[4], b[4];
+                    px2(__byte_perm(w0, 0, 0x4440), __byte_perm(w0, 0, 0x4441), __byte_perm(w0, 0, 0x4442), a[0], b[0]);
+                    px2(__byte_perm(w0, 0, 0x4443), __byte_perm(w1, 0, 0x4440), __byte_perm(w1, 0, 0x4441), a[1], b[1]);
+                    px2(__byte_perm(w1, 0, 0x4442), __byte_perm(w1, 0, 0x4443), __byte_perm(w2, 0, 0x4440), a[2], b[2]);
+                    px2(__byte_perm(w2, 0, 0x4441), __byte_perm(w2, 0, 0x4442), __byte_perm(w2, 0, 0x4443), a[3], b[3]);
+                    __half *d0 = S + r * SP + 4 * gq, *d1 = d0 + NP * S_PLANE;
+                    if (SPLIT) {
+                        uint2 hi, lo;
+                        split_h2(a[0], a[1], hi.x, lo.x); split_h2(a[2], a[3], hi.y, lo.y);
+                        *reinterpret_cast<uint2 *>(d0) = hi; *reinterpret_cast<uint2 *>(d0 + S_PLANE) = lo;
+                        split_h2(b[0], b[1], hi.x, lo.x); split_h2(b[2], b[3], hi.y, lo.y);
+                        *reinterpret_cast<uint2 *>(d1) = hi; *reinterpret_cast<uint2 *>(d1 + S_PLANE) = lo;
+                    } else {
+                        *reinterpret_cast<uint2 *>(d0) = make_uint2(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]));
+                        *reinterpret_cast<uint2 *>(d1) = make_uint2(pack_h2(b[0], b[1]), pack_h2(b[2], b[3]));
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < M_RB * IN_W; idx += M_THREADS) {
+                    const int r = (int)(((uint32_t)(idx >> 2) * geo.div_groups) >> 16), i = idx - r * IN_W;
+                    const uint8_t *q = rawt + r * M_RAW_PITCH + 3 * reflect101(x0 - R4 + i, W) - a0;
+                    const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
+                    seen |= b0 | b1 | b2;
+                    float o0, o1;
+                    px2(b0, b1, b2, o0, o1);
+                    store_px(r, i, o0, o1);
+                }
+            }
+        } else {
+            // unaligned frames, frames narrower than the tile: pixel by pixel from global memory
+            for (int idx = tid; idx < M_RB * IN_W; idx += M_THREADS) {
+                const int r = (int)(((uint32_t)(idx >> 2) * geo.div_groups) >> 16), i = idx - r * IN_W;
+                const uint8_t *q = src_frame + (int64_t)reflect101(yb + r, H) * p.io.in_rs + 3 * reflect101(x0 - R4 + i, W);
+                const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
+                seen |= b0 | b1 | b2;
+                float o0, o1;
+                px2(b0, b1, b2, o0, o1);
+                store_px(r, i, o0, o1);
+            }
+        }
+    };
+
+    // ---- H pass of block ib into ring slot ib % KSV
+    auto hpass = [&](int ib) {
+        const int slot = ib % KSV;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            float acc[2][4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[e][c] = 0.f;
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                // half-fragments (16 rows x 8 columns) at columns 16 warp + 8 h, h = 0 .. 2 KSH
+                uint32_t hf[2 * KSH + 1][2];
+                const uint32_t base = S_sh + 2u * (uint32_t)((pl * NP + part) * S_PLANE + l_row * SP + 16 * warp);
+#pragma unroll
+                for (int q = 0; q < KSH; ++q) {
+                    uint32_t r4[4];
+                    ldsm_x4(r4, base + 2u * (uint32_t)(16 * q + 8 * l_hi));
+                    hf[2 * q][0] = r4[0]; hf[2 * q][1] = r4[1]; hf[2 * q + 1][0] = r4[2]; hf[2 * q + 1][1] = r4[3];
+                }
+                {
+                    uint32_t r2[2];
+                    ldsm_x2(r2, base + 2u * (uint32_t)(16 * KSH));
+                    hf[2 * KSH][0] = r2[0]; hf[2 * KSH][1] = r2[1];
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int s = 0; s < KSH; ++s)
+                        mma16816(acc[e], hf[2 * s + e][0], hf[2 * s + e][1], hf[2 * s + e + 1][0], hf[2 * s + e + 1][1], th[2 * s], th[2 * s + 1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                __half *d = HR + (pl * NP) * H_PLANE + (slot * M_RB + g) * M_HP + 8 * (2 * warp + e) + 2 * t;
+                if (SPLIT) {
+                    uint32_t hi, lo;
+                    split_h2(acc[e][0], acc[e][1], hi, lo);
+                    *reinterpret_cast<uint32_t *>(d) = hi; *reinterpret_cast<uint32_t *>(d + H_PLANE) = lo;
+                    split_h2(acc[e][2], acc[e][3], hi, lo);
+                    *reinterpret_cast<uint32_t *>(d + 8 * M_HP) = hi; *reinterpret_cast<uint32_t *>(d + 8 * M_HP + H_PLANE) = lo;
+                } else {
+                    *reinterpret_cast<uint32_t *>(d) = pack_h2(acc[e][0], acc[e][1]);
+                    *reinterpret_cast<uint32_t *>(d + 8 * M_HP) = pack_h2(acc[e][2], acc[e][3]);
+                }
+            }
+        }
+    };
+
+    // ---- V pass of output block ob (window = ring blocks ob .. ob + D), expand the two planes, encode, stage
+    auto vencode = [&](int ob) {
+        float out[2][2][4];                        // [plane][column tile][fragment]
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[pl][e][c] = 0.f;
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+#pragma unroll
+                for (int s = 0; s < KSV; ++s) {
+                    const int slot = (ob + s) % KSV;
+                    uint32_t b4[4];
+                    ldsm_x4_trans(b4, HR_sh + 2u * (uint32_t)((pl * NP + part) * H_PLANE + (slot * M_RB + l_row) * M_HP + 8 * (2 * warp + l_hi)));
+                    const uint32_t a1 = s > 0 ? tv[2 * s - 1] : 0u;
+                    mma16816(out[pl][0], tv[2 * s], a1, tv[2 * s + 1], tv[2 * s], b4[0], b4[1]);
+                    mma16816(out[pl][1], tv[2 * s], a1, tv[2 * s + 1], tv[2 * s], b4[2], b4[3]);
+                }
+            }
+        }
+        // fragment: (row g / g+8, columns 2t, 2t+1) of column tiles 2 warp, 2 warp + 1
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t by[6];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float av = out[0][e][2 * hh + j], bv = out[1][e][2 * hh + j];
+                    by[3 * j] = encode_u8(enc, fmaf(p.P[1], bv, p.P[0] * av));
+                    by[3 * j + 1] = encode_u8(enc, fmaf(p.P[3], bv, p.P[2] * av));
+                    by[3 * j + 2] = encode_u8(enc, fmaf(p.P[5], bv, p.P[4] * av));
+                }
+                uint16_t *o = reinterpret_cast<uint16_t *>(stage + (g + 8 * hh) * M_STAGE_PITCH + 3 * (8 * (2 * warp + e) + 2 * t));
+                o[0] = (uint16_t)(by[0] | (by[1] << 8));
+                o[1] = (uint16_t)(by[2] | (by[3] << 8));
+                o[2] = (uint16_t)(by[4] | (by[5] << 8));
+            }
+    };
+
+    // ---- staged rows of output block ob -> global
+    auto copy_out = [&](int ob) {
+        const int oy0 = y_start + ob * M_RB;
+        if (vec_ok) {
+            constexpr int CH = 3 * G_TW / 16;          // 24 chunks of 16 B per row
+            for (int idx = tid; idx < M_RB * CH; idx += M_THREADS) {
+                const int r = idx / CH, c = idx - r * CH;
+                if (oy0 + r < y_end)
+                    *reinterpret_cast<uint4 *>(dst_frame + (int64_t)(oy0 + r) * p.io.out_rs + (int64_t)x0 * 3 + 16 * c) =
+                        *reinterpret_cast<const uint4 *>(stage + r * M_STAGE_PITCH + 16 * c);
+            }
+        } else {
+            const int nbytes = 3 * min(G_TW, W - x0);
+            for (int idx = tid; idx < M_RB * 3 * G_TW; idx += M_THREADS) {
+                const int r = idx / (3 * G_TW), b = idx - r * (3 * G_TW);
+                if (oy0 + r < y_end && b < nbytes) dst_frame[(int64_t)(oy0 + r) * p.io.out_rs + (int64_t)x0 * 3 + b] = stage[r * M_STAGE_PITCH + b];
+            }
+        }
+    };
+
+    // Two barriers per 16-row block, each interval mixing two kinds of work:
+    //   B(ib): H pass of block ib (tensor + LDSM)      + copy-out of output block ib-1-D (LDS.128 / STG.128)
+    //   A(ib): produce block ib+1 (LDS, LUT, FMA, F2FP) + V pass / encode of output block ib-D (tensor, ALU)
+    // S is written in A and read in B; ring slot ib % KSV is written in B(ib) and last read in A(ib+D); the byte
+    // stage is written in A and read in the following B.
+    produce(0);
+    __syncthreads();
+    for (int ib = 0; ib < n_blocks; ++ib) {
+        hpass(ib);
+        if (ib - 1 - D >= 0) copy_out(ib - 1 - D);
+        __syncthreads();
+        if (ib + 1 < n_blocks) produce(ib + 1);
+        if (ib >= D) vencode(ib - D);
+        __syncthreads();
+    }
+    copy_out(n_blocks - 1 - D);
+
+    if (p.flags != nullptr && !p.fixup) {
+        if (__any_sync(0xffffffffu, (seen & 0xfefefefeu) != 0) && lane == 0) p.flags[frame] = 1u;
+    }
+}
+
 template <int R, class Prod, int NCH>
 static int launch_gauss(const GaussCommon &gc, const typename Prod::Params &pp, cudaStream_t st) {
     using C = GaussCfg<R>;
@@ -672,6 +1034,101 @@ static bool rank2_factor(const float *T, float *Q /*6*/, float *P /*6*/) {
     return resid <= 4e-7 * scale;       // a few float32 ulps of the largest entry: T itself was rounded to float32
 }
 
+// ---- tensor-core variant: host side
+// Taps -> f16 with the rounding error diffused: every tap is rounded to f16, then symmetric pairs are nudged by whole
+// f16 steps, largest step first, until the taps sum to 1 within the finest step.  A flat region then blurs to
+// itself exactly (f32 accumulation), as it does in the reference.
+static double f16_step(double v) {
+    v = std::fabs(v);
+    if (v < 6.103515625e-05) return 5.960464477539063e-08;          // subnormal spacing 2^-24
+    int e;
+    std::frexp(v, &e);                                               // v = m 2^e, m in [0.5, 1)
+    return std::ldexp(1.0, e - 11);
+}
+static void quantize_taps_f16(float *taps, int ksize) {
+    const int c = ksize / 2;
+    double q[G_MAX_TAPS];
+    for (int i = 0; i < ksize; ++i) q[i] = (double)__half2float(__float2half_rn(taps[i]));
+    double sum = 0.0;
+    for (int i = 0; i < ksize; ++i) sum += q[i];
+    for (int k = 0; k <= c; ++k) {                                   // centre (largest step) outwards
+        const double step = f16_step(q[c + k]) * (k ? 2.0 : 1.0);
+        const double m = std::nearbyint((1.0 - sum) / step);
+        if (m == 0.0) continue;
+        const double d = m * f16_step(q[c + k]);
+        q[c + k] += d;
+        if (k) q[c - k] += d;
+        sum += m * step;
+    }
+    for (int i = 0; i < ksize; ++i) taps[i] = (float)q[i];
+}
+
+// AVB_GAUSS_MMA: 0 = CUDA-core kernel (gauss_stream_kernel) always, 1 = tensor-core kernel with hi+lo f16 operands from
+// G_MMA_MIN_RADIUS up (default), 2 = same with single f16 operands (faster, ~0.05 LSB of systematic rounding: flat
+// regions may flip by 1 LSB as a whole), 3 / 4 = modes 1 / 2 at every radius.  Read once per process.
+constexpr int G_MMA_MIN_RADIUS = 8;
+static int gauss_mma_mode() {
+    static const int mode = [] {
+        const char *e = std::getenv("AVB_GAUSS_MMA");
+        return e ? std::atoi(e) : 1;
+    }();
+    return mode;
+}
+
+static int pick_seg_h_mma(int n, int H, int W, int d_blocks, int ctas_per_sm) {
+    const long strips = (long)((W + G_TW - 1) / G_TW) * n;
+    const long slots = (long)sm_count() * ctas_per_sm;
+    const int max_segs = std::max(1, H / (8 * M_RB * d_blocks));      // re-produced rows per segment <= ~12 %
+    int best = 1;
+    double best_score = -1.0;
+    for (int segs = 1; segs <= max_segs && segs <= 64; ++segs) {
+        int seg_h = (H + segs - 1) / segs;
+        seg_h = (seg_h + M_RB - 1) / M_RB * M_RB;
+        const long real_segs = (H + seg_h - 1) / seg_h;
+        const long ctas = strips * real_segs;
+        const long waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);
+        const double useful = (double)seg_h / (double)(seg_h + M_RB * d_blocks);
+        const double score = fill * useful * (waves >= 2 ? 1.0 : 0.85);
+        if (score > best_score + 1e-9) { best_score = score; best = segs; }
+    }
+    int seg_h = (H + best - 1) / best;
+    return (seg_h + M_RB - 1) / M_RB * M_RB;
+}
+
+template <int KSH, int D, bool SPLIT>
+static int launch_gauss_mma(const GaussCommon &gc, const DogProducer::Params &pp, const MmaGeom &geo, cudaStream_t st) {
+    constexpr int NP = SPLIT ? 2 : 1;
+    const size_t smem = (size_t)2 * NP * M_RB * MmaCfg<KSH>::SP * 2 + (size_t)2 * NP * (D + 1) * M_RB * M_HP * 2 +
+                        (size_t)M_RB * M_STAGE_PITCH + (size_t)(256 * M_LUT_COPIES + G_ENC_SMEM) * 4 + 2 * (size_t)M_RB * M_RAW_PITCH;
+    auto kern = gauss_mma_kernel<KSH, D, SPLIT>;
+    AVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((gc.io.W + G_TW - 1) / G_TW, (gc.io.H + gc.seg_h - 1) / gc.seg_h, gc.io.n);
+    AVB_TIMED(gc.fixup ? DogProducer::fixup_name() : DogProducer::name(), st);
+    kern<<<grid, M_THREADS, smem, st>>>(gc, pp, geo);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+template <bool SPLIT>
+static int dispatch_gauss_mma(int radius, GaussCommon gc, const DogProducer::Params &q, cudaStream_t st) {
+    const int d = radius <= 8 ? 1 : 2;
+    MmaGeom geo{};
+    geo.radius = radius;
+    geo.r4 = (radius + 3) & ~3;
+    geo.groups = (G_TW + geo.r4 + radius + 3) / 4;
+    geo.div_groups = (65536u + geo.groups - 1) / geo.groups;
+    for (int idx = 0; idx < M_RB * geo.groups; ++idx)                        // the multiply-shift division is exact on its range
+        if ((int)(((uint32_t)idx * geo.div_groups) >> 16) != idx / geo.groups) { set_error("internal: group divider"); return AVB_E_UNSUPPORTED; }
+    gc.radius = radius;
+    gc.seg_h = pick_seg_h_mma(gc.io.n, gc.io.H, gc.io.W, d, 2);
+    quantize_taps_f16(gc.taps, 2 * radius + 1);
+    if (radius <= 4) return launch_gauss_mma<1, 1, SPLIT>(gc, q, geo, st);
+    if (radius <= 8) return launch_gauss_mma<2, 1, SPLIT>(gc, q, geo, st);
+    if (radius <= 12) return launch_gauss_mma<2, 2, SPLIT>(gc, q, geo, st);
+    return launch_gauss_mma<3, 2, SPLIT>(gc, q, geo, st);
+}
+
 template <class Prod>
 static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp, cudaStream_t st) {
     gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius, radius <= G_MINB3_R ? 3 : G_MINB);
@@ -682,6 +1139,14 @@ static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp
     if (two) {
         for (int i = 0; i < 6; ++i) q.M.m[i] = Q[i];
         q.M.m[6] = q.M.m[7] = q.M.m[8] = 0.f;
+    }
+    if constexpr (std::is_same<Prod, DogProducer>::value) {
+        // measured (20 4K frames, ms, CUDA cores -> tensor cores hi+lo): 29 taps 1.45 -> 1.14, 17 taps 1.09 -> 1.00,
+        // 15 taps 1.04 -> 1.01, 7 taps 0.83 -> 0.97: below ~17 taps the FMAs saved do not pay for the f16 splitting
+        const int min_radius = gauss_mma_mode() >= 3 ? 1 : G_MMA_MIN_RADIUS;      // modes 3 / 4: tensor path at every radius (tests)
+        if (two && radius >= min_radius && radius <= 16 && gauss_mma_mode() != 0)
+            return (gauss_mma_mode() == 2 || gauss_mma_mode() == 4) ? dispatch_gauss_mma<false>(radius, gc, q, st)
+                                                                    : dispatch_gauss_mma<true>(radius, gc, q, st);
     }
     switch (radius) {
 #define AVB_CASE(RR) case RR: return two ? launch_gauss<RR, Prod, 2>(gc, q, st) : launch_gauss<RR, Prod, 3>(gc, q, st);

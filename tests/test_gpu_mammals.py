@@ -21,7 +21,8 @@ def _cmp(got, ref, what, max_frac=0.02):
     assert got.shape == ref.shape and got.dtype == ref.dtype == np.uint8, what
     d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
     assert d.max() <= 1, f"{what}: max diff {d.max()} LSB"
-    assert (d > 0).mean() <= max_frac, f"{what}: {(d > 0).mean():.4f} of bytes differ by 1 LSB"
+    # (frames of a few bytes: a single 1-LSB byte is already several per cent)
+    assert (d > 0).sum() <= max(max_frac * d.size, 2), f"{what}: {(d > 0).mean():.4f} of bytes differ by 1 LSB"
 
 
 @pytest.mark.parametrize("name", GAUSS + ["rat"] + STREAK)

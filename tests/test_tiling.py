@@ -73,7 +73,10 @@ def test_band_rows_and_radius():
 @pytest.mark.parametrize("name", ["Dog", "Bear", "Squirrel"])
 def test_band_plus_halo_equals_whole_frame(name):
     """What visualize_band computes on each rank, emulated in one process: attach the neighbour rows,
-    run the kernel, keep the band.  Must equal the whole-frame output exactly."""
+    run the kernel, keep the band.  Equals the whole-frame output exactly on the CUDA-core kernel (fixed tap
+    order per output); on the tensor-core kernel (radius >= 8: Dog) the f32 accumulation order inside an MMA
+    depends on the row's position in its 16-row block, so a band may differ from the whole frame in the last
+    bit of the accumulator: <= 1 LSB on a handful of bytes."""
     import animal_vision_b200.animals as A
     from animal_vision_b200 import tables
     from animal_vision_b200._abi import AVB_NORM_DIV255
@@ -91,6 +94,11 @@ def test_band_plus_halo_equals_whole_frame(name):
         ext = frame[:, lo:hi].contiguous()
         out = torch.empty_like(ext)
         eng.dichromat_blur(ext, out, sp._matrix(), taps, norm=AVB_NORM_DIV255)
-        assert torch.equal(out[:, y0 - lo:y0 - lo + (y1 - y0)], whole[:, y0:y1]), (name, rank)
+        got, ref = out[:, y0 - lo:y0 - lo + (y1 - y0)], whole[:, y0:y1]
+        if radius >= 8:
+            d = (got.to(torch.int16) - ref.to(torch.int16)).abs()
+            assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 2e-3, (name, rank, int(d.max()), float((d > 0).float().mean()))
+        else:
+            assert torch.equal(got, ref), (name, rank)
     # world == 1 goes through the public entry point
     assert torch.equal(tiling.visualize_band(sp, frame, H, 0, 1), whole)
