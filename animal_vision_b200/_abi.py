@@ -59,6 +59,8 @@ SIGNATURES = {
     "avb_uv_catches_f32": (_i, [_p, _p, _i64, _p, _p, _i, _f, _p]),
     "avb_uv_map_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _i64, _i64, _p, _i, _p, _f, _p, _p]),
     "avb_uv_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "avb_vm_run": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "avb_img_remap": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "avb_uv_map_u8": (_i, [_p, _p, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i, _f, _i, _p, _i, _i, _p, _f, _p, _p, _p]),
 }
 

@@ -146,20 +146,28 @@ struct StatsAcc {                    // scratch per (frame, channel)
     uint32_t mn, mx;
     double sum;
 };
+constexpr int STATS_MAX_C = 16;       // mantis_shrimp.py:167-171: ten band maps normalised at once
 __global__ void __launch_bounds__(256) stats_kernel(const float *__restrict__ in, long long npx, int C, StatsAcc *acc) {
     const int frame = blockIdx.y;
     const float *f = in + (long long)frame * npx * C;
-    uint32_t mn[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[4] = {0u, 0u, 0u, 0u};
-    double sm[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t mn[STATS_MAX_C], mx[STATS_MAX_C];
+    double sm[STATS_MAX_C];
+#pragma unroll
+    for (int c = 0; c < STATS_MAX_C; ++c) { mn[c] = 0xffffffffu; mx[c] = 0u; sm[c] = 0.0; }
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
-        for (int c = 0; c < C; ++c) {
-            const float v = f[i * C + c];
-            const uint32_t o = ord_bits(v);
-            mn[c] = min(mn[c], o); mx[c] = max(mx[c], o);
-            sm[c] += (double)v;
+#pragma unroll
+        for (int c = 0; c < STATS_MAX_C; ++c) {
+            if (c < C) {
+                const float v = f[i * C + c];
+                const uint32_t o = ord_bits(v);
+                mn[c] = min(mn[c], o); mx[c] = max(mx[c], o);
+                sm[c] += (double)v;
+            }
         }
     }
-    for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int c = 0; c < STATS_MAX_C; ++c) {
+        if (c >= C) break;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mn[c] = min(mn[c], __shfl_xor_sync(FULL, mn[c], o));
@@ -384,7 +392,7 @@ extern "C" int avb_img_blur(const float *in_dev, float *out_dev, float *tmp_dev,
 
 extern "C" int avb_img_stats(const float *in_dev, int n, int64_t npx, int C, float *out_dev, void *scratch_dev, avb_stream_t stream) {
     AVB_REQUIRE(in_dev && out_dev && scratch_dev, "null pointer");
-    AVB_REQUIRE(n > 0 && n <= 65535 && npx > 0 && C >= 1 && C <= 4, "bad geometry");
+    AVB_REQUIRE(n > 0 && n <= 65535 && npx > 0 && C >= 1 && C <= STATS_MAX_C, "bad geometry");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     StatsAcc *acc = static_cast<StatsAcc *>(scratch_dev);
     const int count = n * C;

@@ -1,0 +1,184 @@
+// K7: fused per-pixel programs for the UV species + cv2.remap on float32 frames.
+//
+// The fifteen UV species and MantisShrimp (animals/reindeer.py, goldfish.py, ... mantis_shrimp.py) are chains of
+// 100-200 NumPy element-wise operations between a handful of spatial operators (resize, blur, Sobel, remap) and
+// global reductions (min / max / percentile).  The reference materialises a full-frame float32 temporary per
+// operation; here every maximal run of element-wise operations is ONE launch: the host (animal_vision_b200/lazy.py)
+// records the species' arithmetic as an expression DAG, linearises it into a register program and this kernel
+// executes the program per pixel -- operands come straight from the source planes / per-row and per-column tables /
+// per-frame device scalars (reduction results never visit the host), results go straight to the output planes
+// (float32, or the final uint8 frame).  Every instruction is one IEEE float32 operation in the reference's order
+// (no contraction, no re-association), so the result equals NumPy's up to the library transcendental functions.
+//
+// The register file lives in shared memory ([reg][thread], conflict free), instructions are fetched with uniform
+// loads; a program is a few hundred bytes and is cached on the device by content.
+#include <algorithm>
+
+#include "avb_common.cuh"
+
+namespace avb {
+
+constexpr int VM_THREADS = 256;
+
+struct VmParams {
+    const avb_vm_ins *prog;
+    int n_ins, n_regs;
+    int n, H, W;
+    avb_vm_src src[AVB_VM_MAX_SRC];
+    avb_vm_dst dst[AVB_VM_MAX_DST];
+};
+
+__device__ __forceinline__ float vm_srgb_dec(float s) {      // uv_helpers.py:33-37 / classic_rgb_to_hsi.py:16-22
+    return s <= 0.04045f ? __fdiv_rn(s, 12.92f) : powf(__fdiv_rn(__fadd_rn(s, 0.055f), 1.055f), 2.4f);
+}
+__device__ __forceinline__ float vm_srgb_enc(float l) {      // uv_helpers.py:40-44 (1/2.4 acts as a float32 scalar)
+    return l <= 0.0031308f ? __fmul_rn(l, 12.92f) : __fsub_rn(__fmul_rn(1.055f, powf(fmaxf(l, 0.f), 0.41666666f)), 0.055f);
+}
+
+__global__ void __launch_bounds__(VM_THREADS) vm_kernel(const __grid_constant__ VmParams p) {
+    extern __shared__ float regs[];                         // [n_regs][VM_THREADS]
+    float *r = regs + threadIdx.x;
+    const long long npx = (long long)p.H * p.W, total = npx * p.n;
+    for (long long gi = (long long)blockIdx.x * VM_THREADS + threadIdx.x; gi < total; gi += (long long)gridDim.x * VM_THREADS) {
+        const int frame = (int)(gi / npx);
+        const long long pix = gi - (long long)frame * npx;
+        const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
+        for (int pc = 0; pc < p.n_ins; ++pc) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p.prog) + pc);
+            avb_vm_ins in;
+            in.op = raw.x & 0xffu; in.dst = (raw.x >> 8) & 0xffu; in.a = (raw.x >> 16) & 0xffu; in.b = raw.x >> 24; in.imm = raw.y;
+#define RA (r[in.a * VM_THREADS])
+#define RB (r[in.b * VM_THREADS])
+            float v;
+            switch (in.op) {
+                case AVB_VM_LOAD: {
+                    const avb_vm_src &s = p.src[in.a];
+                    long long idx;
+                    switch (s.kind) {
+                        case AVB_VM_SRC_PLANE: idx = (long long)frame * s.frame_stride + pix * s.pix_stride + in.b; break;
+                        case AVB_VM_SRC_ROW: idx = (long long)y * s.pix_stride + in.b; break;
+                        case AVB_VM_SRC_COL: idx = (long long)x * s.pix_stride + in.b; break;
+                        default: idx = (long long)frame * s.frame_stride + in.b; break;      // per-frame scalars
+                    }
+                    v = __ldg(static_cast<const float *>(s.ptr) + idx);
+                    break;
+                }
+                case AVB_VM_CONST: v = __uint_as_float(in.imm); break;
+                case AVB_VM_MOV: v = RA; break;
+                case AVB_VM_ADD: v = __fadd_rn(RA, RB); break;
+                case AVB_VM_SUB: v = __fsub_rn(RA, RB); break;
+                case AVB_VM_MUL: v = __fmul_rn(RA, RB); break;
+                case AVB_VM_DIV: v = __fdiv_rn(RA, RB); break;
+                case AVB_VM_MIN: v = fminf(RA, RB); break;
+                case AVB_VM_MAX: v = fmaxf(RA, RB); break;
+                case AVB_VM_POW: v = powf(RA, RB); break;
+                case AVB_VM_ATAN2: v = atan2f(RA, RB); break;
+                case AVB_VM_GT: v = RA > RB ? 1.f : 0.f; break;
+                case AVB_VM_GE: v = RA >= RB ? 1.f : 0.f; break;
+                case AVB_VM_LT: v = RA < RB ? 1.f : 0.f; break;
+                case AVB_VM_LE: v = RA <= RB ? 1.f : 0.f; break;
+                case AVB_VM_NEG: v = -RA; break;
+                case AVB_VM_ABS: v = fabsf(RA); break;
+                case AVB_VM_SQRT: v = __fsqrt_rn(RA); break;
+                case AVB_VM_EXP: v = expf(RA); break;
+                case AVB_VM_SIN: v = sinf(RA); break;
+                case AVB_VM_COS: v = cosf(RA); break;
+                case AVB_VM_FLOOR: v = floorf(RA); break;
+                case AVB_VM_SRGB_DEC: v = vm_srgb_dec(RA); break;
+                case AVB_VM_SRGB_ENC: v = vm_srgb_enc(RA); break;
+                case AVB_VM_QUANT: v = truncf(fminf(fmaxf(__fadd_rn(__fmul_rn(RA, 255.0f), 0.5f), 0.f), 255.f)); break;   // uv_helpers.py:26-30
+                case AVB_VM_SELECT: v = RA != 0.f ? RB : r[(in.imm & 0xffu) * VM_THREADS]; break;
+                case AVB_VM_STORE: {
+                    const avb_vm_dst &d = p.dst[in.b];
+                    const long long idx = (long long)frame * d.frame_stride + (long long)y * d.row_stride + (long long)x * d.pix_stride + in.imm;
+                    const float val = RA;
+                    if (d.kind == AVB_VM_DST_U8) static_cast<uint8_t *>(d.ptr)[idx] = (uint8_t)val;
+                    else static_cast<float *>(d.ptr)[idx] = val;
+                    continue;
+                }
+                default: continue;
+            }
+#undef RA
+#undef RB
+            r[in.dst * VM_THREADS] = v;
+        }
+    }
+}
+
+// ---- cv2.remap(INTER_LINEAR, BORDER_REFLECT_101) on float32 frames with float32 maps (animals/anableps.py:224-237).
+// OpenCV quantises the map to 1/32 px (INTER_BITS = 5): sx = rint(32 x), integer part sx >> 5, fraction (sx & 31) / 32,
+// the four taps weighted by the float products of the 1-D weights.
+struct RemapP {
+    const float *in;
+    float *out;
+    const float *mx, *my;
+    int n, H, W, C;
+};
+__global__ void __launch_bounds__(256) remap_kernel(const __grid_constant__ RemapP p) {
+    const long long npx = (long long)p.H * p.W, total = npx * p.n;
+    for (long long gi = (long long)blockIdx.x * 256 + threadIdx.x; gi < total; gi += (long long)gridDim.x * 256) {
+        const int frame = (int)(gi / npx);
+        const long long pix = gi - (long long)frame * npx;
+        const int sx = __float2int_rn(__ldg(p.mx + pix) * 32.0f), sy = __float2int_rn(__ldg(p.my + pix) * 32.0f);
+        const int ix = sx >> 5, iy = sy >> 5;
+        const float fx = (float)(sx & 31) * (1.0f / 32.0f), fy = (float)(sy & 31) * (1.0f / 32.0f);
+        const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx), w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+        const int x0 = reflect101(ix, p.W), x1 = reflect101(ix + 1, p.W), y0 = reflect101(iy, p.H), y1 = reflect101(iy + 1, p.H);
+        const float *f = p.in + (long long)frame * npx * p.C;
+        float *o = p.out + gi * p.C;
+        for (int c = 0; c < p.C; ++c) {
+            const float a = f[((long long)y0 * p.W + x0) * p.C + c], b = f[((long long)y0 * p.W + x1) * p.C + c];
+            const float d = f[((long long)y1 * p.W + x0) * p.C + c], e = f[((long long)y1 * p.W + x1) * p.C + c];
+            o[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, w00), __fmul_rn(b, w01)), __fmul_rn(d, w10)), __fmul_rn(e, w11));
+        }
+    }
+}
+
+}  // namespace avb
+
+using namespace avb;
+
+extern "C" int avb_vm_run(const avb_vm_ins *prog_dev, int n_ins, int n_regs, int n, int H, int W,
+                          const avb_vm_src *src_host, int n_src, const avb_vm_dst *dst_host, int n_dst, avb_stream_t stream) {
+    AVB_REQUIRE(prog_dev && n_ins > 0 && n_ins <= AVB_VM_MAX_INS, "bad program");
+    AVB_REQUIRE(n_regs > 0 && n_regs <= AVB_VM_MAX_REGS, "bad register count");
+    AVB_REQUIRE(n > 0 && H > 0 && W > 0, "bad frame geometry");
+    AVB_REQUIRE(n_src >= 0 && n_src <= AVB_VM_MAX_SRC && n_dst > 0 && n_dst <= AVB_VM_MAX_DST, "too many sources / destinations");
+    AVB_REQUIRE((n_src == 0 || src_host) && dst_host, "null descriptor table");
+    VmParams p{};
+    p.prog = prog_dev; p.n_ins = n_ins; p.n_regs = n_regs; p.n = n; p.H = H; p.W = W;
+    for (int i = 0; i < n_src; ++i) {
+        AVB_REQUIRE(src_host[i].ptr && src_host[i].kind >= AVB_VM_SRC_PLANE && src_host[i].kind <= AVB_VM_SRC_FRAME, "bad source descriptor");
+        p.src[i] = src_host[i];
+    }
+    for (int i = 0; i < n_dst; ++i) {
+        AVB_REQUIRE(dst_host[i].ptr && (dst_host[i].kind == AVB_VM_DST_F32 || dst_host[i].kind == AVB_VM_DST_U8), "bad destination descriptor");
+        p.dst[i] = dst_host[i];
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)n_regs * VM_THREADS * sizeof(float);
+    static SmemOptIn optin;
+    if (smem > 48 * 1024) AVB_CUDA_OK(optin.ensure(vm_kernel, AVB_VM_MAX_REGS * VM_THREADS * (int)sizeof(float)));
+    const long long total = (long long)n * H * W;
+    const int per_sm = std::max(1, std::min(8, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + VM_THREADS - 1) / VM_THREADS, (long long)sm_count() * per_sm));
+    AVB_TIMED("k7_vm", st);
+    vm_kernel<<<grid, VM_THREADS, smem, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}
+
+extern "C" int avb_img_remap(const float *in_dev, float *out_dev, int n, int H, int W, int C, const float *mapx_dev,
+                             const float *mapy_dev, avb_stream_t stream) {
+    AVB_REQUIRE(in_dev && out_dev && mapx_dev && mapy_dev, "null pointer");
+    AVB_REQUIRE(in_dev != out_dev, "remap cannot run in place");
+    AVB_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && C <= 16, "bad geometry");
+    RemapP p{in_dev, out_dev, mapx_dev, mapy_dev, n, H, W, C};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = (long long)n * H * W;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm_count() * 16));
+    AVB_TIMED("k7_remap", st);
+    remap_kernel<<<grid, 256, 0, st>>>(p);
+    AVB_CUDA_OK(cudaGetLastError());
+    return AVB_OK;
+}

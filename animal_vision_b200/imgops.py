@@ -85,6 +85,59 @@ class ImgOps:
             y = self._resample_axis(y, Ho, 1, interp, ch, y0)
         return y
 
+    def panorama(self, x, scale_x: float):
+        """uv_helpers.py:84-99 panorama_warp: cv2.resize(INTER_CUBIC) to round(W*scale_x) columns, centre crop back to W.
+        Only the W surviving columns are computed (the tap tables are sliced, not the image)."""
+        n, H, W, Cn = self._check(x)
+        geo = tables.panorama_geometry(W, float(scale_x))
+        if geo is None:
+            return x
+        newW, start = geo
+
+        def build():
+            idx, w = tables.resize_taps(W, newW, "cubic")
+            return np.ascontiguousarray(idx[start:start + W]), np.ascontiguousarray(w[start:start + W])
+        idx, w = self._taps_dev(("panorama", W, newW, start), build)
+        out = self.t.empty_like(x)
+        with self.t.cuda.device(self.eng.device):
+            rc = self.lib.avb_img_resample(x.data_ptr(), out.data_ptr(), n, H, W, Cn, 0, H * W * Cn, W * Cn,
+                                           idx.data_ptr(), w.data_ptr(), int(idx.shape[1]), self.eng.stream_ptr())
+        check(rc, "avb_img_resample")
+        self.eng.launches += 1
+        return out
+
+    def sobel(self, x):
+        """cv2.Sobel(x, CV_32F, 1, 0, ksize=3) and (0, 1) with BORDER_REFLECT_101 (mantis_shrimp.py:124-125 and siblings):
+        the separable pairs ([-1,0,1] along x, [1,2,1] along y) and ([1,2,1], [-1,0,1])."""
+        d = np.array([-1.0, 0.0, 1.0], np.float32)
+        sm = np.array([1.0, 2.0, 1.0], np.float32)
+        return self.blur_taps(x, d, sm), self.blur_taps(x, sm, d)
+
+    def remap(self, x, map_x: np.ndarray, map_y: np.ndarray):
+        """cv2.remap(x, map_x, map_y, INTER_LINEAR, BORDER_REFLECT101) with host-built float32 maps (anableps.py:224-237)."""
+        n, H, W, Cn = self._check(x)
+        mx = np.ascontiguousarray(map_x, np.float32)
+        my = np.ascontiguousarray(map_y, np.float32)
+        assert mx.shape == (H, W) and my.shape == (H, W)
+        import hashlib
+        dx = self.eng.cached(("remap", hashlib.sha1(mx.tobytes()).hexdigest()), lambda: self.eng._dev(mx))
+        dy = self.eng.cached(("remap", hashlib.sha1(my.tobytes()).hexdigest()), lambda: self.eng._dev(my))
+        out = self.t.empty_like(x)
+        with self.t.cuda.device(self.eng.device):
+            rc = self.lib.avb_img_remap(x.data_ptr(), out.data_ptr(), n, H, W, Cn, dx.data_ptr(), dy.data_ptr(), self.eng.stream_ptr())
+        check(rc, "avb_img_remap")
+        self.eng.launches += 1
+        return out
+
+    def percentile_frames(self, x, channel: int, q: float, joint: bool = False):
+        """numpy.percentile(plane, q) of one channel of every frame -> float32 tensor [n, 1] on the device.
+        joint = True: the percentile over ALL channels of a frame together (np.percentile of an (H,W,N) stack)."""
+        n, H, W, Cn = self._check(x)
+        if joint:
+            flat = x.view(n, 1, H * W * Cn, 1)
+            return self.percentile(flat, [(f, 0, q) for f in range(n)]).view(n, 1)
+        return self.percentile(x, [(f, channel, q) for f in range(n)]).view(n, 1)
+
     def blur_taps(self, x, taps_x: np.ndarray, taps_y: np.ndarray = None):
         """Separable correlation, BORDER_REFLECT_101, rows first (cv2.GaussianBlur / sepFilter2D)."""
         t = self.t

@@ -381,7 +381,7 @@ def bandpass_weights(lam: np.ndarray, lo: float, hi: float) -> np.ndarray:
 
 
 MANTIS_BANDS = ((320, 360), (360, 400), (400, 430), (430, 460), (460, 490),
-                (490, 520), (520, 550), (550, 600), (600, 650), (650, 700))   # mantis_shrimp.py:49-60
+                (490, 520), (520, 550), (550, 580), (580, 610), (610, 680))   # mantis_shrimp.py:49-60
 
 
 def mantis_band_matrix(lam: np.ndarray) -> np.ndarray:

@@ -296,6 +296,45 @@ AVB_API int avb_uv_map_f32(const float *ubg_dev, void *out, int out_is_f32, int 
                            int map_mode, const float *map_params_host, float mix_alpha,
                            void *workspace_dev, avb_stream_t stream);
 
+/* ---- K7: fused per-pixel programs + cv2.remap (csrc/k7_pointwise.cu) --------------------------------
+ * The element-wise arithmetic of the UV species (animals/reindeer.py:70-135, goldfish.py, damselfish.py,
+ * rat_uv.py:131-214, anableps.py:124-255, anchovy.py:130-253, guppy.py:132-235, morpho.py, heliconius.py,
+ * pieris.py, kestrel.py:113-234, jumping_spider.py:135-236, dragonfly.py:146-251, hummingbird.py:128-227,
+ * mantis_shrimp.py:143-279) runs as register programs: one launch per maximal run of NumPy element-wise steps.
+ * Every instruction is one IEEE float32 operation (r = register file, 'a' / 'b' register numbers):
+ *   LOAD   r[dst] = src[a] channel b       CONST r[dst] = imm (float bits)     STORE  dst[b] channel imm = r[a]
+ *   SELECT r[dst] = r[a] != 0 ? r[b] : r[imm & 255]
+ *   QUANT  trunc(clip(x*255 + 0.5, 0, 255))          (uv_helpers.py:26-30 from_float01, integer dtypes)
+ *   SRGB_DEC / SRGB_ENC                              (uv_helpers.py:33-44)
+ * Sources: float32 planes [n][H*W][pix_stride] (frame_stride = 0 broadcasts one frame), per-row tables
+ * [H][pix_stride], per-column tables [W][pix_stride], per-frame scalars [n][frame_stride] (reduction results stay on
+ * the device).  Destinations: float32 or uint8, element index frame*frame_stride + y*row_stride + x*pix_stride + ch. */
+enum {
+    AVB_VM_NOP = 0, AVB_VM_LOAD, AVB_VM_CONST, AVB_VM_MOV, AVB_VM_ADD, AVB_VM_SUB, AVB_VM_MUL, AVB_VM_DIV, AVB_VM_MIN,
+    AVB_VM_MAX, AVB_VM_POW, AVB_VM_ATAN2, AVB_VM_GT, AVB_VM_GE, AVB_VM_LT, AVB_VM_LE, AVB_VM_NEG, AVB_VM_ABS,
+    AVB_VM_SQRT, AVB_VM_EXP, AVB_VM_SIN, AVB_VM_COS, AVB_VM_FLOOR, AVB_VM_SRGB_DEC, AVB_VM_SRGB_ENC, AVB_VM_QUANT,
+    AVB_VM_SELECT, AVB_VM_STORE, AVB_VM_N_OPS
+};
+#define AVB_VM_SRC_PLANE 0
+#define AVB_VM_SRC_ROW 1
+#define AVB_VM_SRC_COL 2
+#define AVB_VM_SRC_FRAME 3
+#define AVB_VM_DST_F32 0
+#define AVB_VM_DST_U8 1
+#define AVB_VM_MAX_SRC 24
+#define AVB_VM_MAX_DST 4
+#define AVB_VM_MAX_REGS 48
+#define AVB_VM_MAX_INS 2048
+typedef struct { uint8_t op, dst, a, b; uint32_t imm; } avb_vm_ins;
+typedef struct { const void *ptr; int64_t frame_stride; int32_t pix_stride; int32_t kind; } avb_vm_src;
+typedef struct { void *ptr; int64_t frame_stride; int64_t row_stride; int32_t pix_stride; int32_t kind; } avb_vm_dst;
+AVB_API int avb_vm_run(const avb_vm_ins *prog_dev, int n_ins, int n_regs, int n, int H, int W,
+                       const avb_vm_src *src_host, int n_src, const avb_vm_dst *dst_host, int n_dst, avb_stream_t stream);
+/* cv2.remap(src, map_x, map_y, INTER_LINEAR, BORDER_REFLECT_101) on float32 [n,H,W,C] with float32 maps [H,W]
+ * (animals/anableps.py:224-237): map coordinates quantised to 1/32 px exactly as OpenCV does. */
+AVB_API int avb_img_remap(const float *in_dev, float *out_dev, int n, int H, int W, int C, const float *mapx_dev,
+                          const float *mapy_dev, avb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,7 +136,7 @@ def safe_norm(x: np.ndarray) -> np.ndarray:
 
 # mantis_shrimp.py:49-60: the ten narrow bands (nm) of the "barcode"
 MANTIS_BANDS = ((320, 360), (360, 400), (400, 430), (430, 460), (460, 490),
-                (490, 520), (520, 550), (550, 600), (600, 650), (650, 700))
+                (490, 520), (520, 550), (550, 580), (580, 610), (610, 680))
 
 
 def mantis_band_matrix(lam: np.ndarray) -> np.ndarray:
