@@ -23,8 +23,8 @@ class Goldfish(UVAnimal):
         render = [r, g, b]
         if self.haze_strength > 0.0:                                                       # :141-143
             a = float(np.clip(self.haze_strength, 0.0, 1.0))
-            tint = np.array(self.haze_tint, np.float32)
-            render = [(1.0 - a) * c + a * float(tint[i]) for i, c in enumerate(render)]
+            veil = a * np.array(self.haze_tint, np.float32)
+            render = [(1.0 - a) * c + float(veil[i]) for i, c in enumerate(render)]
         if self.base_blur_sigma > 0.0:                                                     # :146-147
             render = st.lz.channels(st.blur(st.eval(render), self.base_blur_sigma))
         r, g, b = render

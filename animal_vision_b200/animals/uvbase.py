@@ -44,6 +44,24 @@ def radial_sigmoid(H: int, W: int, softness: float, radius: float) -> np.ndarray
     return (1.0 / (1.0 + np.exp(-softness * (r - radius)))).astype(np.float32)
 
 
+def scan_row_gain(H: int, freq: float, soften: float, gain: float) -> np.ndarray:
+    """Per-row gain 1 + gain * (rows - 0.5), rows = 0.5 + 0.5 sin(2 pi freq y) blurred with sigma `soften`
+    (jumping_spider.py:196-203, mantis_shrimp.py:254-261).  The reference blurs an (H,W) image that is constant along x:
+    its horizontal pass is the identity (taps sum to 1), the vertical pass a 1-D REFLECT_101 correlation -- done here."""
+    y = np.linspace(0.0, 1.0, H, dtype=np.float32)[:, None]
+    rows = (0.5 + 0.5 * np.sin(2.0 * np.pi * freq * y)).astype(np.float32)[:, 0]
+    if soften > 0.0:
+        taps = tables.uv_blur_taps(float(soften)).astype(np.float64)
+        r = taps.size // 2
+        idx = np.arange(-r, H + r)
+        period = max(1, 2 * H - 2)
+        idx = np.abs(((idx % period) + period) % period)
+        idx = np.where(idx >= H, period - idx, idx) if H > 1 else np.zeros_like(idx)
+        ext = rows.astype(np.float64)[idx]
+        rows = np.array([np.dot(taps, ext[i:i + taps.size]) for i in range(H)], np.float32)
+    return (1.0 + gain * (rows - 0.5)).astype(np.float32)
+
+
 class UVStage:
     """One visualize call: batch geometry, the K6 operators and the lazy-expression context."""
 
@@ -196,10 +214,15 @@ class UVAnimal(Animal):
         return st
 
     def visualize_batch(self, frames, out=None):
-        """frames: CUDA uint8 (or float32) [N,H,W,3] -> (baseline, view), same dtype and shape."""
+        """frames: CUDA uint8 (or float32) [N,H,W,3] -> (baseline, view), same dtype and shape.
+        out: None, the view tensor, or a (baseline, view) pair of caller-allocated tensors (HostBatchPipeline)."""
         eng = get_engine(frames.device)
         t = eng.torch
-        base = t.empty(tuple(frames.shape), dtype=frames.dtype, device=frames.device)
+        base = None
+        if isinstance(out, (tuple, list)):
+            base, out = out
+        if base is None:
+            base = t.empty(tuple(frames.shape), dtype=frames.dtype, device=frames.device)
         if out is None:
             out = t.empty(tuple(frames.shape), dtype=frames.dtype, device=frames.device)
         self._run(eng, frames, base, out, integer=frames.dtype == t.uint8)

@@ -428,6 +428,11 @@ def resize_taps(src: int, dst: int, interp: str, *, vertical: bool = False):
             idx = np.stack([s - 1, s, s + 1, s + 2], axis=1)
             w = _cubic_coeffs(f)
         return np.clip(idx, 0, src - 1).astype(np.int32), np.ascontiguousarray(w, np.float32)
+    if interp == "nearest":
+        # resizeNN: sx = min(floor(x * ifx), src - 1), ifx = 1 / (dst / src) in double (morpho.py:93 mosaic up-sampling)
+        ifx = 1.0 / (float(dst) / float(src))
+        s = np.minimum(np.floor(np.arange(dst, dtype=np.float64) * ifx).astype(np.int64), src - 1)
+        return s.astype(np.int32)[:, None], np.ones((dst, 1), np.float32)
     if interp != "area":
         raise ValueError(f"unknown interpolation {interp}")
     if dst > src:

@@ -7,7 +7,8 @@ def test_registry_matches_reference_shape():
     from animal_vision_b200 import registry
     from animal_vision_b200.animals import Animal
     ch = registry.animal_choices()
-    assert [c["name"] for c in ch][:3] == ["Cat", "Dog", "Sheep"] and len(ch) == 21
+    assert [c["name"] for c in ch][:3] == ["Cat", "Dog", "Sheep"] and len(ch) == 36          # utils.py:91-130
+    assert [c["name"] for c in ch][20:24] == ["HoneyBee", "ReinDeer", "RatUV", "GoldFish"] and ch[-1]["name"] == "HummingBird"
     assert all(set(c) == {"name", "value"} and isinstance(c["value"], Animal) for c in ch)
     assert all(callable(getattr(c["value"], "visualize")) and callable(getattr(c["value"], "visualize_batch")) for c in ch)
 
@@ -90,3 +91,25 @@ def test_species_batches_on_concurrent_streams_match_serial_results():
         assert torch.equal(out, serial[name][1]), name
         if name == "Cat":
             assert torch.equal(base, serial[name][0]), name
+
+
+def test_uv_species_constructor_contract():
+    """Keyword-only constructors with the reference's parameter names and defaults (reindeer.py:41-66 and siblings);
+    tools/make_golden_uv.py checks the defaults against the reference's signatures when the goldens are generated."""
+    import animal_vision_b200.animals as A
+    r = A.Reindeer()
+    assert r.hsi_scale == 0.25 and r.uv_band == (300.0, 410.0) and r.panorama_scale == 1.3 and r.N_OUTPUTS == 2
+    assert r.lambdas.dtype == np.float32 and r.lambdas.shape == (81,) and r.lambdas[0] == 300.0 and r.lambdas[-1] == 700.0
+    assert A.RatUV().lambdas.shape == (129,) and A.RatUV().lambdas[0] == 320.0                  # rat_uv.py:48
+    assert A.Goldfish(uv_boost=2.0).uv_boost == 2.0 and A.Goldfish().uv_boost == 3.0
+    assert len(A.MantisShrimp().bands) == 10 and A.MantisShrimp().bands[-1] == (610.0, 680.0)  # mantis_shrimp.py:49-60
+    assert A.Morpho(mosaic_downscale=0.01).mosaic_downscale == 0.15                             # morpho.py:59 clip
+    with pytest.raises(TypeError):
+        A.Kestrel(no_such_parameter=1)
+    with pytest.raises(TypeError):
+        A.Reindeer(0.5)                                                                         # keyword-only, as the reference
+    with pytest.raises(AssertionError):
+        A.Dragonfly(lambdas=np.arange(5))                                                       # dragonfly.py:100
+    for cls in (A.Reindeer, A.Anableps, A.Hummingbird):
+        with pytest.raises(AssertionError):
+            cls().visualize(np.zeros((4, 4), np.uint8))                                         # reindeer.py:82-83
