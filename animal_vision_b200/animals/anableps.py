@@ -38,8 +38,10 @@ class Anableps(UVAnimal):
         lz = st.lz
         bt = st.bands(self.lambdas, [self.uv_band, self.blue_band, self.green_band], self.hsi_scale)   # :158-164
         Un, Bv, Gv = st.normed_bands(bt)
-        air_np, maps = self._geometry(st.H, st.W)
-        air_w = lz.table(air_np)
+        gkey = ("anableps_geo", self.horizon_y, self.seam_softness_px, self.ripple_amp_px, self.ripple_waves, self.refract_push_px, st.H, st.W)
+        geo = st.eng.cached(gkey, lambda: self._geometry(st.H, st.W))                     # host tables built once per geometry
+        air_np, maps = geo
+        air_w = lz.keyed(gkey, lambda: air_np)
         warm = np.array(self.air_warmth, np.float32)
         air = [L.clip(c * float(warm[i]), 0.0, 1.0) for i, c in enumerate(st.baseline())]   # :190-191
         if self.air_unsharp_sigma > 0.0 and self.air_clarity_unsharp > 0.0:                 # :192, :116-122
@@ -61,7 +63,7 @@ class Anableps(UVAnimal):
         g = L.clip(g + 0.26 * Gv, 0.0, 1.0)
         water_t = st.eval([r, g, b])
         if maps is not None:                                                               # :218-237 refraction remap
-            water_t = st.ops.remap(water_t, maps[0], maps[1])
+            water_t = st.ops.remap(water_t, maps[0], maps[1], key=gkey)
         water_w = 1.0 - air_w
         render = [a_ * air_w + w_ * water_w for a_, w_ in zip(lz.channels(air_t), lz.channels(water_t))]   # :240
         if self.periph_blur_sigma > 0.0:                                                   # :243-252

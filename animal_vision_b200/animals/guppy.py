@@ -47,7 +47,7 @@ class Guppy(UVAnimal):
         sat = lz.plane(mc_t, 0) / (st.percentile(mc_t, 0, 95.0) + 1e-8)
         render = sat_apply(cur, 1.0 - self.background_desat * (1.0 - Un) * (1.0 - sat))    # :207-208
         if self.vignette_strength > 0.0:                                                   # :211-218
-            t = radial_sigmoid(st.H, st.W, self.vignette_softness, self.vignette_radius)
-            vign = lz.table(1.0 - self.vignette_strength * t)
+            vign = lz.keyed(("guppy_vign", self.vignette_softness, self.vignette_radius, self.vignette_strength),
+                            lambda: 1.0 - self.vignette_strength * radial_sigmoid(st.H, st.W, self.vignette_softness, self.vignette_radius))
             render = [L.clip(c * vign, 0.0, 1.0) for c in render]
         return render

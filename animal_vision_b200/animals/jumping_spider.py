@@ -51,20 +51,21 @@ class JumpingSpider(UVAnimal):
         if self.clarity_sigma > 0.0 and self.clarity_amount > 0.0:                         # :188-191
             render = unsharp(st, render, self.clarity_sigma, self.clarity_amount * self.uv_patch_gain * patch)
         if self.scan_row_gain != 0.0:                                                      # :194-203
-            rg = lz.row(scan_row_gain(st.H, self.scan_row_freq, self.scan_soften, self.scan_row_gain))
+            rg = lz.keyed(("scan_rows", self.scan_row_freq, self.scan_soften, self.scan_row_gain),
+                          lambda: scan_row_gain(st.H, self.scan_row_freq, self.scan_soften, self.scan_row_gain), "row")
             render = [L.clip(c * rg, 0.0, 1.0) for c in render]
         if self.spot_gain > 0.0:                                                           # :206-211
-            sm = lz.table(attention_spots(st.H, st.W, self.spots, self.spot_sigma))
+            sm = lz.keyed(("spots", self.spots, self.spot_sigma), lambda: attention_spots(st.H, st.W, self.spots, self.spot_sigma))
             lifted = st.eval([L.clip(c + self.spot_gain * sm, 0.0, 1.0) for c in render])
             sharp = unsharp(st, None, 0.8, 0.25, materialised=lifted)
             render = [L.clip((1.0 - 0.6 * sm) * c + (0.6 * sm) * s, 0.0, 1.0) for c, s in zip(lz.channels(lifted), sharp)]
         if self.periph_blur_sigma > 0.0 or self.periph_vignette_strength > 0.0:            # :214-226
-            edge_np = radial_sigmoid(st.H, st.W, self.fovea_softness, self.fovea_radius)
-            edge = lz.table(edge_np)
+            edge = st.periph_t(self.fovea_softness, self.fovea_radius)
             if self.periph_blur_sigma > 0.0:
                 t_img = st.eval(render)
                 render = [(1.0 - edge) * c + edge * q for c, q in zip(lz.channels(t_img), lz.channels(st.blur(t_img, self.periph_blur_sigma)))]
             if self.periph_vignette_strength > 0.0:
-                vign = lz.table(1.0 - self.periph_vignette_strength * edge_np)
+                vign = lz.keyed(("spider_vign", self.fovea_softness, self.fovea_radius, self.periph_vignette_strength),
+                                lambda: 1.0 - self.periph_vignette_strength * radial_sigmoid(st.H, st.W, self.fovea_softness, self.fovea_radius))
                 render = [L.clip(c * vign, 0.0, 1.0) for c in render]
         return render

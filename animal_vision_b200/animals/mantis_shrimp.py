@@ -102,7 +102,8 @@ class MantisShrimp(UVAnimal):
         op = self.barcode_opacity                                                          # :253
         render = [L.clip((1.0 - op) * c + op * lz.plane(bb_t, i), 0.0, 1.0) for i, c in enumerate(render)]
         if self.scan_row_gain != 0.0:                                                      # :256-263
-            rg = lz.row(scan_row_gain(st.H, self.scan_row_freq, self.scan_soften, self.scan_row_gain))
+            rg = lz.keyed(("scan_rows", self.scan_row_freq, self.scan_soften, self.scan_row_gain),
+                          lambda: scan_row_gain(st.H, self.scan_row_freq, self.scan_soften, self.scan_row_gain), "row")
             render = [L.clip(c * rg, 0.0, 1.0) for c in render]
         if self.periph_blur_sigma > 0.0:                                                   # :266-275
             render = periph_mix(st, render, self.periph_blur_sigma, self.periph_softness, self.periph_radius)

@@ -25,6 +25,6 @@ class Pieris(UVAnimal):
             t_img = st.eval(render)
             cur, blurred = lz.channels(t_img), lz.channels(st.blur(t_img, self.clarity_unsharp_sigma))
             render = [L.clip(c + self.clarity_amount * (c - q), 0.0, 1.0) for c, q in zip(cur, blurred)]
-        t = radial_sigmoid(st.H, st.W, self.bias_softness, self.bias_radius)              # :109-115
-        att = lz.table(1.0 + self.center_bias * (1.0 - t))
+        att = lz.keyed(("pieris_att", self.bias_softness, self.bias_radius, self.center_bias),                  # :109-115
+                       lambda: 1.0 + self.center_bias * (1.0 - radial_sigmoid(st.H, st.W, self.bias_softness, self.bias_radius)))
         return [L.clip(c * att, 0.0, 1.0) for c in render]

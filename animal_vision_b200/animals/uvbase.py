@@ -139,7 +139,7 @@ class UVStage:
         return self.ops.gaussian_blur(tensor, float(sigma))                                 # uv_helpers.py:67-73
 
     def periph_t(self, softness: float, radius: float) -> L.E:
-        return self.lz.table(radial_sigmoid(self.H, self.W, softness, radius))
+        return self.lz.keyed(("radial_t", float(softness), float(radius)), lambda: radial_sigmoid(self.H, self.W, softness, radius))
 
 
 def unsharp(st: UVStage, img: Sequence[L.E], sigma: float, amount, *, materialised=None) -> List[L.E]:

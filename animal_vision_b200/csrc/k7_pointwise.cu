@@ -35,72 +35,115 @@ __device__ __forceinline__ float vm_srgb_enc(float l) {      // uv_helpers.py:40
     return l <= 0.0031308f ? __fmul_rn(l, 12.92f) : __fsub_rn(__fmul_rn(1.055f, powf(fmaxf(l, 0.f), 0.41666666f)), 0.055f);
 }
 
+// Every thread runs the program on VM_PX pixels at once (pixel j of a thread is VM_THREADS apart from pixel j-1, so each
+// of the VM_PX loads / stores of an instruction is coalesced across the warp): fetch + decode + dispatch are paid once
+// per VM_PX results.  Register file r[reg][j][thread] and the program itself live in shared memory.
+constexpr int VM_PX = 4;
+
+template <class F>
+__device__ __forceinline__ void vm_un(float *r, int dst, int a, F f) {
+#pragma unroll
+    for (int j = 0; j < VM_PX; ++j) r[(dst * VM_PX + j) * VM_THREADS] = f(r[(a * VM_PX + j) * VM_THREADS]);
+}
+template <class F>
+__device__ __forceinline__ void vm_bin(float *r, int dst, int a, int b, F f) {
+#pragma unroll
+    for (int j = 0; j < VM_PX; ++j) r[(dst * VM_PX + j) * VM_THREADS] = f(r[(a * VM_PX + j) * VM_THREADS], r[(b * VM_PX + j) * VM_THREADS]);
+}
+
 __global__ void __launch_bounds__(VM_THREADS) vm_kernel(const __grid_constant__ VmParams p) {
-    extern __shared__ float regs[];                         // [n_regs][VM_THREADS]
-    float *r = regs + threadIdx.x;
+    extern __shared__ __align__(16) float vm_smem[];       // [n_ins] uint2 program | [n_regs][VM_PX][VM_THREADS] registers
+    uint2 *prog = reinterpret_cast<uint2 *>(vm_smem);
+    float *r = vm_smem + 2 * p.n_ins + threadIdx.x;
+    for (int i = threadIdx.x; i < p.n_ins; i += VM_THREADS) prog[i] = __ldg(reinterpret_cast<const uint2 *>(p.prog) + i);
+    __syncthreads();
     const long long npx = (long long)p.H * p.W, total = npx * p.n;
-    for (long long gi = (long long)blockIdx.x * VM_THREADS + threadIdx.x; gi < total; gi += (long long)gridDim.x * VM_THREADS) {
-        const int frame = (int)(gi / npx);
-        const long long pix = gi - (long long)frame * npx;
-        const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
+    for (long long base = (long long)blockIdx.x * (VM_THREADS * VM_PX); base < total; base += (long long)gridDim.x * (VM_THREADS * VM_PX)) {
+        int frame[VM_PX], y[VM_PX], x[VM_PX];
+        long long pix[VM_PX];
+        bool live[VM_PX];
+#pragma unroll
+        for (int j = 0; j < VM_PX; ++j) {
+            long long gi = base + j * VM_THREADS + threadIdx.x;
+            live[j] = gi < total;
+            gi = live[j] ? gi : total - 1;                  // dead lanes recompute the last pixel and do not store
+            frame[j] = (int)(gi / npx);
+            pix[j] = gi - (long long)frame[j] * npx;
+            y[j] = (int)(pix[j] / p.W);
+            x[j] = (int)(pix[j] - (long long)y[j] * p.W);
+        }
         for (int pc = 0; pc < p.n_ins; ++pc) {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p.prog) + pc);
-            avb_vm_ins in;
-            in.op = raw.x & 0xffu; in.dst = (raw.x >> 8) & 0xffu; in.a = (raw.x >> 16) & 0xffu; in.b = raw.x >> 24; in.imm = raw.y;
-#define RA (r[in.a * VM_THREADS])
-#define RB (r[in.b * VM_THREADS])
-            float v;
-            switch (in.op) {
+            const uint2 raw = prog[pc];
+            const int op = raw.x & 0xffu, dst = (raw.x >> 8) & 0xffu, a = (raw.x >> 16) & 0xffu, b = raw.x >> 24;
+            switch (op) {
                 case AVB_VM_LOAD: {
-                    const avb_vm_src &s = p.src[in.a];
-                    long long idx;
-                    switch (s.kind) {
-                        case AVB_VM_SRC_PLANE: idx = (long long)frame * s.frame_stride + pix * s.pix_stride + in.b; break;
-                        case AVB_VM_SRC_ROW: idx = (long long)y * s.pix_stride + in.b; break;
-                        case AVB_VM_SRC_COL: idx = (long long)x * s.pix_stride + in.b; break;
-                        default: idx = (long long)frame * s.frame_stride + in.b; break;      // per-frame scalars
+                    const avb_vm_src &s = p.src[a];
+                    const float *ptr = static_cast<const float *>(s.ptr);
+#pragma unroll
+                    for (int j = 0; j < VM_PX; ++j) {
+                        long long idx;
+                        switch (s.kind) {
+                            case AVB_VM_SRC_PLANE: idx = (long long)frame[j] * s.frame_stride + pix[j] * s.pix_stride + b; break;
+                            case AVB_VM_SRC_ROW: idx = (long long)y[j] * s.pix_stride + b; break;
+                            case AVB_VM_SRC_COL: idx = (long long)x[j] * s.pix_stride + b; break;
+                            default: idx = (long long)frame[j] * s.frame_stride + b; break;      // per-frame scalars
+                        }
+                        r[(dst * VM_PX + j) * VM_THREADS] = __ldg(ptr + idx);
                     }
-                    v = __ldg(static_cast<const float *>(s.ptr) + idx);
                     break;
                 }
-                case AVB_VM_CONST: v = __uint_as_float(in.imm); break;
-                case AVB_VM_MOV: v = RA; break;
-                case AVB_VM_ADD: v = __fadd_rn(RA, RB); break;
-                case AVB_VM_SUB: v = __fsub_rn(RA, RB); break;
-                case AVB_VM_MUL: v = __fmul_rn(RA, RB); break;
-                case AVB_VM_DIV: v = __fdiv_rn(RA, RB); break;
-                case AVB_VM_MIN: v = fminf(RA, RB); break;
-                case AVB_VM_MAX: v = fmaxf(RA, RB); break;
-                case AVB_VM_POW: v = powf(RA, RB); break;
-                case AVB_VM_ATAN2: v = atan2f(RA, RB); break;
-                case AVB_VM_GT: v = RA > RB ? 1.f : 0.f; break;
-                case AVB_VM_GE: v = RA >= RB ? 1.f : 0.f; break;
-                case AVB_VM_LT: v = RA < RB ? 1.f : 0.f; break;
-                case AVB_VM_LE: v = RA <= RB ? 1.f : 0.f; break;
-                case AVB_VM_NEG: v = -RA; break;
-                case AVB_VM_ABS: v = fabsf(RA); break;
-                case AVB_VM_SQRT: v = __fsqrt_rn(RA); break;
-                case AVB_VM_EXP: v = expf(RA); break;
-                case AVB_VM_SIN: v = sinf(RA); break;
-                case AVB_VM_COS: v = cosf(RA); break;
-                case AVB_VM_FLOOR: v = floorf(RA); break;
-                case AVB_VM_SRGB_DEC: v = vm_srgb_dec(RA); break;
-                case AVB_VM_SRGB_ENC: v = vm_srgb_enc(RA); break;
-                case AVB_VM_QUANT: v = truncf(fminf(fmaxf(__fadd_rn(__fmul_rn(RA, 255.0f), 0.5f), 0.f), 255.f)); break;   // uv_helpers.py:26-30
-                case AVB_VM_SELECT: v = RA != 0.f ? RB : r[(in.imm & 0xffu) * VM_THREADS]; break;
-                case AVB_VM_STORE: {
-                    const avb_vm_dst &d = p.dst[in.b];
-                    const long long idx = (long long)frame * d.frame_stride + (long long)y * d.row_stride + (long long)x * d.pix_stride + in.imm;
-                    const float val = RA;
-                    if (d.kind == AVB_VM_DST_U8) static_cast<uint8_t *>(d.ptr)[idx] = (uint8_t)val;
-                    else static_cast<float *>(d.ptr)[idx] = val;
-                    continue;
+                case AVB_VM_CONST: {
+                    const float v = __uint_as_float(raw.y);
+#pragma unroll
+                    for (int j = 0; j < VM_PX; ++j) r[(dst * VM_PX + j) * VM_THREADS] = v;
+                    break;
                 }
-                default: continue;
+                case AVB_VM_MOV: vm_un(r, dst, a, [](float u) { return u; }); break;
+                case AVB_VM_ADD: vm_bin(r, dst, a, b, [](float u, float v) { return __fadd_rn(u, v); }); break;
+                case AVB_VM_SUB: vm_bin(r, dst, a, b, [](float u, float v) { return __fsub_rn(u, v); }); break;
+                case AVB_VM_MUL: vm_bin(r, dst, a, b, [](float u, float v) { return __fmul_rn(u, v); }); break;
+                case AVB_VM_DIV: vm_bin(r, dst, a, b, [](float u, float v) { return __fdiv_rn(u, v); }); break;
+                case AVB_VM_MIN: vm_bin(r, dst, a, b, [](float u, float v) { return fminf(u, v); }); break;
+                case AVB_VM_MAX: vm_bin(r, dst, a, b, [](float u, float v) { return fmaxf(u, v); }); break;
+                case AVB_VM_POW: vm_bin(r, dst, a, b, [](float u, float v) { return powf(u, v); }); break;
+                case AVB_VM_ATAN2: vm_bin(r, dst, a, b, [](float u, float v) { return atan2f(u, v); }); break;
+                case AVB_VM_GT: vm_bin(r, dst, a, b, [](float u, float v) { return u > v ? 1.f : 0.f; }); break;
+                case AVB_VM_GE: vm_bin(r, dst, a, b, [](float u, float v) { return u >= v ? 1.f : 0.f; }); break;
+                case AVB_VM_LT: vm_bin(r, dst, a, b, [](float u, float v) { return u < v ? 1.f : 0.f; }); break;
+                case AVB_VM_LE: vm_bin(r, dst, a, b, [](float u, float v) { return u <= v ? 1.f : 0.f; }); break;
+                case AVB_VM_NEG: vm_un(r, dst, a, [](float u) { return -u; }); break;
+                case AVB_VM_ABS: vm_un(r, dst, a, [](float u) { return fabsf(u); }); break;
+                case AVB_VM_SQRT: vm_un(r, dst, a, [](float u) { return __fsqrt_rn(u); }); break;
+                case AVB_VM_EXP: vm_un(r, dst, a, [](float u) { return expf(u); }); break;
+                case AVB_VM_SIN: vm_un(r, dst, a, [](float u) { return sinf(u); }); break;
+                case AVB_VM_COS: vm_un(r, dst, a, [](float u) { return cosf(u); }); break;
+                case AVB_VM_FLOOR: vm_un(r, dst, a, [](float u) { return floorf(u); }); break;
+                case AVB_VM_SRGB_DEC: vm_un(r, dst, a, [](float u) { return vm_srgb_dec(u); }); break;
+                case AVB_VM_SRGB_ENC: vm_un(r, dst, a, [](float u) { return vm_srgb_enc(u); }); break;
+                case AVB_VM_QUANT:                                                         // uv_helpers.py:26-30
+                    vm_un(r, dst, a, [](float u) { return truncf(fminf(fmaxf(__fadd_rn(__fmul_rn(u, 255.0f), 0.5f), 0.f), 255.f)); });
+                    break;
+                case AVB_VM_SELECT: {
+                    const int c = raw.y & 0xffu;
+#pragma unroll
+                    for (int j = 0; j < VM_PX; ++j)
+                        r[(dst * VM_PX + j) * VM_THREADS] = r[(a * VM_PX + j) * VM_THREADS] != 0.f ? r[(b * VM_PX + j) * VM_THREADS] : r[(c * VM_PX + j) * VM_THREADS];
+                    break;
+                }
+                case AVB_VM_STORE: {
+                    const avb_vm_dst &d = p.dst[b];
+#pragma unroll
+                    for (int j = 0; j < VM_PX; ++j) {
+                        if (!live[j]) continue;
+                        const long long idx = (long long)frame[j] * d.frame_stride + (long long)y[j] * d.row_stride + (long long)x[j] * d.pix_stride + raw.y;
+                        const float val = r[(a * VM_PX + j) * VM_THREADS];
+                        if (d.kind == AVB_VM_DST_U8) static_cast<uint8_t *>(d.ptr)[idx] = (uint8_t)val;
+                        else static_cast<float *>(d.ptr)[idx] = val;
+                    }
+                    break;
+                }
+                default: break;
             }
-#undef RA
-#undef RB
-            r[in.dst * VM_THREADS] = v;
         }
     }
 }
@@ -156,12 +199,13 @@ extern "C" int avb_vm_run(const avb_vm_ins *prog_dev, int n_ins, int n_regs, int
         p.dst[i] = dst_host[i];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)n_regs * VM_THREADS * sizeof(float);
+    const size_t smem = (size_t)n_ins * sizeof(uint2) + (size_t)n_regs * VM_PX * VM_THREADS * sizeof(float);
     static SmemOptIn optin;
-    if (smem > 48 * 1024) AVB_CUDA_OK(optin.ensure(vm_kernel, AVB_VM_MAX_REGS * VM_THREADS * (int)sizeof(float)));
-    const long long total = (long long)n * H * W;
-    const int per_sm = std::max(1, std::min(8, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + VM_THREADS - 1) / VM_THREADS, (long long)sm_count() * per_sm));
+    const int smem_max = AVB_VM_MAX_INS * (int)sizeof(uint2) + AVB_VM_MAX_REGS * VM_PX * VM_THREADS * (int)sizeof(float);
+    if (smem > 48 * 1024) AVB_CUDA_OK(optin.ensure(vm_kernel, smem_max));
+    const long long total = (long long)n * H * W, tiles = (total + VM_THREADS * VM_PX - 1) / (VM_THREADS * VM_PX);
+    const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * per_sm));
     AVB_TIMED("k7_vm", st);
     vm_kernel<<<grid, VM_THREADS, smem, st>>>(p);
     AVB_CUDA_OK(cudaGetLastError());

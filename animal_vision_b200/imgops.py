@@ -113,15 +113,17 @@ class ImgOps:
         sm = np.array([1.0, 2.0, 1.0], np.float32)
         return self.blur_taps(x, d, sm), self.blur_taps(x, sm, d)
 
-    def remap(self, x, map_x: np.ndarray, map_y: np.ndarray):
+    def remap(self, x, map_x: np.ndarray, map_y: np.ndarray, key=None):
         """cv2.remap(x, map_x, map_y, INTER_LINEAR, BORDER_REFLECT101) with host-built float32 maps (anableps.py:224-237)."""
         n, H, W, Cn = self._check(x)
         mx = np.ascontiguousarray(map_x, np.float32)
         my = np.ascontiguousarray(map_y, np.float32)
         assert mx.shape == (H, W) and my.shape == (H, W)
         import hashlib
-        dx = self.eng.cached(("remap", hashlib.sha1(mx.tobytes()).hexdigest()), lambda: self.eng._dev(mx))
-        dy = self.eng.cached(("remap", hashlib.sha1(my.tobytes()).hexdigest()), lambda: self.eng._dev(my))
+        kx = ("remap_x", key) if key is not None else ("remap", hashlib.sha1(mx.tobytes()).hexdigest())
+        ky = ("remap_y", key) if key is not None else ("remap", hashlib.sha1(my.tobytes()).hexdigest())
+        dx = self.eng.cached(kx, lambda: self.eng._dev(mx))
+        dy = self.eng.cached(ky, lambda: self.eng._dev(my))
         out = self.t.empty_like(x)
         with self.t.cuda.device(self.eng.device):
             rc = self.lib.avb_img_remap(x.data_ptr(), out.data_ptr(), n, H, W, Cn, dx.data_ptr(), dy.data_ptr(), self.eng.stream_ptr())

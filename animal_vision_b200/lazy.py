@@ -224,6 +224,22 @@ class Lazy:
         dev = self.eng.cached(("lazy_tab2", hashlib.sha1(a.tobytes()).hexdigest()), lambda: self.eng._dev(a.reshape(1, self.H, self.W, 1)))
         return E("LOAD", src=Source(dev, SRC_PLANE, 0, 1), ch=0)
 
+    def keyed(self, key, build, kind: str = "table") -> E:
+        """A pixel-independent table that is a pure function of `key` (species parameters + geometry): `build()` runs on the
+        host only the first time the key is seen on this device -- a video stream never recomputes its masks.
+        kind: "table" (H,W), "row" (H) or "col" (W)."""
+        full = ("lazy_keyed", kind, self.H, self.W, key)
+        dev = self.eng._cache.get(full)
+        if dev is None:
+            a = np.ascontiguousarray(build(), np.float32)
+            shape = {"table": (self.H, self.W), "row": (self.H,), "col": (self.W,)}[kind]
+            if a.size != int(np.prod(shape)):
+                raise AvbError(f"keyed {kind} has {a.size} values, expected {shape}")
+            dev = self.eng._cache[full] = self.eng._dev(a.reshape((1, self.H, self.W, 1)) if kind == "table" else a.reshape(-1))
+        if kind == "table":
+            return E("LOAD", src=Source(dev, SRC_PLANE, 0, 1), ch=0)
+        return E("LOAD", src=Source(dev, SRC_ROW if kind == "row" else SRC_COL, 0, 1), ch=0)
+
     def scalar(self, tensor, index: int = 0) -> E:
         """A per-frame device scalar: tensor is float32 [n, k] (contiguous), value tensor[frame, index]."""
         t = self.t

@@ -347,6 +347,54 @@ def run_config_legs(dev, species, peak, with_cpu: bool):
     return out
 
 
+# ----------------------------------------------------------------------------- UV species leg
+UV_SPECIES = [("Reindeer", "reindeer"), ("RatUV", "rat_uv"), ("Goldfish", "goldfish"), ("Damselfish", "damselfish"),
+              ("Anableps", "anableps"), ("Anchovy", "anchovy"), ("Guppy", "guppy"), ("Morpho", "morpho"), ("Heliconius", "heliconius"),
+              ("Pieris", "pieris"), ("MantisShrimp", "mantis_shrimp"), ("Kestrel", "kestrel"), ("JumpingSpider", "jumping_spider"),
+              ("Dragonfly", "dragonfly"), ("Hummingbird", "hummingbird")]
+
+
+def run_uv_species_leg(dev, peak, with_cpu: bool):
+    """The 15 panorama / UV species on 1080p uint8 frames (two outputs each: warped baseline + view, 9 B/px algorithmic).
+      device_ms     `visualize_batch` on a device-resident batch of 4 frames, CUDA events, per frame; the batch rotates over
+                    8 distinct batches (199 MB of input, > L2)
+      launches      kernels per call (K6 operators + K7 fused element-wise programs)
+      cpu_reference the oracle port (bit-equal to the reference on the golden frames) on ONE 540x960 frame, this host's cores"""
+    import torch
+    import animal_vision_b200.animals as A
+    from animal_vision_b200.engine import get_engine
+    eng = get_engine(dev)
+    H, W, nb, ring_n = 1080, 1920, 4, 8
+    ring = torch.randint(0, 256, (ring_n, nb, H, W, 3), dtype=torch.uint8, device=dev)
+    small = np.random.default_rng(0).integers(0, 256, (540, 960, 3), dtype=np.uint8)
+    out = {}
+    for cls, fn in UV_SPECIES:
+        sp = getattr(A, cls)()
+        for i in range(2):
+            sp.visualize_batch(ring[i])
+        torch.cuda.synchronize()
+        l0 = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(ring_n):
+            sp.visualize_batch(ring[i])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (ring_n * nb)
+        ach = 9 * H * W / (ms * 1e-3) / 1e9
+        rec = {"device_ms_per_frame": ms, "device_mpix_per_s": H * W / (ms * 1e-3) / 1e6, "launches_per_call": (eng.launches - l0) // ring_n,
+               "roofline_frac_hbm": ach / peak}
+        if with_cpu:
+            from oracle import uv_species as O
+            t0 = time.perf_counter()
+            getattr(O, fn)(small)
+            dt = time.perf_counter() - t0
+            rec["cpu_reference"] = {"ms": dt * 1e3, "mpix_per_s": small.shape[0] * small.shape[1] / dt / 1e6, "frame": "540x960", "kind": "port",
+                                    "cores": _affinity_cores()}
+        out[cls] = rec
+    return {"frame": f"{W}x{H} uint8, batches of {nb}", "algorithmic_bytes_per_px": 9, "species": out}
+
+
 # ----------------------------------------------------------------------------- K4 leg
 MSTPP_FLOP_PER_PATCH = 169.2e9      # SURVEY.md 8a-19: 482x512 patch, 2 x MAC, unpadded channel counts
 
@@ -599,6 +647,7 @@ def run_b200(args):
 
     # ---- BASELINE configs[0..2]: one 1080p frame per species through visualize(np.ndarray) (rank 0 only)
     configs = run_config_legs(dev, species, peak, with_cpu=(world == 1 and not args.no_cpu)) if rank == 0 and not args.no_configs else None
+    uv_species = run_uv_species_leg(dev, peak, with_cpu=(world == 1 and not args.no_cpu)) if rank == 0 and not args.no_configs else None
     barrier()
 
     # sanity: the e2e outputs equal the device-resident outputs (same kernels, same inputs)
@@ -631,6 +680,7 @@ def run_b200(args):
     }
     line["mstpp"] = mstpp
     line["configs"] = configs
+    line["uv_species"] = uv_species
     line["colorimetric"] = colorimetric
     if world == 1 and not args.no_cpu:
         threads = host_threads()

@@ -141,3 +141,30 @@ def test_band_maps_1e5():
             for k, b in enumerate(bands):
                 ref = O.band(hsi, lam, b)
                 assert np.abs(got[..., k] - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-6), (f.dtype, scale, pano, b)
+
+
+def test_frame_batcher_on_the_device_matches_direct_calls():
+    """serving.FrameBatcher with the real device runner: frames from several 'sockets' come back equal to the species'
+    own visualize() (index [1]) -- Dog (one output), Cat (two) and a UV species (two)."""
+    from animal_vision_b200 import serving
+    import animal_vision_b200.animals as A
+    fs = [frames.natural(96, 128, s) for s in range(5)]
+    with serving.FrameBatcher(max_batch=4, max_delay_ms=20.0) as fb:
+        futs = [(k, f, fb.submit(f, k)) for f in fs for k in ("dog", "cat", "reindeer")]
+        res = [(k, f, fu.result(timeout=120)) for k, f, fu in futs]
+    direct = {"dog": A.Dog(), "cat": A.Cat(), "reindeer": A.Reindeer()}
+    for k, f, out in res:
+        assert np.array_equal(out, direct[k].visualize(f)[1]), k
+    assert any(n > 1 for _, n in fb.batches)
+
+
+def test_split_compare_on_device():
+    import torch
+    from animal_vision_b200.renderers.video import split_compare_batch
+    a = torch.randint(0, 256, (3, 64, 97, 3), dtype=torch.uint8, device="cuda")
+    b = torch.randint(0, 256, (3, 64, 97, 3), dtype=torch.uint8, device="cuda")
+    out = split_compare_batch(a, b)
+    ref = a.clone()
+    ref[:, :, 48:] = b[:, :, 48:]
+    ref[:, :, 48:49] = 255
+    assert out.is_cuda and torch.equal(out, ref)
