@@ -1078,7 +1078,8 @@ static int gauss_mma_mode() {
 static int pick_seg_h_mma(int n, int H, int W, int d_blocks, int ctas_per_sm) {
     const long strips = (long)((W + G_TW - 1) / G_TW) * n;
     const long slots = (long)sm_count() * ctas_per_sm;
-    const int max_segs = std::max(1, H / (8 * M_RB * d_blocks));      // re-produced rows per segment <= ~12 %
+    const int max_segs = std::max(1, H / (2 * M_RB));                 // the score below weighs re-produced rows against wave fill:
+                                                                     // a single 1080p frame prefers many short segments, a batch few long ones
     int best = 1;
     double best_score = -1.0;
     for (int segs = 1; segs <= max_segs && segs <= 64; ++segs) {
