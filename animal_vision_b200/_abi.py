@@ -16,7 +16,7 @@ from . import _build
 _lock = threading.Lock()
 _lib = None
 
-AVB_VERSION = 110            # include/avb200.h AVB_VERSION
+AVB_VERSION = 120            # include/avb200.h AVB_VERSION
 AVB_NORM_DIV255 = 0
 AVB_NORM_AUTO = 1
 AVB_ENC_TABLE_MAX = 2048
@@ -45,6 +45,7 @@ SIGNATURES = {
     "avb_mstpp_destroy": (_i, [_p]),
     "avb_mstpp_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "avb_mstpp_forward": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "avb_mstpp_forward_bands": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "avb_band_project_f32": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
     "avb_safe_norm_f32": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
     "avb_dichromat_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p]),

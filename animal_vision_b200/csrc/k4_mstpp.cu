@@ -102,6 +102,9 @@ struct GemmP {
     int Hreal, Wreal, Cpo, crop_top, crop_left;   // OUT_CONVT: Cpo; OUT_CROP: real size + crop origin
     float *zero_ptr; int zero_n;                  // pointwise pipeline only: block (0,0,0) clears this buffer (attention statistics)
     const float *ln_g, *ln_b; int ln_c;           // pointwise pipeline only: LayerNorm over the ln_c real channels of the fp32 A rows
+    // OUT_CROP only (conv_out): band projection fused on the output -- bands_out[px][r] += sum_c v[c] * band_w[r][c]
+    // (uv_helpers.py:142-146 integrate_band on the network's cube; mantis_shrimp.py:49-60).  out may then be null.
+    const float *band_w; float *bands_out; int n_bands;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -248,9 +251,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmP &p, uint32_t tmem_d, i
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4 *>((float *)p.out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else if (crop_ok) {
+                if (p.out != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (n0 + i < NF) ((float *)p.out)[obase + n0 + i] = v[i];
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < NF) ((float *)p.out)[obase + n0 + i] = v[i];
+                }
+                if (p.bands_out != nullptr) {
+                    // a pixel's 32 channels sit in two threads (16 each): both add their half into the zero-initialised
+                    // band map; a two-term sum does not depend on the order of the additions, so this stays reproducible
+                    float *bo = p.bands_out + (obase / NF) * p.n_bands;
+                    for (int r = 0; r < p.n_bands; ++r) {
+                        const float *w = p.band_w + r * NF + n0;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < NF) acc = fmaf(v[i], __ldg(w + i), acc);
+                        atomicAdd(bo + r, acc);
+                    }
+                }
             }
         }
     }
@@ -2014,9 +2032,22 @@ extern "C" int64_t avb_mstpp_workspace_bytes(int n, int H, int W, int pad_multip
     return (int64_t)carve(nullptr, nullptr, n, Hp, Wp);
 }
 
+extern "C" int avb_mstpp_forward_bands(void *handle, const void *in, int in_is_u8, float *out, float *bands_out,
+                                       const float *band_weights_dev, int n_bands, int n, int H, int W,
+                                       int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream);
+
 extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, float *out, int n, int H, int W,
                                  int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream) {
-    AVB_REQUIRE(handle && in && out && workspace_dev, "null pointer");
+    AVB_REQUIRE(out, "null pointer");
+    return avb_mstpp_forward_bands(handle, in, in_is_u8, out, nullptr, nullptr, 0, n, H, W, pad_multiple, centred, workspace_dev, stream);
+}
+
+extern "C" int avb_mstpp_forward_bands(void *handle, const void *in, int in_is_u8, float *out, float *bands_out,
+                                       const float *band_weights_dev, int n_bands, int n, int H, int W,
+                                       int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream) {
+    AVB_REQUIRE(handle && in && workspace_dev && (out || bands_out), "null pointer");
+    AVB_REQUIRE((bands_out == nullptr) == (n_bands == 0) && (bands_out == nullptr || band_weights_dev) && n_bands >= 0 && n_bands <= 64,
+                "bands_out, band_weights_dev and n_bands (1..64) go together");
     AVB_REQUIRE(n > 0 && n <= 65535 && H > 1 && W > 1, "bad geometry");
     AVB_REQUIRE(pad_multiple > 0 && pad_multiple % 8 == 0, "pad_multiple must be a positive multiple of 8");
     Model *M = static_cast<Model *>(handle);
@@ -2049,6 +2080,10 @@ extern "C" int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, flo
         p.A1 = hin; p.lda1 = 32; p.K1 = p.K = 288; p.W = M->conv_out; p.Np = 32; p.rows = Hp * Wp;
         p.Hi = p.Ho = Hp; p.Wi = p.Wo = Wp; p.Cpin = 32;
         p.res1 = ws.x0; p.ldr1 = 32; p.out = out; p.out_mode = OUT_CROP; p.Hreal = H; p.Wreal = W; p.crop_top = top; p.crop_left = left;
+        if (bands_out) {
+            AVB_CUDA_OK(cudaMemsetAsync(bands_out, 0, sizeof(float) * (size_t)n * H * W * n_bands, cx.st));
+            p.band_w = band_weights_dev; p.bands_out = bands_out; p.n_bands = n_bands;
+        }
         launch_conv3(cx, p, "k4_conv3x3");
     }
     AVB_REQUIRE(!cx.unsupported, "layer shape without a kernel");

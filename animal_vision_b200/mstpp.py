@@ -197,6 +197,36 @@ class MSTPlusPlus:
         """Model-direct semantics on channels-last frames: [N,H,W,3] -> [N,H,W,31]."""
         return self._run(frames, 8, False)
 
+    def forward_bands(self, frames, weights: np.ndarray, *, want_cube: bool = False, pad_multiple: int = 8, centred: bool = False):
+        """Forward with the band projection fused on the network output (avb_mstpp_forward_bands): frames [N,H,W,3]
+        float32 / uint8 CUDA, weights [R,31] (e.g. tables.mantis_band_matrix) -> bands [N,H,W,R]; with want_cube also
+        the 31-band cube, otherwise it is never written.  BASELINE config 4: the mantis-shrimp multi-receptor projection."""
+        t = self.eng.torch
+        w = np.ascontiguousarray(weights, np.float32)
+        assert w.ndim == 2 and w.shape[1] == N_FEAT
+        if not (frames.is_cuda and frames.dim() == 4 and frames.shape[3] == 3 and frames.dtype in (t.float32, t.uint8)):
+            raise AvbError("forward_bands: expected a CUDA float32 / uint8 tensor [N,H,W,3]")
+        frames = frames.contiguous()
+        n, h, wd_, _ = frames.shape
+        with t.cuda.device(self.eng.device):
+            need = int(self.eng.lib.avb_mstpp_workspace_bytes(n, h, wd_, pad_multiple, int(centred)))
+            if need <= 0:
+                raise AvbError("avb_mstpp_workspace_bytes: bad geometry")
+            key = self.eng.stream_ptr()
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < need:
+                self._ws[key] = None
+                ws = self._ws[key] = t.empty(need, dtype=t.uint8, device=self.eng.device)
+            import hashlib
+            wdev = self.eng.cached(("band_w", hashlib.sha1(w.tobytes()).hexdigest()), lambda: self.eng._dev(w))
+            bands = t.empty((n, h, wd_, w.shape[0]), dtype=t.float32, device=self.eng.device)
+            cube = t.empty((n, h, wd_, N_FEAT), dtype=t.float32, device=self.eng.device) if want_cube else None
+            rc = self.eng.lib.avb_mstpp_forward_bands(self._h, frames.data_ptr(), int(frames.dtype == t.uint8),
+                                                      None if cube is None else cube.data_ptr(), bands.data_ptr(), wdev.data_ptr(),
+                                                      int(w.shape[0]), n, h, wd_, pad_multiple, int(centred), ws.data_ptr(), self.eng.stream_ptr())
+        check(rc, "avb_mstpp_forward_bands")
+        return (bands, cube) if want_cube else bands
+
     def forward(self, x):
         """MST_Plus_Plus.forward: NCHW float32 CUDA tensor [b,3,h,w] -> [b,31,h,w]."""
         return self._run(x.permute(0, 2, 3, 1), 8, False).permute(0, 3, 1, 2)

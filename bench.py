@@ -440,7 +440,18 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
     for _ in range(iters):
         bands = safe_norm_maps(mantis_bands(cube, net))
     s2.record()
+    # configs[3] as BASELINE words it: forward with the ten-band projection fused on the output (no cube written)
+    from animal_vision_b200 import tables as _tables
+    Wm = _tables.mantis_band_matrix(np.linspace(400.0, 700.0, 31, dtype=np.float32))
+    for _ in range(3):
+        net.forward_bands(x1, Wm)
+    s3, s4 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+    s3.record()
+    for _ in range(iters):
+        fused_bands = net.forward_bands(x1, Wm)
+    s4.record()
     barrier()
+    fused_ms = s3.elapsed_time(s4) / iters
     single_ms, bands_ms = s0.elapsed_time(s1) / iters, s1.elapsed_time(s2) / iters
     cpu_ref = None
     if world == 1 and not args.no_cpu:
@@ -455,7 +466,7 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
         cpu_ref = {"ms_per_patch": cpu_s * 1e3, "patches_per_s": 1.0 / cpu_s, "kind": "port", "cores": _affinity_cores(),
                    "what": "fp32 torch-CPU forward of the reference architecture (oracle restatement, pinned to the reference module), one 482x512 patch, all host threads",
                    "gpu_vs_cpu_max_abs_rel": rel}
-    return {"single_patch_ms": single_ms, "mantis_bands_ms": bands_ms, "cpu_reference": cpu_ref,
+    return {"single_patch_ms": single_ms, "mantis_bands_ms": bands_ms, "single_patch_fused_bands_ms": fused_ms, "cpu_reference": cpu_ref,
             "workload": f"MST++ forward, {nb} x 3x482x512 patches per GPU (BASELINE configs[3]), seeded weights, bf16 operands / fp32 accumulate",
             "patches_per_s": nb * world / (ms * 1e-3), "ms_per_forward": ms, "batch_per_gpu": nb, "concurrent_forwards": parts,
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AVB_VERSION 110            /* 0.1.1 */
+#define AVB_VERSION 120            /* 0.1.2 */
 
 #define AVB_OK 0
 #define AVB_E_ARG (-1)             /* bad argument (null pointer, non-positive size, unsupported radius ...) */
@@ -196,6 +196,14 @@ AVB_API int avb_mstpp_destroy(void *handle);
 AVB_API int64_t avb_mstpp_workspace_bytes(int n, int H, int W, int pad_multiple, int centred);
 AVB_API int avb_mstpp_forward(void *handle, const void *in, int in_is_u8, float *out, int n, int H, int W,
                               int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream);
+/* The same forward with the band projection of `integrate_band` (uv_helpers.py:142-146) FUSED on the network output
+ * (BASELINE config 4: "mantis shrimp multi-receptor projection via MST++"): bands_out [n,H,W,n_bands] float32 =
+ * cube . band_weights^T, band_weights_dev [n_bands][31] (e.g. the ten raised-cosine bands of mantis_shrimp.py:49-60),
+ * evaluated in the epilogue of conv_out from the accumulator registers.  out may be NULL: the 31-band cube is then never
+ * written (30 MB per 482x512 patch).  bands_out = NULL, n_bands = 0 is avb_mstpp_forward. */
+AVB_API int avb_mstpp_forward_bands(void *handle, const void *in, int in_is_u8, float *out, float *bands_out,
+                                    const float *band_weights_dev, int n_bands, int n, int H, int W,
+                                    int pad_multiple, int centred, void *workspace_dev, avb_stream_t stream);
 
 /* Spectral band projection out[px][r] = sum_b cube[px][b] * weights[r][b] -- np.tensordot over the band
  * axis as in uv_helpers.py:142-146 integrate_band and animals/mantis_shrimp.py:49-60 (ten bands);

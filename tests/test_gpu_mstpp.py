@@ -85,6 +85,16 @@ def test_full_patch_482x512_and_mantis_bands(model):
     ref_full = uv.project_cube(ref[0].permute(1, 2, 0).numpy(), Wm)
     mx, l2 = _rel(got, ref_full)
     assert mx <= TOL and l2 <= TOL
+    # the projection FUSED into the conv_out epilogue (avb_mstpp_forward_bands): same bands, cube optional
+    xh = x.cuda().permute(0, 2, 3, 1).contiguous()
+    fused, cube2 = net.forward_bands(xh, Wm, want_cube=True)
+    assert torch.equal(cube2[0], cube)                                        # the cube itself is unchanged
+    assert np.abs(fused[0].cpu().numpy() - ref_b).max() <= 1e-5 * np.abs(ref_b).max()
+    only = net.forward_bands(xh, Wm)
+    assert torch.equal(only, fused)                                           # reproducible, with or without the cube store
+    b2 = torch.cat([xh, xh.flip(1)], 0)
+    fb = net.forward_bands(b2, Wm)
+    assert torch.equal(fb[0], fused[0]) and fb.shape == (2, 482, 512, 10)
 
 
 def test_bad_state_dict_is_rejected():
