@@ -137,7 +137,12 @@ __device__ __forceinline__ uint32_t encode_u8(const EncTable &t, float x) {
     uint32_t b = __float_as_uint(__saturatef(x));
     b = max(b, t.lo_bits);
     uint32_t ent = t.e[(b - t.lo_bits) >> t.shift];
+#ifdef AVB_ENC_NO_THRESHOLD
+    // EXPERIMENT: spend the 1-LSB budget -- the bucket's start byte without the threshold compare
+    return ent & 0xffu;
+#else
     return (ent & 0xffu) + (((b & t.mask) >= (ent >> 8)) ? 1u : 0u);
+#endif
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {

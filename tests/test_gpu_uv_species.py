@@ -168,3 +168,14 @@ def test_split_compare_on_device():
     ref[:, :, 48:] = b[:, :, 48:]
     ref[:, :, 48:49] = 255
     assert out.is_cuda and torch.equal(out, ref)
+
+
+def test_map_uv_purple_yellow(golden):
+    """uv_mappers.py:67-87 against the reference's own output (float32 linear RGB, <= 1e-5)."""
+    from animal_vision_b200.uv_mappers import map_uv_purple_yellow
+    g = golden("uv_mapper_py")
+    got = map_uv_purple_yellow(g["U"])
+    assert got.shape == g["out"].shape and got.dtype == np.float32
+    assert np.abs(got - g["out"]).max() <= 1e-5
+    with pytest.raises(ValueError):
+        map_uv_purple_yellow(np.zeros((4, 4, 3), np.float32))

@@ -95,3 +95,12 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def mapper_golden():
+    """tests/golden/uv_mapper_py.npz: reference uv_mappers.map_uv_purple_yellow on a seeded plane."""
+    um = R.module("uv_mappers")
+    U = (frames.natural(60, 84, 4)[..., 0].astype(np.float32) / 255.0) ** 2
+    path = os.path.join(ROOT, "tests", "golden", "uv_mapper_py.npz")
+    np.savez_compressed(path, U=U, out=um.map_uv_purple_yellow(U))
+    print("wrote", path)
