@@ -4,8 +4,9 @@
 // the reference: classic_rgb_to_hsi.py:47-82, honeybee.py:126-135).
 //
 // The global statistics force several passes over the frame; every pass RE-COMPUTES the receptor
-// catches from the uint8 input (3 B/px, L2-resident between passes for a frame group) instead of
-// round-tripping fp32 planes through HBM:
+// catches from the uint8 input (3 B/px from HBM per pass: a 20-frame launch is 498 MB, far beyond the 126 MB L2; running
+// frames in L2-sized groups was measured and is SLOWER -- 2.61 -> 3.06 / 3.72 / 5.73 ms per 20 4K frames for groups of
+// 4 / 2 / 1, the passes are issue bound, not DRAM bound) instead of round-tripping fp32 planes through HBM:
 //   stats    raw catches -> per-frame max and sum of each receptor          (white patch / gray world)
 //   prep     (1 thread per frame) fold the adaptation into the receptor matrix, size the bins
 //   hist     adapted + blurred catches -> mapper quantities -> 2048 linear bins per quantity
