@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "avb_common.cuh"
@@ -1341,6 +1342,146 @@ __global__ void __launch_bounds__(256) attn_stats_kernel(const __grid_constant__
     }
 }
 
+// ---- the same statistics on the tensor cores (round 2).  The CUDA-core kernel above issues 87 warp instructions per
+// pixel (a 4x4 register tile of G per thread: 47 us for the 250 K pixels of the full-resolution level, 11 % of a forward);
+// G = K^T Q over 16 pixels is ONE K-step of mma.sync.m16n8k16 (bf16 operands are exactly what q|k|v holds, f32
+// accumulate), i.e. ~1 warp instruction per pixel, which leaves the kernel bound by reading q and k once.
+// A head's 31 channels start at column 31*head: the (up to) five aligned 8-channel chunks covering them are staged as a
+// 40-wide bf16 window (zero padded to 48), G_window = K_w^T Q_w is 3 x 5 MMA tiles, the head's block is cut out at the
+// end; |k_i|^2 and |q_j|^2 are the diagonals of K_w^T K_w / Q_w^T Q_w (the 2 diagonal tiles of every 16-row block).
+// Both operands come straight from the [pixel][channel] rows with ldmatrix.trans.  Same fixed-point merge, same layout,
+// same geometry-only split as above: bit-reproducible and batch invariant.
+constexpr int AS_TP = 64, AS_PITCH = 56;          // pixels per staging round; bf16 per staged row (112 B = 7 x 16 B: conflict-free ldmatrix)
+__device__ __forceinline__ void as_ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void as_mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) attn_stats_mma_kernel(const __grid_constant__ AttnStatP p) {
+    pdl_wait();
+    __shared__ __align__(16) bf16 qs[2][AS_TP][AS_PITCH];          // two stages: cp.async of round r+1 while round r multiplies
+    __shared__ __align__(16) bf16 ks[2][AS_TP][AS_PITCH];
+    __shared__ float Gs[48][40];                   // window Gram, summed over the CTA's warps in a fixed order
+    __shared__ float Ds[2][48];                    // diagonals: |k|^2, |q|^2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int p0 = blockIdx.x * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
+    const int ld = 3 * p.Cp;
+    const int lo8 = (head * NF) & ~7, off = head * NF - lo8;
+    for (int e = tid; e < 2 * AS_TP * AS_PITCH / 2; e += 128) {      // pad columns (and chunks beyond Cp) stay zero for the whole kernel
+        reinterpret_cast<uint32_t *>(&qs[0][0][0])[e] = 0u;
+        reinterpret_cast<uint32_t *>(&ks[0][0][0])[e] = 0u;
+    }
+    for (int e = tid; e < 48 * 40; e += 128) (&Gs[0][0])[e] = 0.f;
+    if (tid < 96) (&Ds[0][0])[tid] = 0.f;
+    float accG[3][5][4], accK[3][2][4], accQ[3][2][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accG[i][j][c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accK[i][j][c] = accQ[i][j][c] = 0.f;
+    }
+    __syncthreads();
+    const uint32_t qs_sh = tc::smem_u32(&qs[0][0][0]), ks_sh = tc::smem_u32(&ks[0][0][0]);
+    constexpr uint32_t STAGE = AS_TP * AS_PITCH * 2;                 // bytes per stage of one operand
+    // ldmatrix.trans lane roles.  A fragment (16 channels x 16 pixels) of tile mt: matrices (px 0-7 | 8-15) x (ch +0 | +8):
+    //   matrix mi = lane >> 3: pixel row (lane & 7) + 8 (mi >> 1), channel 16 mt + 8 (mi & 1)  -> a0..a3
+    // B fragments (16 pixels x 8 channels) of tiles nt, nt+1: pixel row (lane & 7) + 8 (mi & 1), channel 8 (nt + (mi >> 1))
+    const int a_px = (lane & 7) + 8 * (lane >> 4), a_ch = 8 * ((lane >> 3) & 1);
+    const int b_px = (lane & 7) + 8 * ((lane >> 3) & 1), b_ch = 8 * (lane >> 4);
+    auto stage_round = [&](int t0, int st) {                          // 16-byte cp.async per (pixel, chunk); rows past the end are zero filled
+        for (int e = tid; e < AS_TP * 10; e += 128) {
+            const int px = e / 10, c = e - px * 10;
+            const int isk = c >= 5, chunk = c - 5 * isk, col0 = lo8 + 8 * chunk;
+            if (col0 >= p.Cp) continue;
+            const bool live = t0 + px < p1;
+            const bf16 *src = p.qkv + ((long long)b * p.rows + (live ? t0 + px : p0)) * ld + isk * p.Cp + col0;
+            const uint32_t dst = (isk ? ks_sh : qs_sh) + st * STAGE + 2u * (uint32_t)(px * AS_PITCH + 8 * chunk);
+            const int bytes = live ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int n_rounds = (p1 - p0 + AS_TP - 1) / AS_TP;
+    if (n_rounds > 0) stage_round(p0, 0);
+    for (int r = 0; r < n_rounds; ++r) {
+        if (r + 1 < n_rounds) {
+            stage_round(p0 + (r + 1) * AS_TP, (r + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        {
+            const uint32_t qb = qs_sh + (r & 1) * STAGE, kb = ks_sh + (r & 1) * STAGE;
+            const int r0 = 16 * warp;                               // this warp's 16 pixels of the round
+            uint32_t aK[3][4], aQ[3][4], bQ[6][2], bK[6][2];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                as_ldsm_x4_trans(aK[mt], kb + 2u * (uint32_t)((r0 + a_px) * AS_PITCH + 16 * mt + a_ch));
+                as_ldsm_x4_trans(aQ[mt], qb + 2u * (uint32_t)((r0 + a_px) * AS_PITCH + 16 * mt + a_ch));
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 3; ++n2) {
+                uint32_t r4[4];
+                as_ldsm_x4_trans(r4, qb + 2u * (uint32_t)((r0 + b_px) * AS_PITCH + 16 * n2 + b_ch));
+                bQ[2 * n2][0] = r4[0]; bQ[2 * n2][1] = r4[1]; bQ[2 * n2 + 1][0] = r4[2]; bQ[2 * n2 + 1][1] = r4[3];
+                as_ldsm_x4_trans(r4, kb + 2u * (uint32_t)((r0 + b_px) * AS_PITCH + 16 * n2 + b_ch));
+                bK[2 * n2][0] = r4[0]; bK[2 * n2][1] = r4[1]; bK[2 * n2 + 1][0] = r4[2]; bK[2 * n2 + 1][1] = r4[3];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < 5; ++nt) as_mma_bf16(accG[mt][nt], aK[mt], bQ[nt][0], bQ[nt][1]);
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {                       // the two 8-column tiles on the diagonal of row block mt
+                    as_mma_bf16(accK[mt][d], aK[mt], bK[2 * mt + d][0], bK[2 * mt + d][1]);
+                    as_mma_bf16(accQ[mt][d], aQ[mt], bQ[2 * mt + d][0], bQ[2 * mt + d][1]);
+                }
+            }
+        }
+        __syncthreads();                                             // the stage is overwritten by the copies issued next round
+    }
+    // fragment (row g / g+8, columns 2t, 2t+1) of tile (mt, nt) -> window matrix; warps add in the fixed order 0,1,2,3
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Gs[16 * mt + g + 8 * (c >> 1)][8 * nt + 2 * t + (c & 1)] += accG[mt][nt][c];
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int row = g + 8 * (c >> 1), col = 8 * d + 2 * t + (c & 1);     // inside the 16 x 16 diagonal block
+                        if (row == col) { Ds[0][16 * mt + row] += accK[mt][d][c]; Ds[1][16 * mt + row] += accQ[mt][d][c]; }
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(p.stats) + ((long long)b * p.heads + head) * 1024;
+    for (int e = tid; e < 1024; e += 128) {
+        const int i = e >> 5, j = e & 31;
+        float v;
+        if (i < NF && j < NF) v = Gs[off + i][off + j];
+        else if (i < NF) v = Ds[0][off + i];                                                  // [i][31] = |k_i|^2
+        else if (j < NF) v = Ds[1][off + j];                                                  // [31][j] = |q_j|^2
+        else v = 0.f;
+        atomicAdd(out + e, (unsigned long long)__double2ll_rn((double)v * STAT_SCALE));
+    }
+}
+
 // attn = softmax_j(rescale * G_ij / (max(|k_i|,1e-12) max(|q_j|,1e-12)))  (:127-131), then
 // M[co][h*31+j] = sum_i Wproj[co][h*31+i] attn_h[i][j]  -> bf16 [B][Cp][Cp] (zero padded).
 struct AttnFinP {
@@ -1901,7 +2042,16 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
         AVB_TIMED("k4_attn_stats", cx.st);
-        launch_pdl(attn_stats_kernel, dim3(ctas, m.heads, cx.B), dim3(256), 0, cx.st, p);
+        static const bool cuda_core_stats = [] { const char *e = std::getenv("AVB_MSTPP_STATS_CUDA_CORES"); return e && e[0] == '1'; }();
+        if (cuda_core_stats) {
+            launch_pdl(attn_stats_kernel, dim3(ctas, m.heads, cx.B), dim3(256), 0, cx.st, p);
+        } else {
+            // the tensor-core kernel streams: two CTAs per SM over all heads, each a long double-buffered run of pixels
+            ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 2 / std::max(1, m.heads)));
+            p.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
+            ctas = (rows + p.px_per_cta - 1) / p.px_per_cta;
+            launch_pdl(attn_stats_mma_kernel, dim3(ctas, m.heads, cx.B), dim3(128), 0, cx.st, p);
+        }
     }
     {
         AttnFinP p{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};

@@ -1,9 +1,11 @@
 """GPU parity of the UV species against golden vectors generated from the unmodified reference
 (tools/make_golden_uv.py -> tests/golden/uv_species.npz) and against the oracle at other shapes.
 Tolerances (BASELINE.json north_star): <= 1 LSB on uint8 outputs; <= 1e-5 relative on the float32 spectral intermediates
-(the band maps, test_band_maps_1e5).  Float32 FRAMES in -> float32 frames out are held to 1e-3 of the [0,1] output range
-(a quarter of an 8-bit step): several species divide by sums of near-zero saliency maps (hummingbird.py:189-192,
-w = c / (cb + cg + cr + 1e-8)), which amplifies float32 rounding -- the reference's own as much as ours -- to ~2e-4."""
+(the band maps, test_band_maps_1e5) and <= 2e-5 of the [0,1] output range on float32 frames in -> float32 frames out
+(measured: 2.4e-7 ... 4.5e-6 for fourteen species).  Hummingbird alone is held to 1e-3: its tint weights are RATIOS of
+difference-of-Gaussian maps, w = c / (cb + cg + cr + 1e-8) (hummingbird.py:160-165, :189-192); where all three are ~1e-6
+(cancellation residue of two nearly equal blurs) the ratio is rounding noise in the reference as much as here and moves
+the blended tint by ~2e-4 -- still 1/20 of an 8-bit step, and its uint8 outputs are within 1 LSB like everyone's."""
 import os
 
 import numpy as np
@@ -55,7 +57,10 @@ def _noise_mask(name, shape, reach=9):
     return cv2.dilate(flat, np.ones((2 * reach + 1, 2 * reach + 1), np.uint8)).astype(bool)
 
 
-def _cmp(got, ref, what, max_frac=0.02, ftol=1e-3, mask=None):
+FTOL = {"hummingbird": 1e-3}
+
+
+def _cmp(got, ref, what, max_frac=0.02, ftol=2e-5, mask=None):
     assert got.shape == ref.shape and got.dtype == ref.dtype, what
     keep = np.ones(ref.shape[:2], bool) if mask is None else ~mask
     if ref.dtype == np.uint8:
@@ -90,7 +95,7 @@ def test_against_reference_golden(name, golden):
             mask = _noise_mask(name, ref.shape)
             if case in ("natural", "noise", "dark"):
                 assert mask.mean() < 0.5, f"{key}: {mask.mean():.2f} of the frame masked"
-        _cmp(base if which == "base" else out, ref, key, mask=mask)
+        _cmp(base if which == "base" else out, ref, key, mask=mask, ftol=FTOL.get(name, 2e-5))
         seen += 1
     assert seen >= 5, f"no golden vectors for {name}"
 
