@@ -136,6 +136,19 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(const __grid_constant__ 
                 case AVB_VM_QUANT:                                                         // uv_helpers.py:26-30
                     vm_un(r, dst, a, [](float u) { return truncf(fminf(fmaxf(__fadd_rn(__fmul_rn(u, 255.0f), 0.5f), 0.f), 255.f)); });
                     break;
+                case AVB_VM_ADDI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fadd_rn(u, m); }); break; }
+                case AVB_VM_SUBI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fsub_rn(u, m); }); break; }
+                case AVB_VM_RSUBI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fsub_rn(m, u); }); break; }
+                case AVB_VM_MULI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fmul_rn(u, m); }); break; }
+                case AVB_VM_DIVI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fdiv_rn(u, m); }); break; }
+                case AVB_VM_RDIVI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return __fdiv_rn(m, u); }); break; }
+                case AVB_VM_MINI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return fminf(u, m); }); break; }
+                case AVB_VM_MAXI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return fmaxf(u, m); }); break; }
+                case AVB_VM_POWI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return powf(u, m); }); break; }
+                case AVB_VM_GTI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return u > m ? 1.f : 0.f; }); break; }
+                case AVB_VM_GEI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return u >= m ? 1.f : 0.f; }); break; }
+                case AVB_VM_LTI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return u < m ? 1.f : 0.f; }); break; }
+                case AVB_VM_LEI: { const float m = __uint_as_float(raw.y); vm_un(r, dst, a, [m](float u) { return u <= m ? 1.f : 0.f; }); break; }
                 case AVB_VM_SELECT: {
                     const int c = raw.y & 0xffu;
 #pragma unroll

@@ -19,7 +19,13 @@ from ._abi import AvbError, check
 
 OPS = {name: i for i, name in enumerate(
     ["NOP", "LOAD", "CONST", "MOV", "ADD", "SUB", "MUL", "DIV", "MIN", "MAX", "POW", "ATAN2", "GT", "GE", "LT", "LE", "NEG",
-     "ABS", "SQRT", "EXP", "SIN", "COS", "FLOOR", "SRGB_DEC", "SRGB_ENC", "QUANT", "SELECT", "STORE"])}   # enum in include/avb200.h
+     "ABS", "SQRT", "EXP", "SIN", "COS", "FLOOR", "SRGB_DEC", "SRGB_ENC", "QUANT", "SELECT", "STORE",
+     "ADDI", "SUBI", "RSUBI", "MULI", "DIVI", "RDIVI", "MINI", "MAXI", "POWI", "GTI", "GEI", "LTI", "LEI"])}   # enum in include/avb200.h
+# (op, constant on the right) / (op, constant on the left) -> immediate form; comparisons flip when the constant is on the left
+_IMM_RIGHT = {"ADD": "ADDI", "SUB": "SUBI", "MUL": "MULI", "DIV": "DIVI", "MIN": "MINI", "MAX": "MAXI", "POW": "POWI",
+              "GT": "GTI", "GE": "GEI", "LT": "LTI", "LE": "LEI"}
+_IMM_LEFT = {"ADD": "ADDI", "SUB": "RSUBI", "MUL": "MULI", "DIV": "RDIVI", "MIN": "MINI", "MAX": "MAXI",
+             "GT": "LTI", "GE": "LEI", "LT": "GTI", "LE": "GEI"}
 SRC_PLANE, SRC_ROW, SRC_COL, SRC_FRAME = 0, 1, 2, 3
 MAX_SRC, MAX_DST, MAX_REGS, MAX_INS = 24, 4, 48, 2048
 
@@ -106,8 +112,22 @@ def luma(rgb: Sequence[E]) -> E:
     return 0.2126 * rgb[0] + 0.7152 * rgb[1] + 0.0722 * rgb[2]
 
 
+def _imm_form(nd):
+    """(immediate op, register operand, constant) when one operand of a binary node is a constant, else None.
+    IEEE add / mul / min / max are commutative, so `c + x` may issue as `x + c` with identical bits."""
+    if len(nd.args) != 2:
+        return None
+    a, b = nd.args
+    if b.op == "CONST" and nd.op in _IMM_RIGHT and a.op != "CONST":
+        return _IMM_RIGHT[nd.op], a, b.imm
+    if a.op == "CONST" and nd.op in _IMM_LEFT and b.op != "CONST":
+        return _IMM_LEFT[nd.op], b, a.imm
+    return None
+
+
 def _compile(stores):
     """stores: [(E, dst_index, channel)] -> (instruction array uint32[n,2], n_regs, sources)."""
+    roots = {id(r) for r, _, _ in stores}
     order, state = [], {}
     for root, _, _ in stores:                      # iterative post-order over the DAG (shared nodes once)
         stack = [(root, 0)]
@@ -117,9 +137,11 @@ def _compile(stores):
                 if id(node) in state:
                     continue
                 state[id(node)] = 1
-            if i < len(node.args):
+            imm = _imm_form(node)
+            kids = (imm[1],) if imm else node.args      # a constant folded into an immediate is never materialised
+            if i < len(kids):
                 stack.append((node, i + 1))
-                child = node.args[i]
+                child = kids[i]
                 if id(child) not in state:
                     stack.append((child, 0))
             else:
@@ -127,7 +149,8 @@ def _compile(stores):
     pos = {id(nd): k for k, nd in enumerate(order)}
     last = {id(nd): -1 for nd in order}
     for k, nd in enumerate(order):
-        for a in nd.args:
+        imm = _imm_form(nd)
+        for a in ((imm[1],) if imm else nd.args):
             last[id(a)] = max(last[id(a)], k)
     store_at = {}
     for root, d, ch in stores:
@@ -139,11 +162,16 @@ def _compile(stores):
     def emit(op, dst=0, a=0, b=0, imm=0):
         ins.append((OPS[op] | (dst << 8) | (a << 16) | (b << 24), int(imm) & 0xffffffff))
 
+    def fbits(v):
+        return int(np.float32(v).view(np.uint32))
+
     for k, nd in enumerate(order):
-        args = [reg[id(a)] for a in nd.args]
+        imm = _imm_form(nd)
+        operands = (imm[1],) if imm else nd.args
+        args = [reg[id(a)] for a in operands]
         # operands whose last consumer this is: their registers are free again -- also for this very result, since an
         # instruction reads its operands before it writes
-        for aid in {id(x) for x in nd.args}:
+        for aid in {id(x) for x in operands}:
             if last[aid] == k:
                 free.append(reg[aid])
         if free:
@@ -159,7 +187,9 @@ def _compile(stores):
                 sources.append(nd.src)
             emit("LOAD", r, src_index[key], nd.ch)
         elif nd.op == "CONST":
-            emit("CONST", r, imm=int(np.float32(nd.imm).view(np.uint32)))
+            emit("CONST", r, imm=fbits(nd.imm))
+        elif imm:
+            emit(imm[0], r, args[0], imm=fbits(imm[2]))
         elif nd.op == "SELECT":
             emit("SELECT", r, args[0], args[1], args[2])
         elif len(args) == 1:

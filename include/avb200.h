@@ -321,7 +321,12 @@ enum {
     AVB_VM_NOP = 0, AVB_VM_LOAD, AVB_VM_CONST, AVB_VM_MOV, AVB_VM_ADD, AVB_VM_SUB, AVB_VM_MUL, AVB_VM_DIV, AVB_VM_MIN,
     AVB_VM_MAX, AVB_VM_POW, AVB_VM_ATAN2, AVB_VM_GT, AVB_VM_GE, AVB_VM_LT, AVB_VM_LE, AVB_VM_NEG, AVB_VM_ABS,
     AVB_VM_SQRT, AVB_VM_EXP, AVB_VM_SIN, AVB_VM_COS, AVB_VM_FLOOR, AVB_VM_SRGB_DEC, AVB_VM_SRGB_ENC, AVB_VM_QUANT,
-    AVB_VM_SELECT, AVB_VM_STORE, AVB_VM_N_OPS
+    AVB_VM_SELECT, AVB_VM_STORE,
+    /* immediate forms: the second operand is the float in `imm` (R*: reversed, imm op r[a]) -- a constant never costs
+     * an instruction or a register of its own */
+    AVB_VM_ADDI, AVB_VM_SUBI, AVB_VM_RSUBI, AVB_VM_MULI, AVB_VM_DIVI, AVB_VM_RDIVI, AVB_VM_MINI, AVB_VM_MAXI, AVB_VM_POWI,
+    AVB_VM_GTI, AVB_VM_GEI, AVB_VM_LTI, AVB_VM_LEI,
+    AVB_VM_N_OPS
 };
 #define AVB_VM_SRC_PLANE 0
 #define AVB_VM_SRC_ROW 1

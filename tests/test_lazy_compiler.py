@@ -30,6 +30,13 @@ def _interp(ins, n_regs, sources, npx, n_dst_ch):
             continue
         elif op == "SELECT":
             v = np.where(r[a] != 0, r[b], r[imm & 255])
+        elif op.endswith("I") and op[:-1] in ("ADD", "SUB", "RSUB", "MUL", "DIV", "RDIV", "MIN", "MAX", "POW", "GT", "GE", "LT", "LE"):
+            x, m = r[a], np.float32(np.uint32(imm).view(np.float32))
+            with np.errstate(all="ignore"):
+                v = {"ADDI": lambda: x + m, "SUBI": lambda: x - m, "RSUBI": lambda: m - x, "MULI": lambda: x * m, "DIVI": lambda: x / m,
+                     "RDIVI": lambda: m / x, "MINI": lambda: np.minimum(x, m), "MAXI": lambda: np.maximum(x, m), "POWI": lambda: np.power(x, m),
+                     "GTI": lambda: (x > m).astype(np.float32), "GEI": lambda: (x >= m).astype(np.float32),
+                     "LTI": lambda: (x < m).astype(np.float32), "LEI": lambda: (x <= m).astype(np.float32)}[op]()
         else:
             x, y = r[a], r[b]
             with np.errstate(all="ignore"):
@@ -66,6 +73,23 @@ def test_program_equals_numpy_and_registers_are_reused():
         c = np.minimum(c * f(1.01) + (Y if k % 2 else Z), f(2.0))
     assert np.array_equal(got[(0, 0)], r0) and np.array_equal(got[(0, 1)], r1)
     assert np.array_equal(got[(1, 0)], c) and np.array_equal(got[(1, 1)], X)
+    names = [NAMES[int(w0) & 255] for w0, _ in ins]
+    assert "CONST" not in names and "MULI" in names and "MINI" in names          # constants ride in the instruction word
+
+
+def test_constants_on_either_side_and_comparisons():
+    img = np.random.default_rng(1).random((129, 2), dtype=np.float32) * 2 - 1
+    src = L.Source(_FakeTensor(img), L.SRC_PLANE, 0, 2)
+    x, y = (L.E("LOAD", src=src, ch=c) for c in range(2))
+    exprs = [1.0 - x, 2.0 / (y + 3.0), L.where(0.25 < x, x - 0.5, 0.5 - y), L.maximum(0.1, x) ** 1.3, L.where(x >= 0.0, 1.0, L.where(0.0 > y, 2.0, 3.0)),
+             L._e(0.75) + L._e(0.5) * x]
+    ins, n_regs, sources = L._compile([(e, 0, i) for i, e in enumerate(exprs)])
+    got = _interp(ins, n_regs, sources, 129, len(exprs))
+    X, Y, f = img[:, 0], img[:, 1], np.float32
+    ref = [f(1.0) - X, f(2.0) / (Y + f(3.0)), np.where(f(0.25) < X, X - f(0.5), f(0.5) - Y), np.power(np.maximum(f(0.1), X), f(1.3)),
+           np.where(X >= 0, f(1.0), np.where(f(0.0) > Y, f(2.0), f(3.0))), f(0.75) + f(0.5) * X]
+    for i, r in enumerate(ref):
+        assert np.array_equal(got[(0, i)], r.astype(np.float32)), i
 
 
 def test_limits_raise():
