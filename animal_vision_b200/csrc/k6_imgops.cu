@@ -79,28 +79,26 @@ struct ResampleP {
     long long in_fs, in_rs;          // element strides of the input (frame, row); pixels are packed (C floats)
     const int *idx; const float *w;  // [len(axis)][taps]
 };
+// grid (ceil(Wout / 256), Hout, n): a thread owns one output pixel (all C channels share its taps) -- no per-element
+// 64-bit division, the tap index / weight loads are amortised over the channels
 __global__ void __launch_bounds__(256) resample_kernel(const __grid_constant__ ResampleP p) {
-    const long long total = (long long)p.n * p.Hout * p.Wout * p.C;
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        const int c = (int)(e % p.C);
-        long long r = e / p.C;
-        const int x = (int)(r % p.Wout); r /= p.Wout;
-        const int y = (int)(r % p.Hout);
-        const long long f = r / p.Hout;
-        const float *base = p.in + f * p.in_fs;
-        float acc = 0.f;
-        if (p.axis == 0) {
-            const float *row = base + (long long)y * p.in_rs + c;
-            const int *ix = p.idx + (long long)x * p.taps;
-            const float *wt = p.w + (long long)x * p.taps;
-            for (int t = 0; t < p.taps; ++t) acc = fmaf(__ldg(wt + t), row[(long long)__ldg(ix + t) * p.C], acc);
-        } else {
-            const float *col = base + (long long)x * p.C + c;
-            const int *ix = p.idx + (long long)y * p.taps;
-            const float *wt = p.w + (long long)y * p.taps;
-            for (int t = 0; t < p.taps; ++t) acc = fmaf(__ldg(wt + t), col[(long long)__ldg(ix + t) * p.in_rs], acc);
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= p.Wout) return;
+    const float *base = p.in + (long long)blockIdx.z * p.in_fs;
+    float *o = p.out + (((long long)blockIdx.z * p.Hout + y) * p.Wout + x) * p.C;
+    const int sel = p.axis == 0 ? x : y;
+    const int *ix = p.idx + (long long)sel * p.taps;
+    const float *wt = p.w + (long long)sel * p.taps;
+    for (int c0 = 0; c0 < p.C; c0 += 4) {                              // four channels at a time keep the accumulators in registers
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int nc = min(4, p.C - c0);
+        for (int t = 0; t < p.taps; ++t) {
+            const float wv = __ldg(wt + t);
+            const long long s = __ldg(ix + t);
+            const float *q = p.axis == 0 ? base + (long long)y * p.in_rs + s * p.C + c0 : base + s * p.in_rs + (long long)x * p.C + c0;
+            for (int c = 0; c < nc; ++c) acc[c] = fmaf(wv, q[c], acc[c]);
         }
-        p.out[e] = acc;
+        for (int c = 0; c < nc; ++c) o[c0 + c] = acc[c];
     }
 }
 
@@ -138,6 +136,59 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ BlurP
             }
         }
         p.out[e] = acc;
+    }
+}
+
+// The same separable correlation as ONE tiled kernel (C <= 4, the planes the UV species blur): a CTA owns 32 rows x 64 pixels,
+// stages them with their (Ry, Rx) halo in shared memory (REFLECT_101 resolved while loading), runs the row pass into a
+// second shared tile and the column pass from there -- the intermediate never goes to HBM and every input element is read
+// once instead of 2R+1 times through L1.  Tap order and fused multiply-adds are those of blur_kernel: identical bits.
+constexpr int BT_X = 64, BT_Y = 32;
+struct BlurTileP {
+    const float *in; float *out;
+    int n, H, W, C, Rx, Ry;
+    const float *taps_x, *taps_y;
+};
+__global__ void __launch_bounds__(256) blur_tile_kernel(const __grid_constant__ BlurTileP p) {
+    extern __shared__ float bt_smem[];
+    const int C = p.C, Rx = p.Rx, Ry = p.Ry;
+    const int SW = (BT_X + 2 * Rx) * C, TW = BT_X * C, SH = BT_Y + 2 * Ry;
+    float *S = bt_smem;                      // [SH][SW] input tile with halo
+    float *T = S + SH * SW;                  // [SH][TW] after the row pass
+    float *tx = T + SH * TW, *ty = tx + 2 * Rx + 1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * Rx + 1; i += 256) tx[i] = __ldg(p.taps_x + i);
+    for (int i = tid; i < 2 * Ry + 1; i += 256) ty[i] = __ldg(p.taps_y + i);
+    const int x0 = blockIdx.x * BT_X, y0 = blockIdx.y * BT_Y;
+    const float *f = p.in + (long long)blockIdx.z * p.H * p.W * C;
+    const int tr = tid >> 6, tc = tid & 63;                            // 4 rows x 64 lanes: no per-element division anywhere
+    for (int r = tr; r < SH; r += 4) {
+        const float *row = f + (long long)reflect101(y0 - Ry + r, p.H) * p.W * C;
+        for (int cx = tc; cx < BT_X + 2 * Rx; cx += 64) {
+            const float *q = row + (long long)reflect101(x0 - Rx + cx, p.W) * C;
+            for (int c = 0; c < C; ++c) S[r * SW + cx * C + c] = __ldg(q + c);
+        }
+    }
+    __syncthreads();
+    for (int r = tr; r < SH; r += 4) {
+        for (int i = tc; i < TW; i += 64) {
+            const float *q = S + r * SW + i;
+            float acc = 0.f;
+            for (int k = 0; k <= 2 * Rx; ++k) acc = fmaf(tx[k], q[k * C], acc);
+            T[r * TW + i] = acc;
+        }
+    }
+    __syncthreads();
+    float *o = p.out + (long long)blockIdx.z * p.H * p.W * C;
+    const int live = min(TW, (p.W - x0) * C);                           // elements of a tile row inside the image
+    for (int r = tr; r < BT_Y && y0 + r < p.H; r += 4) {
+        float *orow = o + ((long long)(y0 + r) * p.W + x0) * C;
+        for (int i = tc; i < live; i += 64) {
+            const float *q = T + r * TW + i;
+            float acc = 0.f;
+            for (int k = 0; k <= 2 * Ry; ++k) acc = fmaf(ty[k], q[k * TW], acc);
+            orow[i] = acc;
+        }
     }
 }
 
@@ -368,7 +419,8 @@ extern "C" int avb_img_resample(const float *in_dev, float *out_dev, int n, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ResampleP p{in_dev, out_dev, n, Hout, Wout, C, taps, axis, in_frame_stride, in_row_stride, idx_dev, w_dev};
     AVB_TIMED(axis == 0 ? "k6_resample_x" : "k6_resample_y", st);
-    resample_kernel<<<grid_for((long long)n * Hout * Wout * C), 256, 0, st>>>(p);
+    AVB_REQUIRE(Hout <= 65535 && n <= 65535, "frame height / batch too large for one launch");
+    resample_kernel<<<dim3((Wout + 255) / 256, Hout, n), 256, 0, st>>>(p);
     AVB_CUDA_OK(cudaGetLastError());
     return AVB_OK;
 }
@@ -382,6 +434,18 @@ extern "C" int avb_img_blur(const float *in_dev, float *out_dev, float *tmp_dev,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned g = grid_for((long long)n * H * W * C);
     AVB_TIMED("k6_blur", st);
+    {
+        const int Rx = kx / 2, Ry = ky / 2;
+        const size_t smem = sizeof(float) * ((size_t)(BT_Y + 2 * Ry) * (BT_X + 2 * Rx) * C + (size_t)(BT_Y + 2 * Ry) * BT_X * C + kx + ky);
+        if (C <= 4 && smem <= 100 * 1024 && n <= 65535 && in_dev != out_dev) {
+            static SmemOptIn optin;
+            AVB_CUDA_OK(optin.ensure(blur_tile_kernel, 100 * 1024));
+            BlurTileP tp{in_dev, out_dev, n, H, W, C, Rx, Ry, taps_x_dev, taps_y_dev};
+            blur_tile_kernel<<<dim3((W + BT_X - 1) / BT_X, (H + BT_Y - 1) / BT_Y, n), 256, smem, st>>>(tp);
+            AVB_CUDA_OK(cudaGetLastError());
+            return AVB_OK;
+        }
+    }
     BlurP p{in_dev, tmp_dev, n, H, W, C, kx / 2, 0, taps_x_dev};          // rows first, as cv2.GaussianBlur
     blur_kernel<<<g, 256, sizeof(float) * kx, st>>>(p);
     p.in = tmp_dev; p.out = out_dev; p.R = ky / 2; p.axis = 1; p.taps = taps_y_dev;
