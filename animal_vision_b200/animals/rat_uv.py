@@ -50,7 +50,7 @@ class RatUV(UVAnimal):
                 base_out[idx], out[idx] = sub_b, sub_o
             return st0
         self._night = modes[0] == "night"
-        return super()._run(eng, frames, base_out, out, integer)
+        return super()._run(eng, frames, base_out, out, integer, st=st0)        # the stage that made the decision is reused
 
     def _render(self, st):
         lz = st.lz

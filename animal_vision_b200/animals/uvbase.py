@@ -204,8 +204,8 @@ class UVAnimal(Animal):
     def _panorama_scale(self) -> float:
         return float(getattr(self, "panorama_scale", 1.0))
 
-    def _run(self, eng, frames, base_out, out, integer: bool):
-        st = UVStage(eng, frames)
+    def _run(self, eng, frames, base_out, out, integer: bool, st: "UVStage" = None):
+        st = st if st is not None else UVStage(eng, frames)
         st.set_panorama(self._panorama_scale())
         enc = (lambda e: L.quantize(L.linear_to_srgb(L.clip(e, 0.0, 1.0)))) if integer else (lambda e: L.linear_to_srgb(L.clip(e, 0.0, 1.0)))
         st.lz.run([([enc(c) for c in st.baseline()], base_out)])                            # reindeer.py:98-99
