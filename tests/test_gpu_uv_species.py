@@ -184,3 +184,52 @@ def test_map_uv_purple_yellow(golden):
     assert np.abs(got - g["out"]).max() <= 1e-5
     with pytest.raises(ValueError):
         map_uv_purple_yellow(np.zeros((4, 4, 3), np.float32))
+
+
+VARIANTS = [
+    ("reindeer", dict(hsi_scale=1.0, panorama_scale=1.0, winter_mode=False, snow_glare_compression=0.0)),
+    ("reindeer", dict(lambdas=np.linspace(320.0, 720.0, 41, dtype=np.float32), uv_band=(320.0, 420.0), scatter_sigma=0.1)),
+    ("goldfish", dict(haze_strength=0.0, periph_blur_sigma=0.0, base_blur_sigma=0.0, hsi_scale=0.5)),
+    ("damselfish", dict(unsharp_sigma=0.0, uv_gloss_boost=0.0, periph_extra_blur=0.0, panorama_scale=1.0)),
+    ("rat_uv", dict(hsi_scale=1.0, uv_boost_alpha=1.5, panorama_scale=1.1)),
+    ("anableps", dict(ripple_amp_px=0.0, refract_push_px=0.0, haze_strength=0.0, air_clarity_unsharp=0.0)),
+    ("guppy", dict(haze_strength=0.0, unsharp_amount=0.0, vignette_strength=0.0, base_soft_sigma=0.0)),
+    ("morpho", dict(mosaic_downscale=1.0, gloss_sigma=2.0)),
+    ("heliconius", dict(base_soft_sigma=0.0, unsharp_amount=0.0)),
+    ("pieris", dict(clarity_amount=0.0, panorama_scale=1.0)),
+    ("kestrel", dict(sky_haze=0.0, ground_contrast=0.0, unsharp_amount=0.0, periph_blur_sigma=0.0)),
+    ("jumping_spider", dict(scan_row_gain=0.0, spot_gain=0.0, periph_blur_sigma=0.0, periph_vignette_strength=0.0)),
+    ("jumping_spider", dict(spots=((0.3, 0.3),), scan_soften=0.0, clarity_amount=0.0)),
+    ("dragonfly", dict(unsharp_amount=0.0, highlight_strength=0.0, periph_blur_sigma=0.0, base_soft_sigma=0.0)),
+    ("hummingbird", dict(combo_sheen=0.0, guide_gain=0.0, combo_saturation=0.0, periph_blur_sigma=0.0)),
+    ("mantis_shrimp", dict(bands=((320.0, 400.0), (400.0, 500.0), (500.0, 600.0), (600.0, 700.0)), scan_row_gain=0.0, haze_strength=0.0)),
+]
+
+
+@pytest.mark.parametrize("name,kw", VARIANTS, ids=[f"{n}-{i}" for i, (n, _) in enumerate(VARIANTS)])
+def test_constructor_variants_against_oracle(name, kw):
+    """Non-default constructor arguments take the reference's other branches (disabled stages, full-resolution HSI, custom
+    wavelength grids / band lists): same kwargs to the oracle and to the device class."""
+    f = frames.natural(90, 126, 11)
+    ref_base, ref_out = getattr(O, name)(f, **kw)
+    mask = _noise_mask(name, f.shape)
+    base, out = _cls(name)(**kw).visualize(f)
+    _cmp(base, ref_base, f"{name} {sorted(kw)} base")
+    _cmp(out, ref_out, f"{name} {sorted(kw)} out", max_frac=0.03, mask=mask)
+
+
+def test_host_batch_pipeline_with_a_two_output_uv_species():
+    """pipeline.HostBatchPipeline (H2D || kernels || D2H) with a UV species: both outputs (warped baseline, view) equal the
+    device-resident call."""
+    import torch
+    from animal_vision_b200.animals import Goldfish
+    from animal_vision_b200.pipeline import HostBatchPipeline
+    fs = np.stack([frames.natural(72, 100, s) for s in range(5)])
+    host = torch.from_numpy(fs).pin_memory()
+    pipe, sp = HostBatchPipeline(chunk_frames=2), Goldfish()
+    assert pipe.n_outputs(sp) == 2
+    outs = pipe.pinned_like(host, 2)
+    h2d, d2h = pipe.run([(sp, host, outs)])
+    assert h2d == fs.nbytes and d2h == 2 * fs.nbytes
+    base, view = sp.visualize_batch(host.cuda())
+    assert torch.equal(outs[0], base.cpu()) and torch.equal(outs[1], view.cpu())
