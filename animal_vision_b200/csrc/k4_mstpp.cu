@@ -18,6 +18,7 @@
 // -- i.e. attention-apply and the output projection become ONE pointwise GEMM on v.
 #include <cuda.h>          // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched through the runtime
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -999,6 +1000,430 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv3_stream_kernel(const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------ fused feed-forward block
+// FeedForward of an MSAB (MST_Plus_Plus.py:141-158 behind the PreNorm of :57-65)
+//     x += W4 . GELU( dw3x3( GELU( W0 . LayerNorm(x) ) ) )
+// in ONE kernel per 128 hidden channels: the 4c-wide hidden maps never reach HBM (the three-kernel form wrote and read
+// 2 x 256 B per pixel of them at the full-resolution level).  A CTA owns a strip of <= 126 columns and walks down a
+// segment of rows; per image row (M = 128 pixels = strip + x halo):
+//   in :  T1[128 px][128 hidden] = LN(x row)[128][CP] . W0^T        CP/16 tcgen05.mma, N = 128, accumulator in TMEM
+//   E1 :  T1 -> f16 -> GELU (packed f16) -> ring slot of the row ([px][128 ch], zeros outside the map = the conv's padding)
+//   dw :  depthwise 3x3 on the CUDA cores from three ring rows: lane = 4 channels (its 9 x 4 taps live in registers as
+//         half2), warp = a run of 8 pixels, packed HFMA2 (f16 keeps 11 mantissa bits through the nine-term sum: less
+//         rounding than ONE bf16 store of the three-kernel form), -> GELU (packed f16) -> f16 A operand of the out GEMM
+//   out:  T3[128 px][CP] = hidden2[128][128] . W4^T                 8 tcgen05.mma, N = CP
+//   E3 :  T3 + residual row -> x
+// Warp-specialised: 16 loader / epilogue warps run  E1(h), stage LN(x row h+1) | E3(h-2), dw(h-1)  per hidden row h, a 17th
+// warp issues  in(h+1) | out(h-1);  hand-offs are mbarriers (tcgen05.commit one way, one arrival per warp the other) plus
+// ONE named barrier per row among the 16 warps (row h of the ring complete); the ring has four slots so that the write of
+// row h+1 never meets a reader of row h-3.  Measured dead end: the depthwise conv as 72 tcgen05.mma per row (N = 16,
+// diagonal 16x16 tap tiles, A descriptors shifted by dx * 16 B): correct, but an M = 128 MMA re-reads its 4 KB A tile from
+// shared memory in ~128 clk whatever N is -- 144 us per launch against 153 us for the three kernels it replaced.
+// Hidden widths above 128 (level 1) run as one pass per 128-channel chunk: chunk 0 writes x = xin + part0, chunk c adds
+// part_c in place (stream order: the sum order is fixed, the forward stays bit-reproducible); LN(xin) is recomputed.
+struct FfnP {
+    const float *xin;          // [B, H, W, CP] fp32: the residual stream after the attention block (LayerNorm input)
+    const float *res;          // rows the chunk's contribution is added to (xin for chunk 0, out afterwards)
+    float *out;                // [B, H, W, CP]; never aliases xin (halo rows of xin are read while neighbours write out)
+    const uint8_t *wblob;      // this chunk's GEMM operands in shared-memory layout: W0 | W4
+    const float *dw_w;         // depthwise taps of this chunk: [9][dw_stride] fp32, 128 channels used
+    const float *ln_g, *ln_b;
+    int dw_stride, ln_c, H, W, strip_w, seg_rows;
+};
+constexpr int FF_HC = 128;                                  // hidden channels per pass
+constexpr int FF_PXS = 2 * FF_HC + 16;                      // ring bytes per pixel: 128 f16 channels + 16 (conflict-free row-per-lane stores)
+constexpr int FF_SLOT = 128 * FF_PXS;
+constexpr int FF_SLOTS = 4;
+constexpr int FF_ALBO = 2048 + 16;                          // out-GEMM A operand: bytes between k-chunks (padded: conflict-free 8-byte stores)
+constexpr int FF_AOUT = (FF_HC / 8) * FF_ALBO;
+constexpr int FF_TMEM_T1 = 0, FF_TMEM_T3 = 128;
+template <int CP>
+struct FfnCfg {
+    static constexpr int W0_BYTES = (CP / 8) * 2048;        // [CP/8 k-chunks][128 n][16 B]
+    static constexpr int W4_BYTES = (FF_HC / 8) * CP * 16;  // [16 k-chunks][CP n][16 B]
+    static constexpr int BLOB = W0_BYTES + W4_BYTES;
+    static constexpr int AIN = (CP / 8) * 2048;
+    static constexpr int SMEM = FF_SLOTS * FF_SLOT + FF_AOUT + AIN + BLOB + 2 * CP * 4;
+};
+constexpr int FF_EPI_WARPS = 16;                            // loader / epilogue warps; one more warp issues the MMAs
+constexpr int FF_THREADS = (FF_EPI_WARPS + 1) * 32;
+
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "tcgen05.ld shapes used here");
+    uint32_t r[N];
+    if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    } else if constexpr (N == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// GELU for the fused kernel's two hidden-map stages (256 evaluations per pixel: the SFU is their bound):
+//   x Phi(x) = x/2 (1 + tanh(x (a1 + a3 x^2 + a5 x^4))),  minimax fit of the odd polynomial: |error| < 2.6e-5 absolute
+// before the 2^-11 relative error of tanh.approx -- one SFU operation and six FMA-pipe instructions (the erfc form above
+// takes two SFU operations and twelve), an order of magnitude inside the bf16 rounding of the maps it produces.
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float x2 = x * x;
+    float q = fmaf(x2, -0.0003515167885330909f, 0.03700564602227854f);
+    q = fmaf(q, x2, 0.7975078842854375f);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(q * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, th, hx);
+}
+
+// The same in packed f16 (both hidden-map stages of the fused kernel keep f16 maps): cubic argument polynomial
+// (|error| < 2.7e-4 before tanh.approx, monotonic for every x, so overflowing inputs saturate to x / 0 instead of
+// turning over), 9 instructions per PAIR of values including the two SFU operations.
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+    const __half2 a1 = __float2half2_rn(0.8001570785f), a3 = __float2half2_rn(0.0347008934f), hf = __float2half2_rn(0.5f);
+    const __half2 t = __hmul2(__hfma2(__hmul2(x, x), a3, a1), x);
+    uint32_t th;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(*reinterpret_cast<const uint32_t *>(&t)));
+    const __half2 hx = __hmul2(x, hf);
+    return __hfma2(hx, *reinterpret_cast<const __half2 *>(&th), hx);
+}
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {       // round to f16, clamped to the finite range
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return *reinterpret_cast<const __half2 *>(&r);
+}
+// tcgen05.ld of 32 columns split into issue and wait, so that independent work can sit between the two; the wait names
+// the registers as read-write operands: nothing that uses them can be scheduled above it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// UMMA descriptor from its two 32-bit halves (the low word holds the start address >> 4 and the LBO, so stepping through
+// operand tiles is one integer add on it)
+__device__ __forceinline__ void mma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3ffffu) >> 4) | ((lbo_bytes >> 4) << 16); }
+constexpr uint32_t DESC_HI_SBO128 = (128u >> 4) | (1u << 14);       // SBO = 128 B, descriptor version 1, no swizzle
+
+template <int CP>
+__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_constant__ FfnP p) {
+    typedef FfnCfg<CP> Cfg;
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *ring = dsm;                                    // [4 slots][128 px][272 B]: f16 hidden rows
+    uint8_t *Aout = ring + FF_SLOTS * FF_SLOT;              // [16 k-chunks][128 px][16 B], k-chunks FF_ALBO apart
+    uint8_t *Ain = Aout + FF_AOUT;                          // [CP/8 k-chunks][128 px][16 B]
+    uint8_t *W0s = Ain + Cfg::AIN;
+    uint8_t *W4s = W0s + Cfg::W0_BYTES;
+    float *ln_s = reinterpret_cast<float *>(W0s + Cfg::BLOB);            // gamma[CP] | beta[CP]
+    // 0: weights landed; 1: in, 2: out (tcgen05.commit); 3: E1 done + next LN row staged, 4: dw row staged (one arrival per warp)
+    __shared__ __align__(8) uint64_t bars[5];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, H = p.H, W = p.W;
+    const int xs = blockIdx.x * p.strip_w;                  // first output column of the strip
+    const int wv = min(p.strip_w, W - xs);                  // output columns of this strip
+    const int y_begin = blockIdx.y * p.seg_rows, y_end = min(H, y_begin + p.seg_rows);
+    const int h0 = y_begin - 1;
+
+    // ---- set-up that does not depend on the preceding kernel (overlaps its tail under programmatic dependent launch)
+    if (warp == FF_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        mbar_init(&bars[3], FF_EPI_WARPS);
+        mbar_init(&bars[4], FF_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the chunk's GEMM operands are stored in their shared-memory layout: one bulk copy by the TMA engine
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[0])), "r"((uint32_t)Cfg::BLOB) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(W0s)), "l"(p.wblob), "r"((uint32_t)Cfg::BLOB), "r"(smem_u32(&bars[0])) : "memory");
+    }
+    for (int i = tid; i < CP; i += FF_THREADS) {
+        ln_s[i] = i < p.ln_c ? __ldg(p.ln_g + i) : 0.f;
+        ln_s[CP + i] = i < p.ln_c ? __ldg(p.ln_b + i) : 0.f;
+    }
+    // rows 126, 127 of the out-GEMM operand are never produced (their outputs are discarded): keep them finite
+    for (int i = tid; i < (FF_HC / 8) * 2; i += FF_THREADS)
+        *reinterpret_cast<uint4 *>(Aout + (i >> 1) * FF_ALBO + (126 + (i & 1)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+
+    if (warp == FF_EPI_WARPS) {
+        // ================================================================ MMA issuer (one lane; the warp stays converged)
+        pdl_wait();
+        constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
+        // in: A = B = bf16; out: A = B = f16 (the hidden map after the depthwise stage stays f16, W4 is stored as f16)
+        constexpr uint32_t IDESC_IN = IDESC0 | ((uint32_t)(FF_HC >> 3) << 17);
+        constexpr uint32_t IDESC_OUT = (1u << 4) | ((uint32_t)(BM >> 4) << 24) | ((uint32_t)(CP >> 3) << 17);
+        const uint32_t ain_lo = desc_lo(smem_u32(Ain), 2048), w0_lo = desc_lo(smem_u32(W0s), 2048);
+        const uint32_t aout_lo = desc_lo(smem_u32(Aout), FF_ALBO), w4_lo = desc_lo(smem_u32(W4s), CP * 16);
+        auto issue_in = [&]() {
+#pragma unroll
+            for (int j = 0; j < CP / 16; ++j)
+                mma_f16_lh(tmem_d + FF_TMEM_T1, ain_lo + j * (2 * 2048 / 16), DESC_HI_SBO128, w0_lo + j * (2 * 2048 / 16), DESC_HI_SBO128, IDESC_IN,
+                           j > 0 ? 1u : 0u);
+            mma_commit(&bars[1]);
+        };
+        auto issue_out = [&]() {
+#pragma unroll
+            for (int j = 0; j < FF_HC / 16; ++j)
+                mma_f16_lh(tmem_d + FF_TMEM_T3, aout_lo + j * (2 * FF_ALBO / 16), DESC_HI_SBO128, w4_lo + j * (2 * CP * 16 / 16), DESC_HI_SBO128, IDESC_OUT,
+                           j > 0 ? 1u : 0u);
+            mma_commit(&bars[2]);
+        };
+        uint32_t ph_e1 = 0u, ph_e2 = 0u;
+        mbar_wait(&bars[0], 0u);                                  // weights
+        mbar_wait(&bars[3], ph_e1);                               // first LayerNorm row staged
+        ph_e1 ^= 1u;
+        tc_fence_after();
+        if (lane == 0) issue_in();
+        __syncwarp();
+        for (int h = h0; h <= y_end; ++h) {
+            mbar_wait(&bars[3], ph_e1);                           // T1 drained by E1(h), LN row h+1 staged
+            ph_e1 ^= 1u;
+            tc_fence_after();
+            if (lane == 0 && h + 1 <= y_end) issue_in();
+            __syncwarp();
+            if (h - 1 >= y_begin) {
+                mbar_wait(&bars[4], ph_e2);                       // dw row h-1 staged, T3 drained by E3(h-2)
+                ph_e2 ^= 1u;
+                tc_fence_after();
+                if (lane == 0) issue_out();
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================ loader / epilogue warps
+        // depthwise taps of this lane's four channels, as half2 pairs, for the whole kernel
+        __half2 wreg[9][2];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 wv4 = __ldg(reinterpret_cast<const float4 *>(p.dw_w + (long long)t * p.dw_stride + 4 * lane));
+            wreg[t][0] = __floats2half2_rn(wv4.x, wv4.y);
+            wreg[t][1] = __floats2half2_rn(wv4.z, wv4.w);
+        }
+        pdl_wait();
+        // x row loader: four threads per pixel, LayerNorm over the ln_c real channels in registers
+        constexpr int CPT = CP / 4, NV = CPT / 4;              // 8 or 16 channels per thread = 2 or 4 float4
+        const int lr = tid >> 2, lq = tid & 3;
+        const int lx = xs - 1 + lr;
+        const bool lx_ok = (unsigned)lx < (unsigned)W;
+        const float *xin_b = p.xin + (long long)b * H * W * CP;
+        uint4 areg[NV];
+        auto a_fetch = [&](int h) {
+            if (lx_ok && (unsigned)h < (unsigned)H) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(xin_b + ((long long)h * W + lx) * CP + lq * CPT);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) areg[i] = __ldg(q + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) areg[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        auto a_store = [&]() {
+            uint8_t *d = Ain + (lq * (CPT / 8)) * 2048 + lr * 16;
+            const int ch0 = lq * CPT;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
+                s += (ch0 + 4 * i < p.ln_c ? f.x : 0.f) + (ch0 + 4 * i + 1 < p.ln_c ? f.y : 0.f) +
+                     (ch0 + 4 * i + 2 < p.ln_c ? f.z : 0.f) + (ch0 + 4 * i + 3 < p.ln_c ? f.w : 0.f);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            const float mean = s / (float)p.ln_c;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
+                const float d0 = ch0 + 4 * i < p.ln_c ? f.x - mean : 0.f, d1 = ch0 + 4 * i + 1 < p.ln_c ? f.y - mean : 0.f;
+                const float d2 = ch0 + 4 * i + 2 < p.ln_c ? f.z - mean : 0.f, d3 = ch0 + 4 * i + 3 < p.ln_c ? f.w - mean : 0.f;
+                q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            const float rstd = rsqrtf(q / (float)p.ln_c + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < NV; i += 2) {       // gamma / beta are zero on the padded channels: they stay exactly zero
+                float4 f0 = *reinterpret_cast<const float4 *>(&areg[i]), f1 = *reinterpret_cast<const float4 *>(&areg[i + 1]);
+                const float *g = ln_s + ch0 + 4 * i, *be = ln_s + CP + ch0 + 4 * i;
+                f0.x = (f0.x - mean) * rstd * g[0] + be[0]; f0.y = (f0.y - mean) * rstd * g[1] + be[1];
+                f0.z = (f0.z - mean) * rstd * g[2] + be[2]; f0.w = (f0.w - mean) * rstd * g[3] + be[3];
+                f1.x = (f1.x - mean) * rstd * g[4] + be[4]; f1.y = (f1.y - mean) * rstd * g[5] + be[5];
+                f1.z = (f1.z - mean) * rstd * g[6] + be[6]; f1.w = (f1.w - mean) * rstd * g[7] + be[7];
+                *reinterpret_cast<uint4 *>(d + (i / 2) * 2048) =
+                    make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            }
+        };
+
+        // E1 / E3: thread = (pixel em = TMEM lane, quarter eq of the columns)
+        const int em = 32 * (warp & 3) + lane;
+        const uint32_t lane_bits = (uint32_t)(32 * (warp & 3)) << 16;
+        const int eq = warp >> 2;
+        auto h2u = [](uint32_t lo, uint32_t hi) {    // two accumulator columns -> f16 pair -> GELU
+            const __half2 t = gelu_h2(f2h2_sat(__uint_as_float(lo), __uint_as_float(hi)));
+            return *reinterpret_cast<const uint32_t *>(&t);
+        };
+        // hidden row h -> ring slot (h may be -1); the LayerNorm of row h+1 is computed while the TMEM load is in flight
+        auto e1 = [&](int h, bool stage_next) {
+            const int x = xs - 1 + em;
+            const bool live = (unsigned)h < (unsigned)H && (unsigned)x < (unsigned)W;
+            uint8_t *dst = ring + ((h + 4) & 3) * FF_SLOT + em * FF_PXS + eq * 64;
+            uint32_t v[32];
+            tmem_ld32_issue(tmem_d + FF_TMEM_T1 + lane_bits + (uint32_t)(32 * eq), v);
+            if (stage_next) a_store();                          // registers hold row h+1; in(h) has finished with the stage
+            tmem_ld32_wait(v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (live) o = make_uint4(h2u(v[8 * k], v[8 * k + 1]), h2u(v[8 * k + 2], v[8 * k + 3]), h2u(v[8 * k + 4], v[8 * k + 5]), h2u(v[8 * k + 6], v[8 * k + 7]));
+                *reinterpret_cast<uint4 *>(dst + 16 * k) = o;
+            }
+        };
+        // the residual values E3(y) adds are fetched into registers one stage ahead of their use
+        constexpr int QC = CP / 4;                              // 8 or 16 output channels per thread
+        float4 rres[QC / 4];
+        auto res_fetch = [&](int y) {
+            if (em < wv) {
+                const float4 *q = reinterpret_cast<const float4 *>(p.res + ((((long long)b * H + y) * W) + xs + em) * CP + QC * eq);
+#pragma unroll
+                for (int i = 0; i < QC / 4; ++i) rres[i] = q[i];
+            }
+        };
+        auto e3 = [&](int y) {
+            const long long o = ((((long long)b * H + y) * W) + xs + em) * CP + QC * eq;
+            float v[QC];
+            tmem_ldn<QC>(tmem_d + FF_TMEM_T3 + lane_bits + (uint32_t)(QC * eq), v);
+            if (em < wv) {
+#pragma unroll
+                for (int i = 0; i < QC; i += 4) {
+                    const float4 r = rres[i / 4];
+                    *reinterpret_cast<float4 *>(p.out + o + i) = make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w);
+                }
+            }
+        };
+        // depthwise 3x3 + GELU of output row y: warp = output pixels 8 warp .. 8 warp + 7 (ring pixel + 1 is the centre),
+        // lane = channels 4 lane .. 4 lane + 3; two half-runs of four pixels from a 3 x 6 register window
+        auto dw = [&](int y) {
+            const uint8_t *r0 = ring + ((y + 3) & 3) * FF_SLOT + lane * 8;
+            const uint8_t *r1 = ring + ((y + 4) & 3) * FF_SLOT + lane * 8;
+            const uint8_t *r2 = ring + ((y + 5) & 3) * FF_SLOT + lane * 8;
+            uint8_t *ao = Aout + (lane >> 1) * FF_ALBO + (lane & 1) * 8;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int p0 = 8 * warp + 4 * hf;
+                uint2 v[3][6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const int px = min(p0 + c, 127);              // pixels 128, 129 only feed the discarded outputs 126, 127
+                    v[0][c] = *reinterpret_cast<const uint2 *>(r0 + px * FF_PXS);
+                    v[1][c] = *reinterpret_cast<const uint2 *>(r1 + px * FF_PXS);
+                    v[2][c] = *reinterpret_cast<const uint2 *>(r2 + px * FF_PXS);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half2 a0 = __hmul2(*reinterpret_cast<const __half2 *>(&v[0][j].x), wreg[0][0]);
+                    __half2 a1 = __hmul2(*reinterpret_cast<const __half2 *>(&v[0][j].y), wreg[0][1]);
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) {
+                        const uint2 &u = v[t / 3][j + t % 3];
+                        a0 = __hfma2(*reinterpret_cast<const __half2 *>(&u.x), wreg[t][0], a0);
+                        a1 = __hfma2(*reinterpret_cast<const __half2 *>(&u.y), wreg[t][1], a1);
+                    }
+                    a0 = gelu_h2(a0);
+                    a1 = gelu_h2(a1);
+                    const int m = p0 + j;
+                    if (m < 126)
+                        *reinterpret_cast<uint2 *>(ao + m * 16) = make_uint2(*reinterpret_cast<const uint32_t *>(&a0), *reinterpret_cast<const uint32_t *>(&a1));
+                }
+            }
+        };
+        auto publish = [&](uint64_t *bar) {     // this warp's shared-memory writes and TMEM reads are done: one arrival per warp
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+
+        uint32_t ph_in = 0u, ph_out = 0u;
+        a_fetch(h0);
+        a_store();
+        publish(&bars[3]);
+        a_fetch(h0 + 1);
+        for (int h = h0; h <= y_end; ++h) {
+            mbar_wait(&bars[1], ph_in);                         // in(h) complete: T1 holds row h, the LN stage is free
+            ph_in ^= 1u;
+            tc_fence_after();
+            if (h - 2 >= y_begin) res_fetch(h - 2);             // E3(h-2) runs after this iteration's barrier
+            e1(h, h + 1 <= y_end);
+            publish(&bars[3]);
+            if (h + 2 <= y_end) a_fetch(h + 2);
+            asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_WARPS * 32) : "memory");      // ring row h complete, readers of row h-3 done
+            const int y = h - 1;
+            if (y >= y_begin) {
+                if (y - 1 >= y_begin) {
+                    mbar_wait(&bars[2], ph_out);                // out(y-1) complete: T3 holds row y-1, the dw stage is free
+                    ph_out ^= 1u;
+                    tc_fence_after();
+                    e3(y - 1);
+                }
+                dw(y);
+                publish(&bars[4]);
+            }
+        }
+        res_fetch(y_end - 1);
+        mbar_wait(&bars[2], ph_out);
+        tc_fence_after();
+        e3(y_end - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == FF_EPI_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(256) : "memory");
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------ conv_in
@@ -1614,6 +2039,7 @@ struct MsabW {
     const float *pos0, *pos2, *ffn_dw;                            // device fp32 [9][Cp] / [9][Hp]
     const bf16 *wqkv, *ffn0, *ffn4;                               // device bf16
     const float *wqkv32;                                          // device fp32 [3*Cp][Cp] (tf32 TMA kernel)
+    const uint8_t *ffn_blob;                                      // fused FFN (Cp <= 64): per 128-channel hidden chunk W0 | W4
 };
 struct BodyW {
     const bf16 *embedding, *mapping;     // [32][9*32]
@@ -1664,6 +2090,13 @@ static uint16_t f2bf(float f) {          // round to nearest even
     return (uint16_t)(u >> 16);
 }
 
+static uint16_t f2h(float f) {           // IEEE half, round to nearest even
+    const __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
 struct Cursor {
     const float *p; int64_t left;
     const float *take(int64_t n) {
@@ -1711,6 +2144,29 @@ static bool pack_msab(Packer &pk, Cursor &cur, MsabW &m, int c) {
               for (int k = 0; k < c; ++k) d[(size_t)(t * Cp + r) * Cp + k] = src[t][(size_t)r * c + k]; }
     { uint16_t *d = pk.b16((const void **)&m.ffn0, (size_t)Hp * Cp); put_dense(d, Cp, f0, 4 * c, c, 0, 0); }
     { uint16_t *d = pk.b16((const void **)&m.ffn4, (size_t)Cp * Hp); put_dense(d, Hp, f4, c, 4 * c, 0, 0); }
+    m.ffn_blob = nullptr;
+    if (Cp <= 64) {
+        // operands of ffn_fused_kernel, chunk by chunk, in the kernel's shared-memory layout (canonical K-major, 16-byte
+        // entries of 8 k values): W0 [Cp/8][128 n][8] bf16, W4 [16][Cp n][8] f16
+        const int w0_el = (Cp / 8) * 128 * 8, w4_el = 16 * Cp * 8, chunk_el = w0_el + w4_el;
+        const int chunks = Hp / 128;
+        uint16_t *d = pk.b16((const void **)&m.ffn_blob, (size_t)chunks * chunk_el);
+        for (int ck = 0; ck < chunks; ++ck) {
+            uint16_t *w0 = d + (size_t)ck * chunk_el, *w4 = w0 + w0_el;
+            for (int kc = 0; kc < Cp / 8; ++kc)
+                for (int n = 0; n < 128; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int hid = ck * 128 + n, ch = kc * 8 + e;
+                        w0[(kc * 128 + n) * 8 + e] = (hid < 4 * c && ch < c) ? f2bf(f0[(size_t)hid * c + ch]) : 0;
+                    }
+            for (int kc = 0; kc < 16; ++kc)
+                for (int n = 0; n < Cp; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int hid = ck * 128 + kc * 8 + e;
+                        w4[(kc * Cp + n) * 8 + e] = (hid < 4 * c && n < c) ? f2h(f4[(size_t)n * 4 * c + hid]) : 0;
+                    }
+        }
+    }
     return true;
 }
 
@@ -1771,7 +2227,7 @@ static bool pack_model(Packer &pk, Model &M, const float *params, int64_t count)
 
 // ------------------------------------------------------------------------------------ host: schedule
 struct Workspace {
-    float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0;
+    float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0, *xt;
     long long *stats;
     bf16 *qkv, *p1, *p2, *ln, *hid1, *hid2, *M;
     size_t bytes;
@@ -1783,7 +2239,7 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 #define WS_F(name, elems) { float *ptr = (float *)take((elems) * 4); if (w) w->name = ptr; }
 #define WS_B(name, elems) { bf16 *ptr = (bf16 *)take((elems) * 2); if (w) w->name = ptr; }
     WS_F(x0, n0 * 32) WS_F(hA, n0 * 32) WS_F(hB, n0 * 32) WS_F(f0, n0 * 32) WS_F(f1, n1 * 64) WS_F(f2, n2 * 128)
-    WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32)
+    WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32) WS_F(xt, n0 * 32)
     { long long *ptr = (long long *)take((size_t)B * 4 * 1024 * 8); if (w) w->stats = ptr; }
     WS_B(qkv, n0 * 96) WS_B(p1, n0 * 32) WS_B(p2, n0 * 32) WS_B(ln, n0 * 32) WS_B(hid1, n0 * 128) WS_B(hid2, n0 * 128)
     WS_B(M, (size_t)B * 128 * 128)
@@ -2032,6 +2488,24 @@ static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const f
     launch_pdl(dwconv_kernel<DW_CPT>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, cx.st, p);
 }
 
+// FeedForward behind its PreNorm in one kernel per 128 hidden channels: x = xin + W4 GELU(dw(GELU(W0 LN(xin))))
+template <int CP>
+static void ffn_fused_launch(Ctx &cx, const MsabW &m, const float *xin, float *x, int H, int W) {
+    typedef tc::FfnCfg<CP> Cfg;
+    static SmemOptIn opt_in;              // per instantiation, per device
+    opt_in.ensure(tc::ffn_fused_kernel<CP>, Cfg::SMEM);
+    // strips of <= 126 output columns (128 with the x halo = one MMA tile), row segments so that one CTA per SM is busy
+    const int strips = (W + 125) / 126, strip_w = (W + strips - 1) / strips;
+    int segs = std::max(1, sm_count() / std::max(1, strips * cx.B));
+    const int seg_rows = std::max(std::min(H, 4), (H + segs - 1) / segs);
+    segs = (H + seg_rows - 1) / seg_rows;
+    for (int ck = 0; ck < m.Hp / tc::FF_HC; ++ck) {
+        tc::FfnP p{xin, ck == 0 ? xin : x, x, m.ffn_blob + (size_t)ck * Cfg::BLOB, m.ffn_dw + ck * tc::FF_HC, m.ln_g, m.ln_b, m.Hp, m.c, H, W, strip_w, seg_rows};
+        AVB_TIMED("k4_ffn_fused", cx.st);
+        launch_pdl(tc::ffn_fused_kernel<CP>, dim3(strips, segs, cx.B), dim3(tc::FF_THREADS), Cfg::SMEM, cx.st, p);
+    }
+}
+
 // MSAB with num_blocks = 1 (MST_Plus_Plus.py:160-186), in place on x (fp32 [B*rows, Cp]).
 static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws) {
     const int rows = H * W, Cp = m.Cp, Hp = m.Hp;
@@ -2074,12 +2548,22 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         AVB_TIMED("k4_dw_pos", cx.st);
         launch_pdl(dwpos_fused_kernel, dim3((W + DP_TX - 1) / DP_TX, (H + DP_TY - 1) / DP_TY, cx.B * (Cp / DP_CB)), dim3(256), 0, cx.st, p);
     }
+    // the fused feed-forward kernel reads halo rows of its input while neighbouring CTAs write the output: the
+    // attention block then leaves its result in ws.xt and the feed-forward block brings it back to x
+    static const bool ffn_unfused = [] { const char *e = std::getenv("AVB_MSTPP_FFN_UNFUSED"); return e && e[0] == '1'; }();
+    static const int ffn_fused_max_cp = [] { const char *e = std::getenv("AVB_MSTPP_FFN_FUSED_MAXCP"); return e ? atoi(e) : 32; }();
+    const bool ffn_fused = !ffn_unfused && m.ffn_blob != nullptr && (Cp == 32 || Cp == 64) && Cp <= ffn_fused_max_cp;
     // x = v M^T + b + pos + x
     {
         GemmP p = gemm_defaults();
         p.A1 = ws.qkv + 2 * Cp; p.lda1 = 3 * Cp; p.K1 = p.K = Cp; p.W = ws.M; p.w_bstride = (long long)Cp * Cp; p.Np = Cp; p.rows = rows;
-        p.bias = m.bproj; p.res1 = x; p.ldr1 = Cp; p.res2 = ws.p2; p.ldr2 = Cp; p.out = x; p.ldo = Cp;
+        p.bias = m.bproj; p.res1 = x; p.ldr1 = Cp; p.res2 = ws.p2; p.ldr2 = Cp; p.out = ffn_fused ? ws.xt : x; p.ldo = Cp;
         launch_gemm<true, MODE_PW>(cx, p, "k4_gemm_attn_proj");
+    }
+    if (ffn_fused) {
+        if (Cp == 32) ffn_fused_launch<32>(cx, m, ws.xt, x, H, W);
+        else ffn_fused_launch<64>(cx, m, ws.xt, x, H, W);
+        return;
     }
     // FFN: x = W4 GELU(dw(GELU(W0 LN(x)))) + x; the LayerNorm runs inside the FFN-in GEMM's loader
     {

@@ -58,7 +58,7 @@ def main():
         print(f"  {nm:22s} {t:8.3f} ms  {c:4d} launches  {100 * t / tot:5.1f}%")
     print(f"  sum of kernels {tot:.3f} ms, {nrec} launches")
     if "--seq" in sys.argv:
-        for i in range(min(nrec, 40)):
+        for i in range(min(nrec, 64)):
             nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
             print(f"    {i:3d} {nm:22s} {msbuf[i] * 1e3:8.1f} us")
     for parts in (2, 4):
@@ -75,6 +75,7 @@ def main():
             print(f"  {parts} streams: {ms2:.3f} ms/forward, {n / ms2 * 1e3:.1f} patch/s, bitwise equal to the single-stream output: {bool(torch.equal(y2, y))}")
     if check:
         xs = x[:1].cpu().permute(0, 3, 1, 2)
+        from oracle import mstpp as O
         ref = O.forward(xs, sd).permute(0, 2, 3, 1).numpy()
         got = y[:1].cpu().numpy()
         d = np.abs(got - ref)
