@@ -1245,45 +1245,53 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
         pdl_wait();
         // x row loader: four threads per pixel, LayerNorm over the ln_c real channels in registers
         constexpr int CPT = CP / 4, NV = CPT / 4;              // 8 or 16 channels per thread = 2 or 4 float4
+        const float ln_inv_c = 1.0f / (float)p.ln_c, ln_pad = (float)(CP - p.ln_c);
         const int lr = tid >> 2, lq = tid & 3;
         const int lx = xs - 1 + lr;
         const bool lx_ok = (unsigned)lx < (unsigned)W;
-        const float *xin_b = p.xin + (long long)b * H * W * CP;
+        // running 32-bit element offsets (advanced by one image row per call: no 64-bit index arithmetic in the loop;
+        // the host refuses maps of 2^31 elements or more)
+        const uint32_t row_pitch = (uint32_t)(W * CP);
+        uint32_t a_off = (uint32_t)((((long long)b * H + h0) * W + lx) * CP + lq * CPT);         // row of the next a_fetch (wraps for row -1: unused)
+        int a_row = h0;
         uint4 areg[NV];
-        auto a_fetch = [&](int h) {
-            if (lx_ok && (unsigned)h < (unsigned)H) {
-                const uint4 *q = reinterpret_cast<const uint4 *>(xin_b + ((long long)h * W + lx) * CP + lq * CPT);
+        auto a_fetch = [&]() {
+            if (lx_ok && (unsigned)a_row < (unsigned)H) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(p.xin + a_off);
 #pragma unroll
                 for (int i = 0; i < NV; ++i) areg[i] = __ldg(q + i);
             } else {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) areg[i] = make_uint4(0u, 0u, 0u, 0u);
             }
+            a_off += row_pitch;
+            ++a_row;
         };
         auto a_store = [&]() {
             uint8_t *d = Ain + (lq * (CPT / 8)) * 2048 + lr * 16;
             const int ch0 = lq * CPT;
+            // the padded channels of the residual stream are exactly zero: they add nothing to the sum, and (0 - mean)^2
+            // each to the squared deviations, which is taken out again in closed form -- no per-channel masks
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
-                s += (ch0 + 4 * i < p.ln_c ? f.x : 0.f) + (ch0 + 4 * i + 1 < p.ln_c ? f.y : 0.f) +
-                     (ch0 + 4 * i + 2 < p.ln_c ? f.z : 0.f) + (ch0 + 4 * i + 3 < p.ln_c ? f.w : 0.f);
+                s += (f.x + f.y) + (f.z + f.w);
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            const float mean = s / (float)p.ln_c;
+            const float mean = s * ln_inv_c;
             float q = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const float4 f = *reinterpret_cast<const float4 *>(&areg[i]);
-                const float d0 = ch0 + 4 * i < p.ln_c ? f.x - mean : 0.f, d1 = ch0 + 4 * i + 1 < p.ln_c ? f.y - mean : 0.f;
-                const float d2 = ch0 + 4 * i + 2 < p.ln_c ? f.z - mean : 0.f, d3 = ch0 + 4 * i + 3 < p.ln_c ? f.w - mean : 0.f;
+                const float d0 = f.x - mean, d1 = f.y - mean, d2 = f.z - mean, d3 = f.w - mean;
                 q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
             }
             q += __shfl_xor_sync(0xffffffffu, q, 1);
             q += __shfl_xor_sync(0xffffffffu, q, 2);
-            const float rstd = rsqrtf(q / (float)p.ln_c + 1e-5f);
+            q = fmaxf(fmaf(-ln_pad, mean * mean, q), 0.f);
+            const float rstd = rsqrtf(fmaf(q, ln_inv_c, 1e-5f));
 #pragma unroll
             for (int i = 0; i < NV; i += 2) {       // gamma / beta are zero on the padded channels: they stay exactly zero
                 float4 f0 = *reinterpret_cast<const float4 *>(&areg[i]), f1 = *reinterpret_cast<const float4 *>(&areg[i + 1]);
@@ -1305,14 +1313,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
             const __half2 t = gelu_h2(f2h2_sat(__uint_as_float(lo), __uint_as_float(hi)));
             return *reinterpret_cast<const uint32_t *>(&t);
         };
-        // hidden row h -> ring slot (h may be -1); the LayerNorm of row h+1 is computed while the TMEM load is in flight
+        // hidden row h -> ring slot (h may be -1), after staging the LayerNorm of row h+1
         auto e1 = [&](int h, bool stage_next) {
             const int x = xs - 1 + em;
             const bool live = (unsigned)h < (unsigned)H && (unsigned)x < (unsigned)W;
             uint8_t *dst = ring + ((h + 4) & 3) * FF_SLOT + em * FF_PXS + eq * 64;
+            if (stage_next) a_store();                          // registers hold row h+1; in(h) has finished with the stage
             uint32_t v[32];
             tmem_ld32_issue(tmem_d + FF_TMEM_T1 + lane_bits + (uint32_t)(32 * eq), v);
-            if (stage_next) a_store();                          // registers hold row h+1; in(h) has finished with the stage
             tmem_ld32_wait(v);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1324,24 +1332,27 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
         // the residual values E3(y) adds are fetched into registers one stage ahead of their use
         constexpr int QC = CP / 4;                              // 8 or 16 output channels per thread
         float4 rres[QC / 4];
-        auto res_fetch = [&](int y) {
+        // residual / output rows advance with every res_fetch / e3 call (one per output row, in order)
+        uint32_t r_off = (uint32_t)(((((long long)b * H + y_begin) * W) + xs + em) * CP + QC * eq), o_off = r_off;
+        auto res_fetch = [&]() {
             if (em < wv) {
-                const float4 *q = reinterpret_cast<const float4 *>(p.res + ((((long long)b * H + y) * W) + xs + em) * CP + QC * eq);
+                const float4 *q = reinterpret_cast<const float4 *>(p.res + r_off);
 #pragma unroll
                 for (int i = 0; i < QC / 4; ++i) rres[i] = q[i];
             }
+            r_off += row_pitch;
         };
-        auto e3 = [&](int y) {
-            const long long o = ((((long long)b * H + y) * W) + xs + em) * CP + QC * eq;
+        auto e3 = [&]() {
             float v[QC];
             tmem_ldn<QC>(tmem_d + FF_TMEM_T3 + lane_bits + (uint32_t)(QC * eq), v);
             if (em < wv) {
 #pragma unroll
                 for (int i = 0; i < QC; i += 4) {
                     const float4 r = rres[i / 4];
-                    *reinterpret_cast<float4 *>(p.out + o + i) = make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w);
+                    *reinterpret_cast<float4 *>(p.out + o_off + i) = make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w);
                 }
             }
+            o_off += row_pitch;
         };
         // depthwise 3x3 + GELU of output row y: warp = output pixels 8 warp .. 8 warp + 7 (ring pixel + 1 is the centre),
         // lane = channels 4 lane .. 4 lane + 3; two half-runs of four pixels from a 3 x 6 register window
@@ -1387,18 +1398,18 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
         };
 
         uint32_t ph_in = 0u, ph_out = 0u;
-        a_fetch(h0);
+        a_fetch();
         a_store();
         publish(&bars[3]);
-        a_fetch(h0 + 1);
+        a_fetch();
         for (int h = h0; h <= y_end; ++h) {
             mbar_wait(&bars[1], ph_in);                         // in(h) complete: T1 holds row h, the LN stage is free
             ph_in ^= 1u;
             tc_fence_after();
-            if (h - 2 >= y_begin) res_fetch(h - 2);             // E3(h-2) runs after this iteration's barrier
+            if (h - 2 >= y_begin) res_fetch();                  // row h-2: E3(h-2) runs after this iteration's barrier
             e1(h, h + 1 <= y_end);
             publish(&bars[3]);
-            if (h + 2 <= y_end) a_fetch(h + 2);
+            if (h + 2 <= y_end) a_fetch();                      // row h+2
             asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_WARPS * 32) : "memory");      // ring row h complete, readers of row h-3 done
             const int y = h - 1;
             if (y >= y_begin) {
@@ -1406,16 +1417,16 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
                     mbar_wait(&bars[2], ph_out);                // out(y-1) complete: T3 holds row y-1, the dw stage is free
                     ph_out ^= 1u;
                     tc_fence_after();
-                    e3(y - 1);
+                    e3();
                 }
                 dw(y);
                 publish(&bars[4]);
             }
         }
-        res_fetch(y_end - 1);
+        res_fetch();
         mbar_wait(&bars[2], ph_out);
         tc_fence_after();
-        e3(y_end - 1);
+        e3();
     }
     tc_fence_before();
     __syncthreads();
@@ -1605,22 +1616,25 @@ struct DwPosP {
     int B, H, W, Cp;
 };
 constexpr int DP_TX = 16, DP_TY = 8, DP_CB = 32;
-__global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant__ DwPosP p) {
-    pdl_wait();
-    constexpr int IW = DP_TX + 4, IH = DP_TY + 4, MW = DP_TX + 2, MH = DP_TY + 2;
-    __shared__ __align__(16) bf16 sin[IH * IW][DP_CB];
-    __shared__ __align__(16) bf16 smid[MH * MW][DP_CB];
-    __shared__ __align__(16) float sw[2][9][DP_CB];
+constexpr int DP_IW = DP_TX + 4, DP_IH = DP_TY + 4, DP_MW = DP_TX + 2, DP_MH = DP_TY + 2;
+constexpr int DP_SMEM = (DP_IH * DP_IW + DP_MH * DP_MW) * DP_CB * 2 + 2 * 9 * DP_CB * 4;
+// one tile by a CTA of NT threads (NT a multiple of 8); smem: DP_SMEM bytes, 16-byte aligned
+template <int NT>
+__device__ __forceinline__ void dwpos_tile(const DwPosP &p, int bx, int by, int bz, uint8_t *smem) {
+    constexpr int IW = DP_IW, IH = DP_IH, MW = DP_MW, MH = DP_MH;
+    bf16 (*sin)[DP_CB] = reinterpret_cast<bf16 (*)[DP_CB]>(smem);
+    bf16 (*smid)[DP_CB] = reinterpret_cast<bf16 (*)[DP_CB]>(smem + IH * IW * DP_CB * 2);
+    float (*sw)[9][DP_CB] = reinterpret_cast<float (*)[9][DP_CB]>(smem + (IH * IW + MH * MW) * DP_CB * 2);
     const int tid = threadIdx.x;
     const int cblocks = p.Cp / DP_CB;
-    const int b = blockIdx.z / cblocks, c0 = (blockIdx.z - b * cblocks) * DP_CB;
-    const int x0 = blockIdx.x * DP_TX, y0 = blockIdx.y * DP_TY;
-    for (int i = tid; i < 2 * 9 * DP_CB; i += 256) {
+    const int b = bz / cblocks, c0 = (bz - b * cblocks) * DP_CB;
+    const int x0 = bx * DP_TX, y0 = by * DP_TY;
+    for (int i = tid; i < 2 * 9 * DP_CB; i += NT) {
         const int which = i / (9 * DP_CB), r = i - which * 9 * DP_CB, t = r / DP_CB, c = r - t * DP_CB;
         sw[which][t][c] = __ldg((which ? p.w2 : p.w1) + t * p.Cp + c0 + c);
     }
     // stage v: (IH x IW) pixels x 32 channels = 4 x 16-byte vectors per pixel, zeros outside the map
-    for (int i = tid; i < IH * IW * 4; i += 256) {
+    for (int i = tid; i < IH * IW * 4; i += NT) {
         const int px = i >> 2, q = i & 3;
         const int yy = y0 - 2 + px / IW, xx = x0 - 2 + px % IW;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -1655,7 +1669,7 @@ __global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant_
     };
     // first conv + GELU on the tile and its 1-pixel halo
     load_weights(0);
-    for (int i = tid; i < MH * MW * 8; i += 256) {
+    for (int i = tid; i < MH * MW * 8; i += NT) {
         const int px = i >> 3, g = i & 7;
         const int my = px / MW, mx = px - my * MW;
         const int yy = y0 - 1 + my, xx = x0 - 1 + mx;
@@ -1670,7 +1684,7 @@ __global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant_
     __syncthreads();
     // second conv
     load_weights(1);
-    for (int i = tid; i < DP_TY * DP_TX * 8; i += 256) {
+    for (int i = tid; i < DP_TY * DP_TX * 8; i += NT) {
         const int px = i >> 3, g = i & 7;
         const int ty = px / DP_TX, tx = px - ty * DP_TX;
         const int yy = y0 + ty, xx = x0 + tx;
@@ -1681,6 +1695,11 @@ __global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant_
                 make_uint2(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]));
         }
     }
+}
+__global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant__ DwPosP p) {
+    pdl_wait();
+    __shared__ __align__(16) uint8_t smem[DP_SMEM];
+    dwpos_tile<256>(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 
 // ------------------------------------------------------------------------------------ attention statistics
@@ -1794,16 +1813,21 @@ __device__ __forceinline__ void as_mma_bf16(float (&c)[4], const uint32_t (&a)[4
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__global__ void __launch_bounds__(128) attn_stats_mma_kernel(const __grid_constant__ AttnStatP p) {
-    pdl_wait();
-    __shared__ __align__(16) bf16 qs[2][AS_TP][AS_PITCH];          // two stages: cp.async of round r+1 while round r multiplies
-    __shared__ __align__(16) bf16 ks[2][AS_TP][AS_PITCH];
-    __shared__ float Gs[48][40];                   // window Gram, summed over the CTA's warps in a fixed order
-    __shared__ float Ds[2][48];                    // diagonals: |k|^2, |q|^2
+struct AttnStatSmem {
+    bf16 qs[2][AS_TP][AS_PITCH];                   // two stages: cp.async of round r+1 while round r multiplies
+    bf16 ks[2][AS_TP][AS_PITCH];
+    float Gs[48][40];                              // window Gram, summed over the CTA's warps in a fixed order
+    float Ds[2][48];                               // diagonals: |k|^2, |q|^2
+};
+// one CTA of 128 threads: pixels [bx * px_per_cta, ...) of (image b, head)
+__device__ __forceinline__ void attn_stats_cta(const AttnStatP &p, int bx, int head, int b, AttnStatSmem &S) {
+    bf16 (*qs)[AS_TP][AS_PITCH] = S.qs;
+    bf16 (*ks)[AS_TP][AS_PITCH] = S.ks;
+    float (*Gs)[40] = S.Gs;
+    float (*Ds)[48] = S.Ds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int p0 = blockIdx.x * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
+    const int p0 = bx * p.px_per_cta, p1 = min(p.rows, p0 + p.px_per_cta);
     const int ld = 3 * p.Cp;
     const int lo8 = (head * NF) & ~7, off = head * NF - lo8;
     for (int e = tid; e < 2 * AS_TP * AS_PITCH / 2; e += 128) {      // pad columns (and chunks beyond Cp) stay zero for the whole kernel
@@ -1916,6 +1940,11 @@ __global__ void __launch_bounds__(128) attn_stats_mma_kernel(const __grid_consta
         atomicAdd(out + e, (unsigned long long)__double2ll_rn((double)v * STAT_SCALE));
     }
 }
+__global__ void __launch_bounds__(128) attn_stats_mma_kernel(const __grid_constant__ AttnStatP p) {
+    pdl_wait();
+    __shared__ __align__(16) AttnStatSmem S;
+    attn_stats_cta(p, blockIdx.x, blockIdx.y, blockIdx.z, S);
+}
 
 // attn = softmax_j(rescale * G_ij / (max(|k_i|,1e-12) max(|q_j|,1e-12)))  (:127-131), then
 // M[co][h*31+j] = sum_i Wproj[co][h*31+i] attn_h[i][j]  -> bf16 [B][Cp][Cp] (zero padded).
@@ -1973,6 +2002,87 @@ __global__ void __launch_bounds__(1024) attn_finalize_kernel(const __grid_consta
         }
         M[e] = __float2bfloat16_rn(v);
     }
+}
+
+// ------------------------------------------------------------------------------------ attention side kernel
+// Everything between the q|k|v GEMM and the projection GEMM of an MSAB in ONE launch of heterogeneous CTAs (128 threads):
+//   blocks [0, nA)   statistics (attn_stats_cta); the LAST statistics CTA of an (image, head) -- a ticket counter behind
+//                    a __threadfence -- turns the finished sums into that head's softmax and its 31 columns of
+//                    M = Wproj . blockdiag(attn) (what attn_finalize_kernel did in a launch of its own)
+//   blocks [nA, ..)  positional-embedding tiles (dwpos_tile), which depend on v only
+// The two parts are independent (one reads q|k and is bound by HBM, the other is CUDA-core work on v), so they overlap
+// on the SMs instead of running back to back, and two launches per block disappear.  Which CTA finalises is a race, what
+// it computes is not: the sums are integers (fixed point) and the finalising arithmetic has one fixed order.
+struct AttnSideP {
+    AttnStatP st;
+    AttnFinP fin;
+    DwPosP dp;
+    unsigned *tickets;      // [B][heads], zeroed by the q|k|v GEMM together with the statistics
+    int ctasA, nA, gx, gy;  // statistics CTAs per (image, head), their total; positional-embedding grid (x, y)
+};
+union AttnSideSmem {
+    AttnStatSmem st;
+    uint8_t dp[DP_SMEM];
+};
+__device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int h, float (*attn)[32], float *rq) {
+    const int tid = threadIdx.x;
+    const long long *S = p.stats + ((long long)b * p.heads + h) * 1024;
+    if (tid < 32) rq[tid] = tid < NF ? 1.0f / fmaxf(sqrtf((float)((double)__ldcg(S + 31 * 32 + tid) * (1.0 / STAT_SCALE))), 1e-12f) : 0.f;
+    __syncthreads();
+    if (tid < NF) {          // softmax row i = tid (same arithmetic, same order as attn_finalize_kernel)
+        const int i = tid;
+        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf((float)((double)__ldcg(S + i * 32 + 31) * (1.0 / STAT_SCALE))), 1e-12f);
+        float row[NF], mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            row[j] = (float)((double)__ldcg(S + i * 32 + j) * (1.0 / STAT_SCALE)) * (sc * rq[j]);
+            mx = fmaxf(mx, row[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) { row[j] = __expf(row[j] - mx); sum += row[j]; }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) attn[i][j] = row[j] * inv;
+    }
+    __syncthreads();
+    bf16 *M = p.M + (long long)b * p.Cp * p.Cp;
+    for (int e = tid; e < p.Cp * 32; e += 128) {
+        const int co = e >> 5, j = e & 31;
+        if (j < NF) {
+            float v = 0.f;
+            if (co < p.c) {
+                const float *wrow = p.wproj + (long long)co * p.c + h * NF;
+#pragma unroll
+                for (int i = 0; i < NF; ++i) v = fmaf(__ldg(wrow + i), attn[i][j], v);
+            }
+            M[(long long)co * p.Cp + h * NF + j] = __float2bfloat16_rn(v);
+        } else if (h == p.heads - 1) {
+            for (int k = p.c; k < p.Cp; ++k) M[(long long)co * p.Cp + k] = __float2bfloat16_rn(0.f);     // padded columns
+        }
+    }
+}
+__global__ void __launch_bounds__(128) attn_side_kernel(const __grid_constant__ AttnSideP p) {
+    pdl_wait();
+    __shared__ __align__(16) AttnSideSmem sm;
+    __shared__ int is_last;
+    const int bid = blockIdx.x;
+    if (bid >= p.nA) {
+        const int r = bid - p.nA;
+        const int bx = r % p.gx, q = r / p.gx;
+        dwpos_tile<128>(p.dp, bx, q % p.gy, q / p.gy, sm.dp);
+        return;
+    }
+    const int bx = bid % p.ctasA, q = bid / p.ctasA;
+    const int head = q % p.st.heads, b = q / p.st.heads;
+    attn_stats_cta(p.st, bx, head, b, sm.st);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(p.tickets + b * p.st.heads + head, 1u) == (unsigned)(p.ctasA - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    attn_finalize_head(p.fin, b, head, reinterpret_cast<float (*)[32]>(&sm.st.Gs[0][0]), &sm.st.Ds[0][0]);
 }
 
 // ------------------------------------------------------------------------------------ band projection
@@ -2229,6 +2339,7 @@ static bool pack_model(Packer &pk, Model &M, const float *params, int64_t count)
 struct Workspace {
     float *x0, *hA, *hB, *f0, *f1, *f2, *u1, *u0, *d1, *d0, *xt;
     long long *stats;
+    unsigned *tickets;
     bf16 *qkv, *p1, *p2, *ln, *hid1, *hid2, *M;
     size_t bytes;
 };
@@ -2240,6 +2351,7 @@ static size_t carve(Workspace *w, uint8_t *base, int B, int Hp, int Wp) {
 #define WS_B(name, elems) { bf16 *ptr = (bf16 *)take((elems) * 2); if (w) w->name = ptr; }
     WS_F(x0, n0 * 32) WS_F(hA, n0 * 32) WS_F(hB, n0 * 32) WS_F(f0, n0 * 32) WS_F(f1, n1 * 64) WS_F(f2, n2 * 128)
     WS_F(u1, n1 * 64) WS_F(u0, n0 * 32) WS_F(d1, n1 * 64) WS_F(d0, n0 * 32) WS_F(xt, n0 * 32)
+    { unsigned *ptr = (unsigned *)take((size_t)B * 4 * 4); if (w) w->tickets = ptr; }       // directly in front of stats: cleared together
     { long long *ptr = (long long *)take((size_t)B * 4 * 1024 * 8); if (w) w->stats = ptr; }
     WS_B(qkv, n0 * 96) WS_B(p1, n0 * 32) WS_B(p2, n0 * 32) WS_B(ln, n0 * 32) WS_B(hid1, n0 * 128) WS_B(hid2, n0 * 128)
     WS_B(M, (size_t)B * 128 * 128)
@@ -2499,6 +2611,7 @@ static void ffn_fused_launch(Ctx &cx, const MsabW &m, const float *xin, float *x
     int segs = std::max(1, sm_count() / std::max(1, strips * cx.B));
     const int seg_rows = std::max(std::min(H, 4), (H + segs - 1) / segs);
     segs = (H + seg_rows - 1) / seg_rows;
+    if ((long long)cx.B * H * W * CP >= (1LL << 31)) { cx.unsupported = 1; return; }      // 32-bit element offsets inside the kernel
     for (int ck = 0; ck < m.Hp / tc::FF_HC; ++ck) {
         tc::FfnP p{xin, ck == 0 ? xin : x, x, m.ffn_blob + (size_t)ck * Cfg::BLOB, m.ffn_dw + ck * tc::FF_HC, m.ln_g, m.ln_b, m.Hp, m.c, H, W, strip_w, seg_rows};
         AVB_TIMED("k4_ffn_fused", cx.st);
@@ -2514,9 +2627,28 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         GemmP p = gemm_defaults();
         p.A1 = x; p.lda1 = Cp; p.K1 = p.K = Cp; p.W = m.wqkv; p.W32 = m.wqkv32; p.Np = 3 * Cp; p.rows = rows;
         p.out = ws.qkv; p.ldo = 3 * Cp; p.out_bf16 = 1;
-        p.zero_ptr = reinterpret_cast<float *>(ws.stats); p.zero_n = 2 * cx.B * m.heads * 1024;      // int64 entries, accumulated with atomics
+        // tickets | statistics (int64 entries, accumulated with atomics): one contiguous clear
+        p.zero_ptr = reinterpret_cast<float *>(ws.tickets);
+        p.zero_n = (int)(reinterpret_cast<float *>(ws.stats) - reinterpret_cast<float *>(ws.tickets)) + 2 * cx.B * m.heads * 1024;
         launch_gemm<false, MODE_PW>(cx, p, "k4_gemm_qkv");
     }
+    static const bool attn_unmerged = [] { const char *e = std::getenv("AVB_MSTPP_ATTN_UNMERGED"); return e && e[0] == '1'; }();
+    if (!attn_unmerged) {
+        // statistics (+ softmax / M by the last CTA of every head) and the positional embedding in one launch
+        AttnSideP p{};
+        p.st = AttnStatP{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
+        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 2 / std::max(1, m.heads)));     // geometry only: batch invariant
+        p.st.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
+        ctas = (rows + p.st.px_per_cta - 1) / p.st.px_per_cta;
+        p.fin = AttnFinP{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
+        p.dp = DwPosP{ws.qkv + 2 * Cp, 3 * Cp, ws.p2, Cp, m.pos0, m.pos2, cx.B, H, W, Cp};
+        p.tickets = ws.tickets;
+        p.ctasA = ctas; p.nA = ctas * m.heads * cx.B;
+        p.gx = (W + DP_TX - 1) / DP_TX; p.gy = (H + DP_TY - 1) / DP_TY;
+        const long long total = (long long)p.nA + (long long)p.gx * p.gy * cx.B * (Cp / DP_CB);
+        AVB_TIMED("k4_attn_side", cx.st);
+        launch_pdl(attn_side_kernel, dim3((unsigned)total), dim3(128), 0, cx.st, p);
+    } else {
     // Gram + norms over all pixels
     {
         AttnStatP p{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
@@ -2547,6 +2679,7 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         DwPosP p{ws.qkv + 2 * Cp, 3 * Cp, ws.p2, Cp, m.pos0, m.pos2, cx.B, H, W, Cp};
         AVB_TIMED("k4_dw_pos", cx.st);
         launch_pdl(dwpos_fused_kernel, dim3((W + DP_TX - 1) / DP_TX, (H + DP_TY - 1) / DP_TY, cx.B * (Cp / DP_CB)), dim3(256), 0, cx.st, p);
+    }
     }
     // the fused feed-forward kernel reads halo rows of its input while neighbouring CTAs write the output: the
     // attention block then leaves its result in ws.xt and the feed-forward block brings it back to x
