@@ -1520,10 +1520,19 @@ __device__ __forceinline__ void dw_unpack(const typename DwVec<CPT>::T &raw, flo
 #pragma unroll
     for (int q = 0; q < CPT / 2; ++q) { f[2 * q] = __low2float(h2[q]); f[2 * q + 1] = __high2float(h2[q]); }
 }
+// Round 2: packed f16 arithmetic.  The bf16 rows are converted to f16 pairs as they are loaded (exact: f16 has more mantissa
+// bits, and hidden activations are far inside its range; the conversion saturates), the nine taps accumulate with HFMA2 (11
+// mantissa bits through the sum -- less rounding than the bf16 store that follows), GELU as tc::gelu_h2 (defined with the fused
+// feed-forward kernel above): 15 instead of 41 instructions per element.
+__device__ __forceinline__ uint32_t dw_bf2_to_h2(uint32_t v) {    // two bf16 -> two f16
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(v & 0xffff0000u)), "f"(__uint_as_float(v << 16)));
+    return r;
+}
 template <int CPT>
 __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP p) {
+    static_assert(CPT == 4, "one uint2 (four bf16 channels) per load");
     pdl_wait();
-    typedef typename DwVec<CPT>::T V;
     const int groups = p.Cp / CPT;
     const int segs = (p.H + p.seg - 1) / p.seg;
     const long long total = (long long)p.B * segs * p.W * groups;
@@ -1536,14 +1545,13 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
     const int sg = (int)(t % segs), b = (int)(t / segs);
     const int y0 = sg * p.seg, y1 = min(p.H, y0 + p.seg);
 
-    float w[9][CPT];
+    __half2 w[9][2];
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-        for (int c = 0; c < CPT; c += 4) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + CPT * g + c));
-            w[k][c] = w0.x; w[k][c + 1] = w0.y; w[k][c + 2] = w0.z; w[k][c + 3] = w0.w;
-        }
+    for (int k = 0; k < 9; ++k) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w + k * p.Cp + CPT * g));
+        w[k][0] = __floats2half2_rn(w0.x, w0.y);
+        w[k][1] = __floats2half2_rn(w0.z, w0.w);
+    }
     // running pointers: rin -> (row being loaded, column x), advanced by one row pitch per load_row
     const long long in_pitch = (long long)p.W * p.ldi, out_pitch = (long long)p.W * p.ldo;
     const bf16 *rin = p.in + (((long long)b * p.H + (y0 - 1)) * p.W + x) * p.ldi + CPT * g;
@@ -1551,51 +1559,47 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
     const int ldi = p.ldi;
     const bool has_l = x > 0, has_r = x + 1 < p.W;
     int y_next = y0 - 1;                                              // row rin points at
-    auto load_row = [&](V (&raw)[3]) {
-        raw[0] = raw[1] = raw[2] = V{};                               // conv zero padding
+    auto load_row = [&](uint2 (&raw)[3]) {
+        raw[0] = raw[1] = raw[2] = make_uint2(0u, 0u);                // conv zero padding
         if ((unsigned)y_next < (unsigned)p.H) {
-            if (has_l) raw[0] = __ldg(reinterpret_cast<const V *>(rin - ldi));
-            raw[1] = __ldg(reinterpret_cast<const V *>(rin));
-            if (has_r) raw[2] = __ldg(reinterpret_cast<const V *>(rin + ldi));
+            if (has_l) raw[0] = __ldg(reinterpret_cast<const uint2 *>(rin - ldi));
+            raw[1] = __ldg(reinterpret_cast<const uint2 *>(rin));
+            if (has_r) raw[2] = __ldg(reinterpret_cast<const uint2 *>(rin + ldi));
         }
         rin += in_pitch;
         ++y_next;
     };
-    float win[3][3][CPT];             // [row slot][dx][channel]
-    V raw[3];
-    load_row(raw);
+    auto unpack = [&](const uint2 (&raw)[3], uint32_t (&dst)[3][2]) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[0][d]);
+        for (int d = 0; d < 3; ++d) { dst[d][0] = dw_bf2_to_h2(raw[d].x); dst[d][1] = dw_bf2_to_h2(raw[d].y); }
+    };
+    uint32_t win[3][3][2];            // [row slot][dx][channel pair] as f16x2
+    uint2 raw[3];
     load_row(raw);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[1][d]);
+    unpack(raw, win[0]);
+    load_row(raw);
+    unpack(raw, win[1]);
     load_row(raw);
     for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
         for (int ph = 0; ph < 3; ++ph) {           // static rotation of the three row slots
             const int y = yb + ph;
             if (y < y1) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) dw_unpack<CPT>(raw[d], win[(ph + 2) % 3][d]);      // row y + 1
+                unpack(raw, win[(ph + 2) % 3]);    // row y + 1
                 if (y + 1 < y1) load_row(raw);
-                float acc[CPT];
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
+                __half2 a0, a1;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) acc[c] = fmaf(win[(ph + ky) % 3][kx][c], w[ky * 3 + kx][c], acc[c]);
-                if (p.gelu_out) {
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) acc[c] = gelu(acc[c]);
-                }
-                uint32_t o[CPT / 2];
-#pragma unroll
-                for (int q = 0; q < CPT / 2; ++q) o[q] = pack_bf16(acc[2 * q], acc[2 * q + 1]);
-                if (CPT == 8) *reinterpret_cast<uint4 *>(rout) = make_uint4(o[0], o[1], o[CPT / 2 - 2], o[CPT / 2 - 1]);
-                else *reinterpret_cast<uint2 *>(rout) = make_uint2(o[0], o[1]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const __half2 v0 = *reinterpret_cast<const __half2 *>(&win[(ph + ky) % 3][kx][0]);
+                        const __half2 v1 = *reinterpret_cast<const __half2 *>(&win[(ph + ky) % 3][kx][1]);
+                        if (ky == 0 && kx == 0) { a0 = __hmul2(v0, w[0][0]); a1 = __hmul2(v1, w[0][1]); }
+                        else { a0 = __hfma2(v0, w[ky * 3 + kx][0], a0); a1 = __hfma2(v1, w[ky * 3 + kx][1], a1); }
+                    }
+                if (p.gelu_out) { a0 = tc::gelu_h2(a0); a1 = tc::gelu_h2(a1); }
+                const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+                *reinterpret_cast<uint2 *>(rout) = make_uint2(pack_bf16(f0.x, f0.y), pack_bf16(f1.x, f1.y));
                 rout += out_pitch;
             }
         }
@@ -1607,8 +1611,7 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const __grid_constant__ DwP
 // of 32 channels, stages v with a 2-pixel halo in shared memory, evaluates the first conv + GELU on the
 // tile plus a 1-pixel halo (rounded to bf16 exactly where the two-kernel pipeline stored it; zero outside
 // the map -- that is the second conv's padding) and the second conv from there.  The intermediate map
-// never goes to HBM and one launch per attention block disappears; the arithmetic order is unchanged, so
-// the result is bit-identical to the two-kernel form.
+// never goes to HBM and one launch per attention block disappears.
 struct DwPosP {
     const bf16 *in; int ldi;
     bf16 *out; int ldo;
@@ -1617,55 +1620,61 @@ struct DwPosP {
 };
 constexpr int DP_TX = 16, DP_TY = 8, DP_CB = 32;
 constexpr int DP_IW = DP_TX + 4, DP_IH = DP_TY + 4, DP_MW = DP_TX + 2, DP_MH = DP_TY + 2;
-constexpr int DP_SMEM = (DP_IH * DP_IW + DP_MH * DP_MW) * DP_CB * 2 + 2 * 9 * DP_CB * 4;
-// one tile by a CTA of NT threads (NT a multiple of 8); smem: DP_SMEM bytes, 16-byte aligned
+constexpr int DP_SMEM = (DP_IH * DP_IW + DP_MH * DP_MW) * DP_CB * 2 + 2 * 9 * DP_CB * 2;
+// One tile by a CTA of NT threads (NT a multiple of 8); smem: DP_SMEM bytes, 16-byte aligned.  Round 2: the tile is
+// converted to f16 when it is staged and both convolutions run as packed HFMA2 (a nine-term f16 sum carries 11 mantissa
+// bits, more than the bf16 the intermediate map used to be rounded to), GELU as gelu_h2: a third of the instructions of
+// the fp32 form (which unpacked every bf16 operand on the ALU pipe).
+__device__ __forceinline__ uint32_t h2_to_bf2(__half2 h) {
+    const float2 f = __half22float2(h);
+    return pack_bf16(f.x, f.y);
+}
 template <int NT>
 __device__ __forceinline__ void dwpos_tile(const DwPosP &p, int bx, int by, int bz, uint8_t *smem) {
     constexpr int IW = DP_IW, IH = DP_IH, MW = DP_MW, MH = DP_MH;
-    bf16 (*sin)[DP_CB] = reinterpret_cast<bf16 (*)[DP_CB]>(smem);
-    bf16 (*smid)[DP_CB] = reinterpret_cast<bf16 (*)[DP_CB]>(smem + IH * IW * DP_CB * 2);
-    float (*sw)[9][DP_CB] = reinterpret_cast<float (*)[9][DP_CB]>(smem + (IH * IW + MH * MW) * DP_CB * 2);
+    __half (*sin)[DP_CB] = reinterpret_cast<__half (*)[DP_CB]>(smem);
+    __half (*smid)[DP_CB] = reinterpret_cast<__half (*)[DP_CB]>(smem + IH * IW * DP_CB * 2);
+    __half (*sw)[9][DP_CB] = reinterpret_cast<__half (*)[9][DP_CB]>(smem + (IH * IW + MH * MW) * DP_CB * 2);
     const int tid = threadIdx.x;
     const int cblocks = p.Cp / DP_CB;
     const int b = bz / cblocks, c0 = (bz - b * cblocks) * DP_CB;
     const int x0 = bx * DP_TX, y0 = by * DP_TY;
     for (int i = tid; i < 2 * 9 * DP_CB; i += NT) {
         const int which = i / (9 * DP_CB), r = i - which * 9 * DP_CB, t = r / DP_CB, c = r - t * DP_CB;
-        sw[which][t][c] = __ldg((which ? p.w2 : p.w1) + t * p.Cp + c0 + c);
+        sw[which][t][c] = __float2half_rn(__ldg((which ? p.w2 : p.w1) + t * p.Cp + c0 + c));
     }
     // stage v: (IH x IW) pixels x 32 channels = 4 x 16-byte vectors per pixel, zeros outside the map
     for (int i = tid; i < IH * IW * 4; i += NT) {
         const int px = i >> 2, q = i & 3;
         const int yy = y0 - 2 + px / IW, xx = x0 - 2 + px % IW;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W)
+        if ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W) {
             v = __ldg(reinterpret_cast<const uint4 *>(p.in + (((long long)b * p.H + yy) * p.W + xx) * p.ldi + c0) + q);
+            v = make_uint4(dw_bf2_to_h2(v.x), dw_bf2_to_h2(v.y), dw_bf2_to_h2(v.z), dw_bf2_to_h2(v.w));
+        }
         reinterpret_cast<uint4 *>(&sin[px][0])[q] = v;
     }
     __syncthreads();
-    // a thread keeps its channel group g = tid & 7 through both loops: the nine weight vectors of the running conv live in
-    // registers instead of being re-read from shared memory for every pixel (18 LDS.128 per output less)
+    // a thread keeps its channel group g = tid & 7 through both loops: the nine tap vectors of the running conv live in
+    // registers (as half2 pairs) instead of being re-read from shared memory for every pixel
     const int g_fixed = tid & 7;
-    float4 wr[9];
+    __half2 wr[9][2];
     auto load_weights = [&](int which) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float4 *>(&sw[which][t][4 * g_fixed]);
+        for (int t = 0; t < 9; ++t) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(&sw[which][t][4 * g_fixed]);
+            wr[t][0] = *reinterpret_cast<const __half2 *>(&w.x);
+            wr[t][1] = *reinterpret_cast<const __half2 *>(&w.y);
+        }
     };
-    auto conv_at = [&](const bf16 (*src)[DP_CB], int pitch, int px_centre, int g, int /*which*/, float (&acc)[4]) {
+    auto conv_at = [&](const __half (*src)[DP_CB], int pitch, int px_centre, int g, __half2 &a0, __half2 &a1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c] = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const uint2 raw = *reinterpret_cast<const uint2 *>(&src[px_centre + (ky - 1) * pitch + (kx - 1)][4 * g]);
-                const float4 w = wr[ky * 3 + kx];
-                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-                acc[0] = fmaf(__low2float(h2[0]), w.x, acc[0]);
-                acc[1] = fmaf(__high2float(h2[0]), w.y, acc[1]);
-                acc[2] = fmaf(__low2float(h2[1]), w.z, acc[2]);
-                acc[3] = fmaf(__high2float(h2[1]), w.w, acc[3]);
-            }
+        for (int t = 0; t < 9; ++t) {
+            const uint2 raw = *reinterpret_cast<const uint2 *>(&src[px_centre + (t / 3 - 1) * pitch + (t % 3 - 1)][4 * g]);
+            const __half2 v0 = *reinterpret_cast<const __half2 *>(&raw.x), v1 = *reinterpret_cast<const __half2 *>(&raw.y);
+            if (t == 0) { a0 = __hmul2(v0, wr[0][0]); a1 = __hmul2(v1, wr[0][1]); }
+            else { a0 = __hfma2(v0, wr[t][0], a0); a1 = __hfma2(v1, wr[t][1], a1); }
+        }
     };
     // first conv + GELU on the tile and its 1-pixel halo
     load_weights(0);
@@ -1675,9 +1684,11 @@ __device__ __forceinline__ void dwpos_tile(const DwPosP &p, int bx, int by, int 
         const int yy = y0 - 1 + my, xx = x0 - 1 + mx;
         uint2 o = make_uint2(0u, 0u);
         if ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W) {
-            float acc[4];
-            conv_at(sin, IW, (my + 1) * IW + (mx + 1), g, 0, acc);
-            o = make_uint2(pack_bf16(gelu(acc[0]), gelu(acc[1])), pack_bf16(gelu(acc[2]), gelu(acc[3])));
+            __half2 a0, a1;
+            conv_at(sin, IW, (my + 1) * IW + (mx + 1), g, a0, a1);
+            a0 = tc::gelu_h2(a0);
+            a1 = tc::gelu_h2(a1);
+            o = make_uint2(*reinterpret_cast<const uint32_t *>(&a0), *reinterpret_cast<const uint32_t *>(&a1));
         }
         *reinterpret_cast<uint2 *>(&smid[px][4 * g]) = o;
     }
@@ -1689,10 +1700,9 @@ __device__ __forceinline__ void dwpos_tile(const DwPosP &p, int bx, int by, int 
         const int ty = px / DP_TX, tx = px - ty * DP_TX;
         const int yy = y0 + ty, xx = x0 + tx;
         if (yy < p.H && xx < p.W) {
-            float acc[4];
-            conv_at(smid, MW, (ty + 1) * MW + (tx + 1), g, 1, acc);
-            *reinterpret_cast<uint2 *>(p.out + (((long long)b * p.H + yy) * p.W + xx) * p.ldo + c0 + 4 * g) =
-                make_uint2(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]));
+            __half2 a0, a1;
+            conv_at(smid, MW, (ty + 1) * MW + (tx + 1), g, a0, a1);
+            *reinterpret_cast<uint2 *>(p.out + (((long long)b * p.H + yy) * p.W + xx) * p.ldo + c0 + 4 * g) = make_uint2(h2_to_bf2(a0), h2_to_bf2(a1));
         }
     }
 }
@@ -2024,9 +2034,14 @@ union AttnSideSmem {
     AttnStatSmem st;
     uint8_t dp[DP_SMEM];
 };
-__device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int h, float (*attn)[32], float *rq) {
+// wsm: the head's 31 columns of Wproj, [c][32] floats (staged here with coalesced loads while the softmax rows are computed)
+__device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int h, float (*attn)[32], float *rq, float (*wsm)[32]) {
     const int tid = threadIdx.x;
     const long long *S = p.stats + ((long long)b * p.heads + h) * 1024;
+    for (int e = tid; e < p.c * 32; e += 128) {
+        const int co = e >> 5, i = e & 31;
+        wsm[co][i] = i < NF ? __ldg(p.wproj + (long long)co * p.c + h * NF + i) : 0.f;
+    }
     if (tid < 32) rq[tid] = tid < NF ? 1.0f / fmaxf(sqrtf((float)((double)__ldcg(S + 31 * 32 + tid) * (1.0 / STAT_SCALE))), 1e-12f) : 0.f;
     __syncthreads();
     if (tid < NF) {          // softmax row i = tid (same arithmetic, same order as attn_finalize_kernel)
@@ -2052,9 +2067,9 @@ __device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int
         if (j < NF) {
             float v = 0.f;
             if (co < p.c) {
-                const float *wrow = p.wproj + (long long)co * p.c + h * NF;
+                const float *wrow = wsm[co];
 #pragma unroll
-                for (int i = 0; i < NF; ++i) v = fmaf(__ldg(wrow + i), attn[i][j], v);
+                for (int i = 0; i < NF; ++i) v = fmaf(wrow[i], attn[i][j], v);
             }
             M[(long long)co * p.Cp + h * NF + j] = __float2bfloat16_rn(v);
         } else if (h == p.heads - 1) {
@@ -2062,7 +2077,10 @@ __device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int
         }
     }
 }
-__global__ void __launch_bounds__(128) attn_side_kernel(const __grid_constant__ AttnSideP p) {
+#ifndef AVB_SIDE_MINB
+#define AVB_SIDE_MINB 4      // resident CTAs per SM the register allocation aims at
+#endif
+__global__ void __launch_bounds__(128, AVB_SIDE_MINB) attn_side_kernel(const __grid_constant__ AttnSideP p) {
     pdl_wait();
     __shared__ __align__(16) AttnSideSmem sm;
     __shared__ int is_last;
@@ -2082,7 +2100,9 @@ __global__ void __launch_bounds__(128) attn_side_kernel(const __grid_constant__ 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    attn_finalize_head(p.fin, b, head, reinterpret_cast<float (*)[32]>(&sm.st.Gs[0][0]), &sm.st.Ds[0][0]);
+    static_assert(sizeof(sm.st.qs) + sizeof(sm.st.ks) >= 124 * 32 * sizeof(float), "Wproj column block fits the staging buffers");
+    attn_finalize_head(p.fin, b, head, reinterpret_cast<float (*)[32]>(&sm.st.Gs[0][0]), &sm.st.Ds[0][0],
+                       reinterpret_cast<float (*)[32]>(&sm.st.qs[0][0][0]));
 }
 
 // ------------------------------------------------------------------------------------ band projection
