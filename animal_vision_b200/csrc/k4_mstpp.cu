@@ -2038,9 +2038,18 @@ union AttnSideSmem {
 __device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int h, float (*attn)[32], float *rq, float (*wsm)[32]) {
     const int tid = threadIdx.x;
     const long long *S = p.stats + ((long long)b * p.heads + h) * 1024;
-    for (int e = tid; e < p.c * 32; e += 128) {
-        const int co = e >> 5, i = e & 31;
-        wsm[co][i] = i < NF ? __ldg(p.wproj + (long long)co * p.c + h * NF + i) : 0.f;
+    for (int e0 = tid; e0 < p.c * 32; e0 += 128 * 8) {          // eight loads in flight per thread: this CTA runs alone, latency is all there is
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + 128 * u, co = e >> 5, i = e & 31;
+            v[u] = (e < p.c * 32 && i < NF) ? __ldg(p.wproj + (long long)co * p.c + h * NF + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + 128 * u;
+            if (e < p.c * 32) wsm[e >> 5][e & 31] = v[u];
+        }
     }
     if (tid < 32) rq[tid] = tid < NF ? 1.0f / fmaxf(sqrtf((float)((double)__ldcg(S + 31 * 32 + tid) * (1.0 / STAT_SCALE))), 1e-12f) : 0.f;
     __syncthreads();
