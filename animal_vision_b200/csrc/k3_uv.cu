@@ -93,6 +93,7 @@ struct UvParams {
     float mix_alpha;             // MAP_MIXED
     float *dbg_catches;          // optional [n][H][W][3] raw catches (test hook), else nullptr
     int aligned_in, aligned_out; // rows / frames 4-byte aligned -> 32-bit pixel-group accesses
+    int no_plane_map;            // AVB_UV_NO_PLANE_MAP=1: always take the second walk (A/B measurements)
     int strips_x, strips_y;
 };
 
@@ -304,6 +305,38 @@ __device__ __forceinline__ float sqrt_sfu(float x) {
 #endif
 }
 
+// atan2 without branches: octant reduction + the degree-17 odd minimax polynomial of Abramowitz &
+// Stegun 4.4.49 (|error| <= 2e-8 in exact arithmetic, 1.1e-7 evaluated in float32).  The hue only
+// needs ~1e-6: an error e in the angle moves the output colour by <= e in linear light, i.e.
+// < 1e-3 LSB after the encode.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float r = 0.0028662257f;
+    r = fmaf(r, s, -0.0161657367f);
+    r = fmaf(r, s, 0.0429096138f);
+    r = fmaf(r, s, -0.0752896400f);
+    r = fmaf(r, s, 0.1065626393f);
+    r = fmaf(r, s, -0.1420889944f);
+    r = fmaf(r, s, 0.1999355085f);
+    r = fmaf(r, s, -0.3333314528f);
+    r = fmaf(r * s, a, a);
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return y < 0.f ? -r : r;
+}
+
+// hue of the opponent mapper (uv_mappers.py:57-60): (atan2(O2, O1) + pi) / 2 pi, float32 constants as NumPy rounds them
+template <bool PRECISE>
+__device__ __forceinline__ float opp_hue(const float (&c)[3]) {
+    const float O1 = c[2] - c[1], O2 = c[1] - c[0];
+    const float PI_F = 3.14159274101257324f;          // float32(np.pi)
+    const float ang = PRECISE ? atan2f(O2, O1) : atan2_fast(O2, O1);
+    return div_by(__fadd_rn(ang, PI_F), 6.28318548202514648f, 0.159154936671257019f);
+}
+
 // ------------------------------------------------------------------ mapper quantities
 // PRECISE (the float32 plane route, whose float outputs are compared at 1e-5): IEEE sqrt / libm atan2 instead of
 // the SFU forms that are ample for uint8 outputs.
@@ -457,6 +490,12 @@ __global__ void uv_prep_kernel(const __grid_constant__ UvParams p) {
     for (int h = 0; h < UV_NH; ++h) st.inv_w[h] = (float)UV_BINS / fmaxf(hb[h], 1e-30f);
 }
 
+// The opponent mapper's map pass reads the planes of the hist pass when a lane's four pixels are one aligned float4 per
+// plane and one aligned 12-byte group of the output (any other geometry takes the second walk, uv_map_kernel).
+__host__ __device__ __forceinline__ bool map_from_planes(const UvParams &p) {
+    return p.mapper == MAP_OPPONENT && p.n_req > 0 && (p.io.W & 3) == 0 && p.aligned_out != 0 && !p.no_plane_map;
+}
+
 // ------------------------------------------------------------------ hist
 template <int QS>
 struct HistOp {
@@ -466,12 +505,17 @@ struct HistOp {
     float inv_w[UV_NH];
     int W;
     bool vec;                    // W % 4 == 0: a lane's 4 pixels are one aligned float4 per plane
+    bool hue_plane;              // opponent mapper: plane 2 = hue (the map pass will read the planes)
     __device__ __forceinline__ void operator()(int y, int gx, const float (&v)[4][3], bool ok) {
         if (!ok || gx >= W) return;
+        // planes written: the histogrammed quantities, and for the opponent mapper its hue as well -- the map pass then
+        // is a plain element-wise kernel on (radius, L, hue) instead of a second walk (decode, adaptation, blur, atan2)
+        constexpr int NPL = QS == QS_OPP ? 3 : QCount<QS>::value;
         float q[4][UV_NH];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             quantities<QS>(v[j], q[j]);
+            if (QS == QS_OPP && hue_plane) q[j][2] = opp_hue<false>(v[j]);
             if (gx + j < W) {
 #pragma unroll
                 for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[j][h], inv_w[h])], 1u);
@@ -479,7 +523,8 @@ struct HistOp {
         }
         const long long o = (long long)y * W + gx;
 #pragma unroll
-        for (int h = 0; h < QCount<QS>::value; ++h) {
+        for (int h = 0; h < NPL; ++h) {
+            if (h >= QCount<QS>::value && !hue_plane) break;
             float *d = planes + h * npx + o;
             if (vec) {
                 *reinterpret_cast<float4 *>(d) = make_float4(q[0][h], q[1][h], q[2][h], q[3][h]);
@@ -508,6 +553,7 @@ __global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_hist_kernel(const __gr
     op.npx = (long long)p.io.H * p.io.W;
     op.planes = p.planes + (long long)frame * UV_NH * op.npx;
     op.vec = (p.io.W & 3) == 0;
+    op.hue_plane = map_from_planes(p);
 #pragma unroll
     for (int h = 0; h < UV_NH; ++h) op.inv_w[h] = st.inv_w[h];
     op.W = p.io.W;
@@ -734,78 +780,32 @@ __device__ __forceinline__ void purple_soft(float U, const MapConsts &k, float (
     }
 }
 
-// atan2 without branches: octant reduction + the degree-17 odd minimax polynomial of Abramowitz &
-// Stegun 4.4.49 (|error| <= 2e-8 in exact arithmetic, 1.1e-7 evaluated in float32).  The hue only
-// needs ~1e-6: an error e in the angle moves the output colour by <= e in linear light, i.e.
-// < 1e-3 LSB after the encode.
-__device__ __forceinline__ float atan2_fast(float y, float x) {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
-    const float s = a * a;
-    float r = 0.0028662257f;
-    r = fmaf(r, s, -0.0161657367f);
-    r = fmaf(r, s, 0.0429096138f);
-    r = fmaf(r, s, -0.0752896400f);
-    r = fmaf(r, s, 0.1065626393f);
-    r = fmaf(r, s, -0.1420889944f);
-    r = fmaf(r, s, 0.1999355085f);
-    r = fmaf(r, s, -0.3333314528f);
-    r = fmaf(r * s, a, a);
-    r = ay > ax ? 1.57079632679489662f - r : r;
-    r = x < 0.f ? 3.14159265358979324f - r : r;
-    return y < 0.f ? -r : r;
+// hsv_to_rgb (uv_mappers.py:14-26) of hue, sat = clip(radius / (P99 + eps)), val = clip(L / (P99 + eps)).
+// Channel c = val * (1 - sat * m_c), m_c = clamp(min(k, 4 - k), 0, 1), k = (n_c + 6 hue) mod 6, n = (5, 3, 1): m is exactly
+// 0, 1, f or 1 - f in every sextant, so these are the p / q / t products of the reference's np.select without a branch
+// (NumPy evaluates q and t in float64 and rounds once; one fused multiply-add keeps the float32 evaluation within an ulp of
+// that).  Measured, 20 4K frames: 1.178 ms against 1.240 ms for a divergent switch over the sextant.
+__device__ __forceinline__ void opp_color(float radius, float L, float hue, const MapConsts &k, float (&rgb)[3]) {
+    const float sat = __saturatef(div_by(radius, k.pr, k.rpr));
+    const float val = __saturatef(div_by(L, k.pL, k.rpL));
+    const float h6 = __fmul_rn(hue, 6.0f);
+    const float hh = h6 >= 6.0f ? h6 - 6.0f : h6;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float kk = hh + (float)(5 - 2 * c);
+        kk = kk >= 6.0f ? kk - 6.0f : kk;
+        const float m = __saturatef(fminf(kk, 4.0f - kk));
+        rgb[c] = __fmul_rn(val, fmaf(-m, sat, 1.0f));
+    }
 }
 
 template <int MAPPER, bool PRECISE = false>
 __device__ __forceinline__ void map_pixel(const float (&c)[3], const MapConsts &k, float (&rgb)[3]) {
     if (MAPPER == MAP_OPPONENT) {
         // uv_mappers.py:53-64 and hsv_to_rgb :14-26
-        const float U = c[0], B = c[1], G = c[2];
-        const float O1 = G - B, O2 = B - U;
-        const float L = div_by(__fadd_rn(__fadd_rn(U, B), G), 3.0f, 0.333333343267440796f);
-        const float r2 = __fadd_rn(__fmul_rn(O1, O1), __fmul_rn(O2, O2));
-        const float radius = PRECISE ? __fsqrt_rn(r2) : sqrt_sfu(r2);
-        const float PI_F = 3.14159274101257324f;          // float32(np.pi)
-        const float ang = PRECISE ? atan2f(O2, O1) : atan2_fast(O2, O1);
-        const float hue = div_by(__fadd_rn(ang, PI_F), 6.28318548202514648f, 0.159154936671257019f);
-        const float sat = __saturatef(div_by(radius, k.pr, k.rpr));
-        const float val = __saturatef(div_by(L, k.pL, k.rpL));
-        const float h6 = __fmul_rn(hue, 6.0f);
-        const float fl = floorf(h6);
-        const float f = h6 - fl;                           // exact
-        int sext = (int)fl;                                // hue in [0,1] -> fl in {0..6}; 6 wraps to 0 (i % 6)
-        sext = sext >= 6 ? sext - 6 : (sext < 0 ? 0 : sext);
-        // NumPy evaluates q and t in float64 (f = h*6 - int32 promotes) and rounds once; one fused
-        // multiply-add keeps the float32 evaluation within an ulp of that
-        const float pp = __fmul_rn(val, __fsub_rn(1.0f, sat));
-        const float qq = __fmul_rn(val, fmaf(-f, sat, 1.0f));
-        const float tt = __fmul_rn(val, fmaf(-(1.0f - f), sat, 1.0f));
-#ifndef UV_HSV_SWITCH
-        // channel c = val * (1 - sat * m_c), m_c = clamp(min(k, 4 - k), 0, 1), k = (n_c + h6) mod 6, n = (5, 3, 1): m is exactly
-        // 0, 1, f or 1 - f in every sextant, so these are the very pp / qq / tt products above without a branch
-        // (measured, 20 4K frames: 1.178 ms against 1.240 ms for the divergent switch below; -DUV_HSV_SWITCH restores it)
-        (void)pp; (void)qq; (void)tt; (void)sext;
-        const float hh = h6 >= 6.0f ? h6 - 6.0f : h6;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float kk = hh + (float)(5 - 2 * c);
-            kk = kk >= 6.0f ? kk - 6.0f : kk;
-            const float m = __saturatef(fminf(kk, 4.0f - kk));
-            rgb[c] = __fmul_rn(val, fmaf(-m, sat, 1.0f));
-        }
-#else
-        // np.select over the sextant (uv_mappers.py:23-25); measured: the divergent switch beats
-        // predicated selects here (1.37 vs 1.62 ms per 20 4K frames)
-        switch (sext) {
-            case 0: rgb[0] = val; rgb[1] = tt; rgb[2] = pp; break;
-            case 1: rgb[0] = qq; rgb[1] = val; rgb[2] = pp; break;
-            case 2: rgb[0] = pp; rgb[1] = val; rgb[2] = tt; break;
-            case 3: rgb[0] = pp; rgb[1] = qq; rgb[2] = val; break;
-            case 4: rgb[0] = tt; rgb[1] = pp; rgb[2] = val; break;
-            default: rgb[0] = val; rgb[1] = pp; rgb[2] = qq; break;
-        }
-#endif
+        float q[UV_NH];
+        quantities<QS_OPP, PRECISE>(c, q);
+        opp_color(q[0], q[1], opp_hue<PRECISE>(c), k, rgb);
     } else if (MAPPER == MAP_FALSECOLOR) {
         falsecolor(c, k, rgb);
     } else if (MAPPER == MAP_MATRIX) {
@@ -900,6 +900,60 @@ __global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_map_kernel(const __gri
     }
 }
 
+
+// ------------------------------------------------------------------ opponent map from the hist pass's planes
+// (radius, L, hue) -> hsv_to_rgb -> sRGB encode: element-wise, four pixels per thread (one float4 per plane in, three
+// 32-bit words out).  Same functions, same operands as the walk (the planes hold exactly the values the walk recomputes),
+// so the bytes are identical; what disappears is the second decode + adaptation + blur + atan2 per pixel
+// (215 -> ~60 instructions per pixel) at the price of 12 instead of 3 bytes read per pixel -- the path is issue bound.
+constexpr int MP_THREADS = 256, MP_GROUPS = 4;       // groups of four pixels per thread
+__global__ void __launch_bounds__(MP_THREADS) uv_map_opp_planes_kernel(const __grid_constant__ UvParams p) {
+    __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    copy_to_smem(enc_s, p.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.enc + 2)));
+    __syncthreads();
+    const EncTable enc = enc_view(enc_s);
+    const UvFrameStats &st = p.stats[frame];
+    MapConsts k;
+    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
+    k.pL = st.pct[1] + p.eps;
+    k.rpr = __frcp_rn(k.pr);
+    k.rpL = __frcp_rn(k.pL);
+    const int W = p.io.W, W4 = W >> 2;
+    const long long npx = (long long)p.io.H * W, groups = npx >> 2;
+    const float *pl = p.planes + (long long)frame * UV_NH * npx;
+    uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs;
+    const long long g0 = ((long long)blockIdx.x * MP_GROUPS) * MP_THREADS + tid;
+    float4 qr[MP_GROUPS], qL[MP_GROUPS], qh[MP_GROUPS];
+#pragma unroll
+    for (int u = 0; u < MP_GROUPS; ++u) {            // all loads first: twelve 16-byte requests in flight per thread
+        const long long g = g0 + (long long)u * MP_THREADS;
+        if (g < groups) {
+            qr[u] = __ldcs(reinterpret_cast<const float4 *>(pl) + g);
+            qL[u] = __ldcs(reinterpret_cast<const float4 *>(pl + npx) + g);
+            qh[u] = __ldcs(reinterpret_cast<const float4 *>(pl + 2 * npx) + g);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < MP_GROUPS; ++u) {
+        const long long g = g0 + (long long)u * MP_THREADS;
+        if (g >= groups) break;
+        const int y = (int)(g / W4), x4 = (int)(g - (long long)y * W4);
+        const float r4[4] = {qr[u].x, qr[u].y, qr[u].z, qr[u].w}, L4[4] = {qL[u].x, qL[u].y, qL[u].z, qL[u].w};
+        const float h4[4] = {qh[u].x, qh[u].y, qh[u].z, qh[u].w};
+        uint32_t by[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float rgb[3];
+            opp_color(r4[j], L4[j], h4[j], k, rgb);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) by[3 * j + i] = encode_u8(enc, rgb[i]);
+        }
+        uint32_t *o32 = reinterpret_cast<uint32_t *>(dst + (int64_t)y * p.io.out_rs + 12 * x4);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
+    }
+}
 
 // ------------------------------------------------------------------ float32 plane path
 // The generality route (float / wide-integer frames, hsi_downsample, blur radii beyond the fused walker):
@@ -1122,7 +1176,11 @@ static int launch_mapper(const UvParams &p, cudaStream_t st) {
     }
     if (p.n_req > 0)
         if (int e = launch_percentiles<QS, R, BANDS>(p, st)) return e;
-    {
+    if (MAPPER == MAP_OPPONENT && map_from_planes(p)) {
+        AVB_TIMED("k3_uv_map", st);
+        const long long groups = ((long long)p.io.H * p.io.W) >> 2, per_cta = (long long)MP_THREADS * MP_GROUPS;
+        uv_map_opp_planes_kernel<<<dim3((unsigned)((groups + per_cta - 1) / per_cta), p.io.n), MP_THREADS, 0, st>>>(p);
+    } else {
         AVB_TIMED("k3_uv_map", st);
         // one task per warp (measured: a persistent grid, 4-5 tasks per warp, is 15 % slower here)
         const int tasks = p.strips_x * p.strips_y;
@@ -1211,6 +1269,10 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
     p.dbg_catches = dbg_catches_dev;
     p.aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_frame_stride | (uintptr_t)in_row_stride) & 3) == 0;
     p.aligned_out = ((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_frame_stride | (uintptr_t)out_row_stride) & 3) == 0;
+    {
+        static const bool off = [] { const char *e = std::getenv("AVB_UV_NO_PLANE_MAP"); return e && e[0] == '1'; }();
+        p.no_plane_map = off ? 1 : 0;
+    }
     const int SW = R ? 120 : 128;
     p.strips_x = (W + SW - 1) / SW;
     p.strips_y = (H + UV_RH - 1) / UV_RH;
