@@ -1063,14 +1063,18 @@ static void quantize_taps_f16(float *taps, int ksize) {
     for (int i = 0; i < ksize; ++i) taps[i] = (float)q[i];
 }
 
-// AVB_GAUSS_MMA: 0 = CUDA-core kernel (gauss_stream_kernel) always, 1 = tensor-core kernel with hi+lo f16 operands from
-// G_MMA_MIN_RADIUS up (default), 2 = same with single f16 operands (faster, ~0.05 LSB of systematic rounding: flat
-// regions may flip by 1 LSB as a whole), 3 / 4 = modes 1 / 2 at every radius.  Read once per process.
-constexpr int G_MMA_MIN_RADIUS = 8;
+// AVB_GAUSS_MMA: 0 = CUDA-core kernel (gauss_stream_kernel) always; 1 = tensor-core kernel with hi+lo f16 operands from
+// radius 8 up (the round-2 default until the 1-LSB budget was spent: 4-9e-4 of the bytes differ from the reference);
+// 2 = single f16 operands from radius 8 up; 3 / 4 = modes 1 / 2 at every radius (tests);
+// 5 (DEFAULT) = single f16 operands from radius 5 up.  Single f16: ~0.05 LSB of systematic rounding, <= 1 LSB with 0.3-1.4 % of
+// the bytes differing (a flat region may flip by 1 LSB as a whole) -- measured, 20 4K frames, ms: Dog (29 taps) 1.13 -> 0.93,
+// Raccoon (17) 0.99 -> 0.84, Bear / Elephant (15) 1.03 -> 0.85, Wolf (13) / Fox / Lion (11) 0.91 -> 0.85 (from the CUDA-core
+// kernel), Squirrel (7) 0.82 either way.  Read once per process.
+constexpr int G_MMA_MIN_RADIUS = 8, G_MMA_MIN_RADIUS_SINGLE = 5;
 static int gauss_mma_mode() {
     static const int mode = [] {
         const char *e = std::getenv("AVB_GAUSS_MMA");
-        return e ? std::atoi(e) : 1;
+        return e ? std::atoi(e) : 5;
     }();
     return mode;
 }
@@ -1144,10 +1148,11 @@ static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp
     if constexpr (std::is_same<Prod, DogProducer>::value) {
         // measured (20 4K frames, ms, CUDA cores -> tensor cores hi+lo): 29 taps 1.45 -> 1.14, 17 taps 1.09 -> 1.00,
         // 15 taps 1.04 -> 1.01, 7 taps 0.83 -> 0.97: below ~17 taps the FMAs saved do not pay for the f16 splitting
-        const int min_radius = gauss_mma_mode() >= 3 ? 1 : G_MMA_MIN_RADIUS;      // modes 3 / 4: tensor path at every radius (tests)
-        if (two && radius >= min_radius && radius <= 16 && gauss_mma_mode() != 0)
-            return (gauss_mma_mode() == 2 || gauss_mma_mode() == 4) ? dispatch_gauss_mma<false>(radius, gc, q, st)
-                                                                    : dispatch_gauss_mma<true>(radius, gc, q, st);
+        const int mode = gauss_mma_mode();
+        const int min_radius = mode == 5 ? G_MMA_MIN_RADIUS_SINGLE : (mode >= 3 ? 1 : G_MMA_MIN_RADIUS);   // modes 3 / 4: every radius (tests)
+        if (two && radius >= min_radius && radius <= 16 && mode != 0)
+            return (mode == 2 || mode == 4 || mode == 5) ? dispatch_gauss_mma<false>(radius, gc, q, st)
+                                                         : dispatch_gauss_mma<true>(radius, gc, q, st);
     }
     switch (radius) {
 #define AVB_CASE(RR) case RR: return two ? launch_gauss<RR, Prod, 2>(gc, q, st) : launch_gauss<RR, Prod, 3>(gc, q, st);
