@@ -919,26 +919,33 @@ __global__ void __launch_bounds__(MP_THREADS) uv_map_opp_planes_kernel(const __g
     k.pL = st.pct[1] + p.eps;
     k.rpr = __frcp_rn(k.pr);
     k.rpL = __frcp_rn(k.pL);
-    const int W = p.io.W, W4 = W >> 2;
-    const long long npx = (long long)p.io.H * W, groups = npx >> 2;
+    const int W = p.io.W;
+    const uint32_t W4 = (uint32_t)W >> 2;
+    const long long npx = (long long)p.io.H * W;
+    const uint32_t groups = (uint32_t)(npx >> 2);    // < 2^31: a frame of 2^33 pixels does not exist
     const float *pl = p.planes + (long long)frame * UV_NH * npx;
     uint8_t *dst = p.io.out + (int64_t)frame * p.io.out_fs;
-    const long long g0 = ((long long)blockIdx.x * MP_GROUPS) * MP_THREADS + tid;
+    const uint32_t g0 = (blockIdx.x * MP_GROUPS) * MP_THREADS + tid;
     float4 qr[MP_GROUPS], qL[MP_GROUPS], qh[MP_GROUPS];
 #pragma unroll
     for (int u = 0; u < MP_GROUPS; ++u) {            // all loads first: twelve 16-byte requests in flight per thread
-        const long long g = g0 + (long long)u * MP_THREADS;
+        const uint32_t g = g0 + (uint32_t)u * MP_THREADS;
         if (g < groups) {
             qr[u] = __ldcs(reinterpret_cast<const float4 *>(pl) + g);
             qL[u] = __ldcs(reinterpret_cast<const float4 *>(pl + npx) + g);
             qh[u] = __ldcs(reinterpret_cast<const float4 *>(pl + 2 * npx) + g);
         }
     }
+    // (row, group in the row) of the first group by one 32-bit division, of the following ones by stepping
+    uint32_t y = g0 / W4, x4 = g0 - y * W4;
 #pragma unroll
     for (int u = 0; u < MP_GROUPS; ++u) {
-        const long long g = g0 + (long long)u * MP_THREADS;
+        const uint32_t g = g0 + (uint32_t)u * MP_THREADS;
         if (g >= groups) break;
-        const int y = (int)(g / W4), x4 = (int)(g - (long long)y * W4);
+        if (u > 0) {
+            x4 += MP_THREADS;
+            while (x4 >= W4) { x4 -= W4; ++y; }
+        }
         const float r4[4] = {qr[u].x, qr[u].y, qr[u].z, qr[u].w}, L4[4] = {qL[u].x, qL[u].y, qL[u].z, qL[u].w};
         const float h4[4] = {qh[u].x, qh[u].y, qh[u].z, qh[u].w};
         uint32_t by[12];
@@ -949,7 +956,7 @@ __global__ void __launch_bounds__(MP_THREADS) uv_map_opp_planes_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 3; ++i) by[3 * j + i] = encode_u8(enc, rgb[i]);
         }
-        uint32_t *o32 = reinterpret_cast<uint32_t *>(dst + (int64_t)y * p.io.out_rs + 12 * x4);
+        uint32_t *o32 = reinterpret_cast<uint32_t *>(dst + (int64_t)y * p.io.out_rs + 12u * x4);
 #pragma unroll
         for (int q = 0; q < 3; ++q) o32[q] = by[4 * q] | (by[4 * q + 1] << 8) | (by[4 * q + 2] << 16) | (by[4 * q + 3] << 24);
     }

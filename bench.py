@@ -471,7 +471,7 @@ def run_mstpp_leg(args, dev, rank, world, max_over_ranks, barrier):
             "patches_per_s": nb * world / (ms * 1e-3), "ms_per_forward": ms, "batch_per_gpu": nb, "concurrent_forwards": parts,
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "unit": "TFLOP/s", "frac": tf / world / peak,
                          "peak_source": src, "algorithmic_flop_per_patch": MSTPP_FLOP_PER_PATCH,
-                         "note": "whole forward (146 dependent launches chained with programmatic dependent launch), not one kernel; at C=31 the network is bound by per-kernel latency and HBM, not by the tensor pipe (SURVEY.md section 7)"}}
+                         "note": "whole forward (104 dependent launches chained with programmatic dependent launch), not one kernel; at C=31 the network is bound by per-kernel latency and HBM, not by the tensor pipe (SURVEY.md section 7)"}}
 
 
 # ----------------------------------------------------------------------------- GPU arm
