@@ -362,6 +362,7 @@ __device__ __forceinline__ int bin_of(float v, float inv_w) {
 
 // ------------------------------------------------------------------ stats: maxima / sums of raw catches
 template <bool BANDS>
+// (no occupancy target: measured 0.265 ms as compiled, 0.284 / 0.321 / 0.355 / 0.393 ms with 4 / 5 / 6 / 8 CTAs per SM requested)
 __global__ void __launch_bounds__(256) uv_stats_kernel(const __grid_constant__ UvParams p) {
     __shared__ float lut_s[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __ldg(p.lut + i);
