@@ -1074,23 +1074,12 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[N]) {
     for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// GELU for the fused kernel's two hidden-map stages (256 evaluations per pixel: the SFU is their bound):
-//   x Phi(x) = x/2 (1 + tanh(x (a1 + a3 x^2 + a5 x^4))),  minimax fit of the odd polynomial: |error| < 2.6e-5 absolute
-// before the 2^-11 relative error of tanh.approx -- one SFU operation and six FMA-pipe instructions (the erfc form above
-// takes two SFU operations and twelve), an order of magnitude inside the bf16 rounding of the maps it produces.
-__device__ __forceinline__ float gelu_tanh(float x) {
-    const float x2 = x * x;
-    float q = fmaf(x2, -0.0003515167885330909f, 0.03700564602227854f);
-    q = fmaf(q, x2, 0.7975078842854375f);
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(q * x));
-    const float hx = 0.5f * x;
-    return fmaf(hx, th, hx);
-}
-
-// The same in packed f16 (both hidden-map stages of the fused kernel keep f16 maps): cubic argument polynomial
-// (|error| < 2.7e-4 before tanh.approx, monotonic for every x, so overflowing inputs saturate to x / 0 instead of
-// turning over), 9 instructions per PAIR of values including the two SFU operations.
+// GELU of the packed-f16 stages (both hidden-map stages of the fused feed-forward kernel, the positional embedding, the
+// coarse-level depthwise conv; the fused kernel alone evaluates 256 per pixel and the SFU is their bound):
+//   x Phi(x) = x/2 (1 + tanh(x (a1 + a3 x^2))),  minimax fit of the cubic argument polynomial: |error| < 2.7e-4 absolute before the
+// 2^-11 relative error of tanh.approx, an order of magnitude inside the bf16 rounding of the maps it produces; monotonic for every
+// x, so overflowing inputs saturate to x / 0 instead of turning over (a quintic fit is ten times closer but bends back beyond
+// |x| = 11); 9 instructions per PAIR of values including the two SFU operations (the erfc form of gelu() takes 14 per value).
 __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
     const __half2 a1 = __float2half2_rn(0.8001570785f), a3 = __float2half2_rn(0.0347008934f), hf = __float2half2_rn(0.5f);
     const __half2 t = __hmul2(__hfma2(__hmul2(x, x), a3, a1), x);
