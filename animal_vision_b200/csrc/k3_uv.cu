@@ -513,14 +513,24 @@ struct HistOp {
         // is a plain element-wise kernel on (radius, L, hue) instead of a second walk (decode, adaptation, blur, atan2)
         constexpr int NPL = QS == QS_OPP ? 3 : QCount<QS>::value;
         float q[4][UV_NH];
+        const bool full = gx + 3 < W;             // every lane but the one on the frame's right edge: no per-pixel bound checks
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             quantities<QS>(v[j], q[j]);
             if (QS == QS_OPP && hue_plane) q[j][2] = opp_hue<false>(v[j]);
-            if (gx + j < W) {
+        }
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[j][h], inv_w[h])], 1u);
-            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (gx + j < W) {
+#pragma unroll
+                    for (int h = 0; h < QCount<QS>::value; ++h) atomicAdd(&hs[h * UV_BINS + bin_of(q[j][h], inv_w[h])], 1u);
+                }
         }
         const long long o = (long long)y * W + gx;
 #pragma unroll
