@@ -1262,6 +1262,7 @@ extern "C" int avb_uv_map_u8(const uint8_t *in, uint8_t *out, int n, int H, int 
     AVB_REQUIRE(n <= 65535, "batch too large for one launch");
     AVB_REQUIRE(in_row_stride >= 3LL * W && out_row_stride >= 3LL * W, "row stride smaller than 3*W");
     AVB_REQUIRE(dec_dev && enc_dev && m3_host && workspace_dev, "null table / workspace pointer");
+    AVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 15) == 0, "workspace_dev must be 16-byte aligned (float4 plane accesses)");
     AVB_REQUIRE(n_bands >= 0 && n_bands <= UV_MAX_BANDS && (n_bands == 0 || bands_dev), "bad band table");
     AVB_REQUIRE(adapt_mode >= 0 && adapt_mode <= 2, "adapt_mode must be 0 (none), 1 (white patch) or 2 (gray world)");
     AVB_REQUIRE(blur_ksize == 0 || ((blur_ksize == 3 || blur_ksize == 5) && blur_taps_host), "blur ksize must be 0, 3 or 5");
@@ -1370,6 +1371,7 @@ extern "C" int avb_uv_map_f32(const float *ubg_dev, void *out, int out_is_f32, i
                               int map_mode, const float *map_params_host, float mix_alpha,
                               void *workspace_dev, avb_stream_t stream) {
     AVB_REQUIRE(ubg_dev && out && workspace_dev, "null pointer");
+    AVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 15) == 0, "workspace_dev must be 16-byte aligned");
     AVB_REQUIRE(n > 0 && n <= 65535 && H > 0 && W > 0 && (long long)H * W < (1LL << 31), "bad frame geometry");
     AVB_REQUIRE(out_is_f32 || (enc_dev && out_row_stride >= 3LL * W), "uint8 output needs the encode table and a row stride >= 3*W");
     AVB_REQUIRE(map_mode >= 0 && map_mode <= MAP_MIXED, "unknown map_mode");

@@ -162,7 +162,7 @@ AVB_API int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_cat, 
  *                  AVB_MAP_MATRIX, [9:12] / [12:15] linear-light purple / warm anchors of the
  *                  purple-yellow map (uv_mappers.py:107-116, evaluated by the host in NumPy)
  *   mix_alpha      blend weight of AVB_MAP_MIXED (honeybee.py:161 passes 0.45)
- *   workspace_dev  avb_uv_workspace_bytes(n, H, W, map_mode) bytes of scratch
+ *   workspace_dev  avb_uv_workspace_bytes(n, H, W, map_mode) bytes of scratch, 16-byte aligned
  *   dbg_catches_dev NULL, or n*H*W*3 float32: raw receptor catches (test hook for the 1e-5 check) */
 #define AVB_MAP_OPPONENT 0
 #define AVB_MAP_FALSECOLOR 1
