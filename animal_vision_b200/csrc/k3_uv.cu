@@ -491,10 +491,11 @@ __global__ void uv_prep_kernel(const __grid_constant__ UvParams p) {
     for (int h = 0; h < UV_NH; ++h) st.inv_w[h] = (float)UV_BINS / fmaxf(hb[h], 1e-30f);
 }
 
-// The opponent mapper's map pass reads the planes of the hist pass when a lane's four pixels are one aligned float4 per
-// plane and one aligned 12-byte group of the output (any other geometry takes the second walk, uv_map_kernel).
+// The map pass of every mapper with percentiles reads the planes of the hist pass -- (radius, L, hue) for the opponent mapper,
+// the adapted, blurred catches themselves for the others -- when a lane's four pixels are one aligned float4 per plane and
+// one aligned 12-byte group of the output (any other geometry, and the matrix mapper, take the second walk, uv_map_kernel).
 __host__ __device__ __forceinline__ bool map_from_planes(const UvParams &p) {
-    return p.mapper == MAP_OPPONENT && p.n_req > 0 && (p.io.W & 3) == 0 && p.aligned_out != 0 && !p.no_plane_map;
+    return p.n_req > 0 && (p.io.W & 3) == 0 && p.aligned_out != 0 && !p.no_plane_map;
 }
 
 // ------------------------------------------------------------------ hist
@@ -912,8 +913,27 @@ __global__ void __launch_bounds__(UV_THREADS, UV_MINB) uv_map_kernel(const __gri
 }
 
 
-// ------------------------------------------------------------------ opponent map from the hist pass's planes
-// (radius, L, hue) -> hsv_to_rgb -> sRGB encode: element-wise, four pixels per thread (one float4 per plane in, three
+__device__ __forceinline__ void fill_map_consts(const UvParams &p, const UvFrameStats &st, int mapper, MapConsts &k) {
+    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
+    k.pL = st.pct[1] + p.eps;
+    k.rpr = __frcp_rn(k.pr);
+    k.rpL = __frcp_rn(k.pL);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { k.d95[i] = fmaxf(st.pct[i], p.eps); k.r95[i] = __frcp_rn(k.d95[i]); }
+    k.d98 = fmaxf(mapper == MAP_PURPLE ? st.pct[0] : st.pct[3], p.eps);
+    k.r98 = __frcp_rn(k.d98);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        k.c0[i] = p.anchors[i];
+        k.c1[i] = p.anchors[3 + i];
+        k.pd[i] = __fsub_rn(k.c0[i], 0.5f);
+        k.m[3 * i] = p.map_m[3 * i]; k.m[3 * i + 1] = p.map_m[3 * i + 1]; k.m[3 * i + 2] = p.map_m[3 * i + 2];
+    }
+    k.alpha = p.mix_alpha;
+}
+
+// ------------------------------------------------------------------ map pass on the hist pass's planes
+// Opponent mapper: (radius, L, hue) -> hsv_to_rgb -> sRGB encode; the other mappers: (U, B, G) -> map_pixel -> encode: element-wise, four pixels per thread (one float4 per plane in, three
 // 32-bit words out).  Same functions, same operands as the walk (the planes hold exactly the values the walk recomputes),
 // so the bytes are identical; what disappears is the second decode + adaptation + blur + atan2 per pixel
 // (215 -> ~60 instructions per pixel) at the price of 12 instead of 3 bytes read per pixel -- the path is issue bound.
@@ -921,7 +941,9 @@ constexpr int MP_THREADS = 256, MP_GROUPS = 4;       // groups of four pixels pe
 #ifndef MP_MINB
 #define MP_MINB 4        // measured: 3 -> 0.578 ms, 4 -> 0.554 ms per 20 4K frames
 #endif
-__global__ void __launch_bounds__(MP_THREADS, MP_MINB) uv_map_opp_planes_kernel(const __grid_constant__ UvParams p) {
+template <int MAPPER>
+__global__ void __launch_bounds__(MP_THREADS, MP_MINB) uv_map_planes_kernel(const __grid_constant__ UvParams p) {
+    constexpr int NPL = MAPPER == MAP_PURPLE ? 1 : 3;       // planes the hist pass wrote for this mapper
     __shared__ uint32_t enc_s[AVB_ENC_TABLE_MAX];
     const int tid = threadIdx.x, frame = blockIdx.y;
     copy_to_smem(enc_s, p.enc, min((int)AVB_ENC_TABLE_MAX, ENC_HEADER + (int)__ldg(p.enc + 2)));
@@ -929,10 +951,7 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) uv_map_opp_planes_kernel(
     const EncTable enc = enc_view(enc_s);
     const UvFrameStats &st = p.stats[frame];
     MapConsts k;
-    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
-    k.pL = st.pct[1] + p.eps;
-    k.rpr = __frcp_rn(k.pr);
-    k.rpL = __frcp_rn(k.pL);
+    fill_map_consts(p, st, MAPPER, k);
     const int W = p.io.W;
     const uint32_t W4 = (uint32_t)W >> 2;
     const long long npx = (long long)p.io.H * W;
@@ -946,8 +965,12 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) uv_map_opp_planes_kernel(
         const uint32_t g = g0 + (uint32_t)u * MP_THREADS;
         if (g < groups) {
             qr[u] = __ldcs(reinterpret_cast<const float4 *>(pl) + g);
-            qL[u] = __ldcs(reinterpret_cast<const float4 *>(pl + npx) + g);
-            qh[u] = __ldcs(reinterpret_cast<const float4 *>(pl + 2 * npx) + g);
+            if (NPL > 1) {
+                qL[u] = __ldcs(reinterpret_cast<const float4 *>(pl + npx) + g);
+                qh[u] = __ldcs(reinterpret_cast<const float4 *>(pl + 2 * npx) + g);
+            } else {
+                qL[u] = qh[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
     // (row, group in the row) of the first group by one 32-bit division, of the following ones by stepping
@@ -966,7 +989,12 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) uv_map_opp_planes_kernel(
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float rgb[3];
-            opp_color(r4[j], L4[j], h4[j], k, rgb);
+            if (MAPPER == MAP_OPPONENT) {
+                opp_color(r4[j], L4[j], h4[j], k, rgb);
+            } else {
+                const float c[3] = {r4[j], L4[j], h4[j]};          // the catches (U, B, G); the purple map reads U only
+                map_pixel<MAPPER>(c, k, rgb);
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) by[3 * j + i] = encode_u8(enc, rgb[i]);
         }
@@ -1054,25 +1082,6 @@ __global__ void __launch_bounds__(256) uv_hist_f32_kernel(const __grid_constant_
     uint32_t *gh = p.uv.hist + (int64_t)frame * UV_NH * UV_BINS;
     for (int i = tid; i < QCount<QS>::value * UV_BINS; i += 256)
         if (hs[i]) atomicAdd(gh + i, hs[i]);
-}
-
-__device__ __forceinline__ void fill_map_consts(const UvParams &p, const UvFrameStats &st, int mapper, MapConsts &k) {
-    k.pr = st.pct[0] + p.eps;               // uv_mappers.py:61-62: percentile + eps, float32
-    k.pL = st.pct[1] + p.eps;
-    k.rpr = __frcp_rn(k.pr);
-    k.rpL = __frcp_rn(k.pL);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { k.d95[i] = fmaxf(st.pct[i], p.eps); k.r95[i] = __frcp_rn(k.d95[i]); }
-    k.d98 = fmaxf(mapper == MAP_PURPLE ? st.pct[0] : st.pct[3], p.eps);
-    k.r98 = __frcp_rn(k.d98);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        k.c0[i] = p.anchors[i];
-        k.c1[i] = p.anchors[3 + i];
-        k.pd[i] = __fsub_rn(k.c0[i], 0.5f);
-        k.m[3 * i] = p.map_m[3 * i]; k.m[3 * i + 1] = p.map_m[3 * i + 1]; k.m[3 * i + 2] = p.map_m[3 * i + 2];
-    }
-    k.alpha = p.mix_alpha;
 }
 
 template <int MAPPER>
@@ -1197,10 +1206,10 @@ static int launch_mapper(const UvParams &p, cudaStream_t st) {
     }
     if (p.n_req > 0)
         if (int e = launch_percentiles<QS, R, BANDS>(p, st)) return e;
-    if (MAPPER == MAP_OPPONENT && map_from_planes(p)) {
+    if (MAPPER != MAP_MATRIX && map_from_planes(p)) {
         AVB_TIMED("k3_uv_map", st);
         const long long groups = ((long long)p.io.H * p.io.W) >> 2, per_cta = (long long)MP_THREADS * MP_GROUPS;
-        uv_map_opp_planes_kernel<<<dim3((unsigned)((groups + per_cta - 1) / per_cta), p.io.n), MP_THREADS, 0, st>>>(p);
+        uv_map_planes_kernel<MAPPER><<<dim3((unsigned)((groups + per_cta - 1) / per_cta), p.io.n), MP_THREADS, 0, st>>>(p);
     } else {
         AVB_TIMED("k3_uv_map", st);
         // one task per warp (measured: a persistent grid, 4-5 tasks per warp, is 15 % slower here)

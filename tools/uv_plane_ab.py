@@ -12,7 +12,8 @@ digests = []
 for shape in ((3, 270, 480), (2, 1080, 1920), (1, 123, 236), (20, 2160, 3840)):
     fr = torch.randint(0, 256, (*shape, 3), dtype=torch.uint8, generator=g).cuda()
     fr[0, : shape[1] // 2] //= 3
-    for kw in ({}, {"adaptation": "gray_world"}, {"blur_sigma_px": None}, {"blur_sigma_px": 0.6}):
+    for kw in ({}, {"adaptation": "gray_world"}, {"blur_sigma_px": None}, {"blur_sigma_px": 0.6}, {"mapping_mode": "falsecolor"},
+               {"mapping_mode": "uv_purple_yellow"}, {"mapping_mode": "falsecolor_uv_mixed"}):
         try:
             sp = A.HoneyBee(**kw)
         except TypeError:
@@ -21,15 +22,16 @@ for shape in ((3, 270, 480), (2, 1080, 1920), (1, 123, 236), (20, 2160, 3840)):
         out = out[-1] if isinstance(out, (tuple, list)) else out
         digests.append(hashlib.sha1(out.cpu().numpy().tobytes()).hexdigest()[:12])
 print("route", "walk" if os.environ.get("AVB_UV_NO_PLANE_MAP") == "1" else "planes", "digests", " ".join(digests))
-sp = A.HoneyBee()
-for _ in range(3): sp.visualize_batch(fr)
-torch.cuda.synchronize()
-lib.avb_profile_begin()
-for _ in range(3): sp.visualize_batch(fr)
-names = C.create_string_buffer(256 * 48); ms = (C.c_float * 256)()
-n = lib.avb_profile_end(names, 48, ms, 256)
-agg = {}
-for i in range(n):
-    nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
-    agg[nm] = agg.get(nm, 0.0) + ms[i] / 3
-print({k: round(v, 3) for k, v in agg.items() if v > 0.02}, "total", round(sum(agg.values()), 3))
+for mode in ("opponent", "falsecolor", "uv_purple_yellow", "falsecolor_uv_mixed"):
+    sp = A.HoneyBee(mapping_mode=mode)
+    for _ in range(3): sp.visualize_batch(fr)
+    torch.cuda.synchronize()
+    lib.avb_profile_begin()
+    for _ in range(3): sp.visualize_batch(fr)
+    names = C.create_string_buffer(256 * 48); ms = (C.c_float * 256)()
+    n = lib.avb_profile_end(names, 48, ms, 256)
+    agg = {}
+    for i in range(n):
+        nm = names.raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode()
+        agg[nm] = agg.get(nm, 0.0) + ms[i] / 3
+    print(mode, {k: round(v, 3) for k, v in agg.items() if v > 0.02}, "total", round(sum(agg.values()), 3))
