@@ -1146,7 +1146,10 @@ static int dispatch_gauss_mma(int radius, GaussCommon gc, const DogProducer::Par
 
 template <class Prod>
 static int dispatch_gauss(int radius, GaussCommon &gc, typename Prod::Params &pp, cudaStream_t st) {
-    gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius, radius <= G_MINB3_R ? 3 : G_MINB);
+#ifndef G_CAT_SEG_SLOTS
+#define G_CAT_SEG_SLOTS 3
+#endif
+    gc.seg_h = pick_seg_h(gc.io.n, gc.io.H, gc.io.W, radius, (Prod::GATHER && radius <= G_MINB4_R) ? G_CAT_SEG_SLOTS : (radius <= G_MINB3_R ? 3 : G_MINB));
     float Q[6];
     const float T[9] = {pp.M.m[0], pp.M.m[1], pp.M.m[2], pp.M.m[3], pp.M.m[4], pp.M.m[5], pp.M.m[6], pp.M.m[7], pp.M.m[8]};
     const bool two = rank2_factor(T, Q, gc.P);

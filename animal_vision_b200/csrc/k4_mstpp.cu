@@ -2043,15 +2043,17 @@ __device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int
             if (e < p.c * 32) wsm[e >> 5][e & 31] = v[u];
         }
     }
-    if (tid < 32) rq[tid] = tid < NF ? 1.0f / fmaxf(sqrtf((float)((double)__ldcg(S + 31 * 32 + tid) * (1.0 / STAT_SCALE))), 1e-12f) : 0.f;
+    // fixed point -> float: int64 -> float rounds once and the scale is a power of two, the same bits as the detour through double
+    constexpr float INV_SCALE = (float)(1.0 / STAT_SCALE);
+    if (tid < 32) rq[tid] = tid < NF ? 1.0f / fmaxf(sqrtf((float)__ldcg(S + 31 * 32 + tid) * INV_SCALE), 1e-12f) : 0.f;
     __syncthreads();
     if (tid < NF) {          // softmax row i = tid (same arithmetic, same order as attn_finalize_kernel)
         const int i = tid;
-        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf((float)((double)__ldcg(S + i * 32 + 31) * (1.0 / STAT_SCALE))), 1e-12f);
+        const float sc = __ldg(p.rescale + h) / fmaxf(sqrtf((float)__ldcg(S + i * 32 + 31) * INV_SCALE), 1e-12f);
         float row[NF], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-            row[j] = (float)((double)__ldcg(S + i * 32 + j) * (1.0 / STAT_SCALE)) * (sc * rq[j]);
+            row[j] = ((float)__ldcg(S + i * 32 + j) * INV_SCALE) * (sc * rq[j]);
             mx = fmaxf(mx, row[j]);
         }
         float sum = 0.f;
@@ -2063,18 +2065,27 @@ __device__ __forceinline__ void attn_finalize_head(const AttnFinP &p, int b, int
     }
     __syncthreads();
     bf16 *M = p.M + (long long)b * p.Cp * p.Cp;
-    for (int e = tid; e < p.Cp * 32; e += 128) {
-        const int co = e >> 5, j = e & 31;
+    // element e = (row co = e / 32, column j = e % 32) of the head's block; a thread's elements e, e + 128, e + 256, e + 384 share
+    // their column and sit four rows apart: four independent accumulation chains (each in the fixed order i = 0 .. 30)
+    for (int e0 = tid; e0 < p.Cp * 32; e0 += 512) {
+        const int co0 = e0 >> 5, j = e0 & 31;
         if (j < NF) {
-            float v = 0.f;
-            if (co < p.c) {
-                const float *wrow = wsm[co];
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < NF; ++i) v = fmaf(wrow[i], attn[i][j], v);
+            for (int i = 0; i < NF; ++i) {
+                const float a = attn[i][j];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = fmaf(wsm[min(co0 + 4 * u, p.c - 1)][i], a, v[u]);
             }
-            M[(long long)co * p.Cp + h * NF + j] = __float2bfloat16_rn(v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int co = co0 + 4 * u;
+                M[(long long)co * p.Cp + h * NF + j] = __float2bfloat16_rn(co < p.c ? v[u] : 0.f);
+            }
         } else if (h == p.heads - 1) {
-            for (int k = p.c; k < p.Cp; ++k) M[(long long)co * p.Cp + k] = __float2bfloat16_rn(0.f);     // padded columns
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                for (int k = p.c; k < p.Cp; ++k) M[(long long)(co0 + 4 * u) * p.Cp + k] = __float2bfloat16_rn(0.f);     // padded columns
         }
     }
 }
