@@ -1704,6 +1704,67 @@ __global__ void __launch_bounds__(256) dwpos_fused_kernel(const __grid_constant_
     dwpos_tile<256>(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 
+// ------------------------------------------------------------------------------------ tiled depthwise 3x3 (coarse-level FFN)
+// The row-walking dwconv_kernel above fetches every input pixel three times (left / centre / right neighbour) through
+// L1 / L2 and is bound by that latency once its arithmetic is packed f16.  Here a CTA stages a 16 x 8 pixel tile of 32
+// channels with its 1-pixel halo in shared memory ONCE (converted to f16 on the way, all of a thread's loads in flight
+// together) and evaluates the conv + GELU from there: lane group = 4 channels with their nine taps in registers as half2.
+constexpr int DT_IW = DP_TX + 2, DT_IH = DP_TY + 2;
+__global__ void __launch_bounds__(256) dwconv_tile_kernel(const __grid_constant__ DwP p) {
+    pdl_wait();
+    __shared__ __align__(16) __half sin[DT_IH * DT_IW][DP_CB];
+    __shared__ __align__(16) __half sw[9][DP_CB];
+    const int tid = threadIdx.x;
+    const int cblocks = p.Cp / DP_CB;
+    const int b = blockIdx.z / cblocks, c0 = (blockIdx.z - b * cblocks) * DP_CB;
+    const int x0 = blockIdx.x * DP_TX, y0 = blockIdx.y * DP_TY;
+    for (int i = tid; i < 9 * DP_CB; i += 256) sw[i / DP_CB][i % DP_CB] = __float2half_rn(__ldg(p.w + (i / DP_CB) * p.Cp + c0 + i % DP_CB));
+    constexpr int NQ = DT_IH * DT_IW * 4, PER = (NQ + 255) / 256;      // 16-byte quads of the staged tile, per thread
+    uint4 v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid + 256 * u, px = i >> 2, q = i & 3;
+        const int yy = y0 - 1 + px / DT_IW, xx = x0 - 1 + px % DT_IW;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);                             // zeros outside the map: the conv's padding
+        if (i < NQ && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W)
+            v[u] = __ldg(reinterpret_cast<const uint4 *>(p.in + (((long long)b * p.H + yy) * p.W + xx) * p.ldi + c0) + q);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid + 256 * u;
+        if (i < NQ)
+            reinterpret_cast<uint4 *>(&sin[i >> 2][0])[i & 3] = make_uint4(dw_bf2_to_h2(v[u].x), dw_bf2_to_h2(v[u].y), dw_bf2_to_h2(v[u].z), dw_bf2_to_h2(v[u].w));
+    }
+    __syncthreads();
+    const int g = tid & 7;                                             // channel group: fixed per thread (stride 256 keeps it)
+    __half2 wr[9][2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(&sw[t][4 * g]);
+        wr[t][0] = *reinterpret_cast<const __half2 *>(&w.x);
+        wr[t][1] = *reinterpret_cast<const __half2 *>(&w.y);
+    }
+#pragma unroll
+    for (int i = tid; i < DP_TY * DP_TX * 8; i += 256) {
+        const int px = i >> 3;
+        const int ty = px / DP_TX, tx = px - ty * DP_TX;
+        const int yy = y0 + ty, xx = x0 + tx;
+        if (yy < p.H && xx < p.W) {
+            const int pc = (ty + 1) * DT_IW + (tx + 1);
+            __half2 a0, a1;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const uint2 raw = *reinterpret_cast<const uint2 *>(&sin[pc + (t / 3 - 1) * DT_IW + (t % 3 - 1)][4 * g]);
+                const __half2 v0 = *reinterpret_cast<const __half2 *>(&raw.x), v1 = *reinterpret_cast<const __half2 *>(&raw.y);
+                if (t == 0) { a0 = __hmul2(v0, wr[0][0]); a1 = __hmul2(v1, wr[0][1]); }
+                else { a0 = __hfma2(v0, wr[t][0], a0); a1 = __hfma2(v1, wr[t][1], a1); }
+            }
+            if (p.gelu_out) { a0 = tc::gelu_h2(a0); a1 = tc::gelu_h2(a1); }
+            *reinterpret_cast<uint2 *>(p.out + (((long long)b * p.H + yy) * p.W + xx) * p.ldo + c0 + 4 * g) = make_uint2(h2_to_bf2(a0), h2_to_bf2(a1));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ attention statistics
 // Per image and head: G[i][j] = sum_px k[px][i] q[px][j], nk[i] = sum k^2, nq[j] = sum q^2
 // (MST_Plus_Plus.py:127-129: the L2 normalisation runs over ALL pixels, so the reduction is global).
@@ -2629,6 +2690,11 @@ static void dwconv(Ctx &cx, const bf16 *in, int ldi, bf16 *out, int ldo, const f
     DwP p{in, ldi, out, ldo, w, cx.B, H, W, Cp, gelu_out, seg};
     const long long total = (long long)cx.B * ((H + seg - 1) / seg) * W * (Cp / DW_CPT);
     AVB_TIMED(name, cx.st);
+    static const bool walk = [] { const char *e = std::getenv("AVB_MSTPP_DW_WALK"); return e && e[0] == '1'; }();
+    if (!walk && Cp % DP_CB == 0 && (ldi & 7) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        launch_pdl(dwconv_tile_kernel, dim3((W + DP_TX - 1) / DP_TX, (H + DP_TY - 1) / DP_TY, cx.B * (Cp / DP_CB)), dim3(256), 0, cx.st, p);
+        return;
+    }
     launch_pdl(dwconv_kernel<DW_CPT>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, cx.st, p);
 }
 
