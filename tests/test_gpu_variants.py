@@ -81,6 +81,7 @@ def test_honeybee_plane_route_equals_the_second_walk():
     {"AVB_MSTPP_ATTN_UNMERGED": "1"},
     {"AVB_MSTPP_ATTN_UNMERGED": "1", "AVB_MSTPP_STATS_CUDA_CORES": "1", "AVB_MSTPP_FFN_UNFUSED": "1"},
     {"AVB_MSTPP_FFN_FUSED_MAXCP": "64"},
+    {"AVB_MSTPP_DW_WALK": "1"},
 ])
 def test_mstpp_schedules_agree(env, tmp_path):
     import numpy as np
