@@ -1147,11 +1147,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     const int y_begin = blockIdx.y * p.seg_rows, y_end = min(H, y_begin + p.seg_rows);
     const int h0 = y_begin - 1;
 
-    // ---- set-up that does not depend on the preceding kernel (overlaps its tail under programmatic dependent launch)
-    if (warp == FF_EPI_WARPS) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    // ---- set-up that does not depend on the preceding kernel (overlaps its tail under programmatic dependent launch): barriers,
+    // the weight copy, LayerNorm parameters.  NOT the TMEM allocation: a CTA that holds tensor memory while it waits for its
+    // predecessor can starve that predecessor's CTAs that are not resident yet (measured with the same idea in the GEMM kernels:
+    // TMEM + weights staged before griddepcontrol.wait made the forward 7 % slower, 3.00 -> 3.22 ms).
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -1171,6 +1170,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     // rows 126, 127 of the out-GEMM operand are never produced (their outputs are discarded): keep them finite
     for (int i = tid; i < (FF_HC / 8) * 2; i += FF_THREADS)
         *reinterpret_cast<uint4 *>(Aout + (i >> 1) * FF_ALBO + (126 + (i & 1)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    pdl_wait();
+    if (warp == FF_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -1179,7 +1183,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
 
     if (warp == FF_EPI_WARPS) {
         // ================================================================ MMA issuer (one lane; the warp stays converged)
-        pdl_wait();
         constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
         // in: A = B = bf16; out: A = B = f16 (the hidden map after the depthwise stage stays f16, W4 is stored as f16)
         constexpr uint32_t IDESC_IN = IDESC0 | ((uint32_t)(FF_HC >> 3) << 17);
@@ -1231,7 +1234,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
             wreg[t][0] = __floats2half2_rn(wv4.x, wv4.y);
             wreg[t][1] = __floats2half2_rn(wv4.z, wv4.w);
         }
-        pdl_wait();
         // x row loader: four threads per pixel, LayerNorm over the ln_c real channels in registers
         constexpr int CPT = CP / 4, NV = CPT / 4;              // 8 or 16 channels per thread = 2 or 4 float4
         const float ln_inv_c = 1.0f / (float)p.ln_c, ln_pad = (float)(CP - p.ln_c);
