@@ -48,3 +48,18 @@ def test_compute_fails_loudly_without_gpu():
     from animal_vision_b200.animals import Dog
     with pytest.raises(AvbError):
         Dog().visualize(np.zeros((4, 4, 3), np.uint8))
+
+
+def test_documented_runtime_switches_exist_in_the_sources():
+    """Every AVB_* environment switch INTEGRATION.md documents is read somewhere in csrc/ (and vice versa for getenv calls)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    section = doc[doc.index("## Run-time switches"):]
+    documented = set(re.findall(r"`(AVB_[A-Z0-9_]+)(?:=[^`]*)?`", section))
+    src = "".join(open(f).read() for f in glob.glob(os.path.join(root, "animal_vision_b200", "csrc", "*.cu")))
+    read = set(re.findall(r'getenv\("(AVB_[A-Z0-9_]+)"\)', src))
+    assert documented, "no switches parsed from INTEGRATION.md"
+    assert documented <= read, f"documented but never read: {sorted(documented - read)}"
+    assert read <= documented, f"read but undocumented: {sorted(read - documented)}"
