@@ -2737,7 +2737,10 @@ static void msab(Ctx &cx, const MsabW &m, float *x, int H, int W, Workspace &ws)
         // statistics (+ softmax / M by the last CTA of every head) and the positional embedding in one launch
         AttnSideP p{};
         p.st = AttnStatP{ws.qkv, ws.stats, rows, Cp, m.heads, 0};
-        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * 2 / std::max(1, m.heads)));     // geometry only: batch invariant
+#ifndef AVB_STATS_PER_SM
+#define AVB_STATS_PER_SM 2     // statistics CTAs per SM and head group (measured, forward: 1 -> 3.12 ms, 2 -> 2.98, 3 -> 2.97, 4 -> 3.00)
+#endif
+        int ctas = std::max(1, std::min((rows + 255) / 256, sm_count() * AVB_STATS_PER_SM / std::max(1, m.heads)));     // geometry only: batch invariant
         p.st.px_per_cta = ((rows + ctas - 1) / ctas + 127) / 128 * 128;
         ctas = (rows + p.st.px_per_cta - 1) / p.st.px_per_cta;
         p.fin = AttnFinP{ws.stats, m.rescale, m.wproj_f32, ws.M, m.c, Cp, m.heads};
