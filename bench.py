@@ -68,7 +68,8 @@ KERNEL_ALGO_BYTES_PER_PX = {"k2_gauss_dichromat": 6.0, "k2_gauss_cat_warp": 6.0,
 NCU_DRAM_TABLE = os.path.join(ROOT, "profiles", "ncu_dram_table.json")
 KERNEL_SPECIES = {"k2_gauss_dichromat": "Dog", "k2_gauss_cat_warp": "Cat", "cat_center_zoom": "Cat",
                   "k3_uv_stats": "HoneyBee", "k3_uv_map": "HoneyBee", "k3_uv_hist": "HoneyBee", "k3_uv_compact": "HoneyBee",
-                  "k3_uv_prep": "HoneyBee", "k3_uv_scan": "HoneyBee", "k3_uv_select": "HoneyBee", "k2_streak": "Dog"}
+                  "k3_uv_prep": "HoneyBee", "k3_uv_scan": "HoneyBee", "k3_uv_select": "HoneyBee", "k2_streak": "Dog",
+                  "frame_flags": "Cat", "k2_gauss_dichromat_fixup": "Dog", "k2_gauss_cat_warp_fixup": "Cat"}
 
 
 def bench_config():
@@ -612,11 +613,25 @@ def run_b200(args):
     traffic, traffic_src = ncu_traffic(dom, frames_per_launch, H, W)
     peak, peak_src = peak_numbers()
     achieved = algo_bytes / (shares[dom]["ms_per_launch"] * 1e-3) / 1e9
+    # the same figure for every kernel that has an algorithmic byte count, and per species path (all its kernels, uint8 in + out(s))
+    for nm, rec in shares.items():
+        if nm in KERNEL_ALGO_BYTES_PER_PX:
+            n_fr = dev_in[KERNEL_SPECIES.get(nm, "Dog")].shape[0]
+            gbs = KERNEL_ALGO_BYTES_PER_PX[nm] * n_fr * H * W / (rec["ms_per_launch"] * 1e-3) / 1e9
+            rec["algorithmic_gbs"] = gbs
+            rec["frac_of_hbm_peak"] = gbs / peak
+    paths = {}
+    for sp in SPECIES:
+        ms_sp = sum(rec["ms_per_launch"] * rec["launches_per_step"] for nm, rec in shares.items() if KERNEL_SPECIES.get(nm) == sp)
+        if ms_sp > 0:
+            gbs = ALGO_BYTES_PER_PX[sp] * dev_in[sp].shape[0] * H * W / (ms_sp * 1e-3) / 1e9
+            paths[sp] = {"kernel_ms_per_step": ms_sp, "algorithmic_bytes_per_px": ALGO_BYTES_PER_PX[sp], "algorithmic_gbs": gbs,
+                         "frac_of_hbm_peak": gbs / peak}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": f"{bpp:g} B/px x {frames_per_launch} frames x {W}x{H}; duration = mean CUDA-event time of this kernel over {prof_steps} step(s)",
-                "kernel_shares": shares}
+                "kernel_shares": shares, "species_paths": paths}
 
     # ---- end to end through the host API: pinned host in -> pinned host out
     pipe = HostBatchPipeline(dev, chunk_frames=args.chunk)
