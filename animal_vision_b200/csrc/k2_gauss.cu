@@ -1227,14 +1227,18 @@ extern "C" int avb_dichromat_blur_u8(const uint8_t *in, uint8_t *out, int n, int
 namespace avb {
 
 // per-frame "some byte >= 2" (the data-dependent branch of get_normalized_image) for kernels that
-// do not visit every input pixel themselves
-__global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *flags) {
+// do not visit every input pixel themselves.  One byte >= 2 anywhere PROVES the frame maximum is > 1, so the
+// question is settled for any ordinary frame by a sparse scan (every row_step-th row: pass 1, 1 / 64 of the
+// frame); only a frame without a witness in the sample (all bytes 0 / 1 there) gets the full scan of pass 2,
+// whose CTAs leave at once when the flag is already set.  Exact either way; 0.107 -> ~0.01 ms per 20 4K frames.
+__global__ void __launch_bounds__(256) frame_flags_kernel(FrameIO io, uint32_t *flags, int row_step, int skip_if_set) {
     const int frame = blockIdx.y;
+    if (skip_if_set && flags[frame] != 0) return;
     const uint8_t *src = io.in + (int64_t)frame * io.in_fs;
     const int row_bytes = 3 * io.W;
     uint32_t seen = 0;
     const bool vec = ((io.in_rs & 15) == 0) && ((io.in_fs & 15) == 0) && ((reinterpret_cast<uintptr_t>(io.in) & 15) == 0);
-    for (int y = blockIdx.x; y < io.H; y += gridDim.x) {
+    for (int y = blockIdx.x * row_step; y < io.H; y += gridDim.x * row_step) {
         const uint8_t *row = src + (int64_t)y * io.in_rs;
         int b = 0;
         if (vec) {
@@ -1388,9 +1392,11 @@ extern "C" int avb_cat_u8(const uint8_t *in, uint8_t *out_human, uint8_t *out_ca
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (norm_mode == AVB_NORM_AUTO && warp_dev) {
         AVB_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * n, st));
-        dim3 grid(H < 256 ? H : 256, n);
         AVB_TIMED("frame_flags", st);
-        frame_flags_kernel<<<grid, 256, 0, st>>>(gc.io, flags_dev);
+        constexpr int STEP = 64;
+        const int sampled = (H + STEP - 1) / STEP;
+        frame_flags_kernel<<<dim3(sampled < 256 ? sampled : 256, n), 256, 0, st>>>(gc.io, flags_dev, STEP, 0);      // witness search
+        frame_flags_kernel<<<dim3(H < 256 ? H : 256, n), 256, 0, st>>>(gc.io, flags_dev, 1, 1);                        // frames still undecided
         AVB_CUDA_OK(cudaGetLastError());
     }
     if (out_human) {

@@ -49,6 +49,26 @@ def test_cat_batch():
         _check(human[i].cpu().numpy(), cat[i].cpu().numpy(), ref_h, ref_c, f"batch[{i}]")
 
 
+@pytest.mark.parametrize("where", [(0, 0), (5, 17), (63, 100), (64, 3), (199, 299), (130, 0)])
+def test_cat_single_witness_byte_decides_the_normalisation(where):
+    """get_normalized_image divides by 255 iff the frame maximum exceeds 1 (animal_utils.py:41-50).  The flag pass looks
+    for a witness in every 64th row first and scans the whole frame only when the sample holds none: a frame of zeros and
+    ones with ONE byte of 2 -- in a sampled row, in an unsampled one, in the last row, in the blind strip's columns -- must
+    take the /255 branch, and the same frame without it the other branch."""
+    import torch
+    from animal_vision_b200.animals import Cat
+    f = frames.le1(200, 300).copy()
+    assert f.max() <= 1
+    g = f.copy()
+    g[where[0], where[1], 1] = 2
+    batch = torch.from_numpy(np.stack([f, g, f])).cuda()
+    human, cat = Cat().visualize_batch(batch)
+    for i, fr in enumerate((f, g, f)):
+        ref_h, ref_c = M.cat_visualize(fr)
+        _check(human[i].cpu().numpy(), cat[i].cpu().numpy(), ref_h, ref_c, f"witness {where} frame {i}")
+    assert not np.array_equal(cat[0].cpu().numpy(), cat[1].cpu().numpy()), "the two branches must differ on this frame"
+
+
 def test_cat_without_fov_warp(golden, golden_meta):
     """Class switch ENABLE_FOV_WARP = False (cat.py:21): centre zoom + L/M merge + blur, no warp."""
     from animal_vision_b200.animals import Cat
